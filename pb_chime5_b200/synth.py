@@ -1,0 +1,78 @@
+"""Seeded synthetic CHiME-5-shaped segments.
+
+STFT-domain mixture of K-1 point sources plus spatially white noise; frame
+activity per speaker from a two-state Markov chain; last class is the
+always-active 'Noise' garbage class (pb_chime5/activity.py:150-156).  The same
+complex64 values go to the GPU and (up-cast, bit-identical) to the oracle.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+
+def make_activity(rng, K, T, D, p_off=0.01, p_on=0.005, min_active=None):
+    """(K, T) bool; rows 0..K-2 speakers, row K-1 'Noise' (all True)."""
+    if min_active is None:
+        min_active = min(2 * D, T)
+    act = np.ones((K, T), dtype=bool)
+    for k in range(K - 1):
+        while True:
+            state = rng.random() < 0.5
+            u = rng.random(T)
+            row = np.empty(T, dtype=bool)
+            for t in range(T):
+                if state:
+                    state = not (u[t] < p_off)
+                else:
+                    state = u[t] < p_on
+                row[t] = state
+            if row.sum() >= min_active:
+                break
+        act[k] = row
+    return act
+
+
+def make_utterance(seed, D=24, T=941, F=513, K=5, noise_std=0.1,
+                   dtype=np.complex64):
+    """Returns Obs (D, T, F) complex64 and activity (K, T) bool."""
+    rng = np.random.default_rng(seed)
+    act = make_activity(rng, K, T, D)
+    S = K - 1
+
+    def cn(*shape):
+        return (rng.standard_normal(shape, dtype=np.float32)
+                + 1j * rng.standard_normal(shape, dtype=np.float32)) * np.float32(0.5 ** 0.5)
+
+    a = cn(F, S, D)
+    a /= np.linalg.norm(a, axis=-1, keepdims=True)
+    sigma = (0.5 + rng.random(S)).astype(np.float32)
+    s = cn(F, S, T) * sigma[None, :, None] * act[None, :S, :]
+    obs = np.einsum('fsd,fst->dtf', a, s) + np.float32(noise_std) * cn(D, T, F)
+    return np.ascontiguousarray(obs.astype(dtype)), act
+
+
+def make_batch(seed0, B, **kw):
+    obs, act = zip(*(make_utterance(seed0 + b, **kw) for b in range(B)))
+    return np.stack(obs), np.stack(act)
+
+
+def make_audio(seed, D=4, N=48000, K=3, stft_size=1024, stft_shift=256):
+    """Raw multichannel audio (D, N) float32 + per-class sample activity
+    (K, N) bool, for the STFT -> ... -> iSTFT end-to-end path."""
+    rng = np.random.default_rng(seed)
+    S = K - 1
+    act = np.ones((K, N), dtype=bool)
+    seg = max(N // 8, 1)
+    for k in range(S):
+        on = rng.random(8 + 1) < 0.6
+        on[k % 8] = True
+        act[k] = np.repeat(on, seg)[:N]
+    src = rng.standard_normal((S, N)).astype(np.float32) * act[:S]
+    # short random FIR per (source, mic) as a toy room
+    h = rng.standard_normal((S, D, 32)).astype(np.float32) * np.exp(-np.arange(32) / 6.0).astype(np.float32)
+    obs = np.zeros((D, N), dtype=np.float32)
+    for k in range(S):
+        for d in range(D):
+            obs[d] += np.convolve(src[k], h[k, d])[:N]
+    obs += 0.05 * rng.standard_normal((D, N)).astype(np.float32)
+    return obs, act
