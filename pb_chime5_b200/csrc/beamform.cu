@@ -1,0 +1,577 @@
+// Mask-based beamforming on the device.
+//   weighted_cov_kernel : get_power_spectral_density_matrix, beamformer.py:61-145
+//                         (also the covariance einsum of cACG._fit, cACG.py:293-300)
+//   bf_weights_kernel   : get_mvdr_vector_souden :546-617 (+ stable_solve,
+//                         math/solve.py:20-114) / get_gev_vector :267-348
+//                         (zhegvd, cythonized/get_gev_vector.pyx:42-150)
+//   bf_refchan_kernel   : get_optimal_reference_channel :524-543 (reduction over F)
+//   bf_apply_kernel     : blind_analytic_normalization :396-418 +
+//                         apply_beamforming_vector :502-510 + 'mask_mul' core.py:270-271
+// Observations are complex64, all arithmetic is float64.
+#include "common.cuh"
+#include "smallmat.cuh"
+
+#ifndef GSS_DP_LIST
+#define GSS_DP_LIST GSS_CASE(2) GSS_CASE(4) GSS_CASE(6) GSS_CASE(8) GSS_CASE(12) GSS_CASE(16) GSS_CASE(24)
+#endif
+
+namespace gss {
+
+// Source of the per-frame weights of the two (or K) classes.
+struct WeightSrc {
+    int mode;                  // 0: w (B,F,K,T) f32 ; 1: two masks (B,F,T) ; 2: posterior (B,F,K,T) + target/context
+    const float* w;            // mode 0 / 2
+    const float* m0;           // mode 1: target mask
+    const float* m1;           // mode 1: distortion mask
+    const int* target_index;   // mode 2 (B)
+    const int* start_ctx;      // mode 2 (B) frames, may be null
+    const int* end_ctx;        // mode 2 (B) frames, may be null
+    int K;                     // classes in w / posterior
+};
+
+// weights of class pair (c0, c0+1) for frame t of bin (b,f); mode 1/2 always give (target, distortion)
+__device__ __forceinline__ void frame_weights(const WeightSrc& s, int b, size_t bf, int T, int t, int c0,
+                                              double& w0, double& w1) {
+    if (s.mode == 0) {
+        const float* base = s.w + (bf * s.K) * T;
+        w0 = (double)base[(size_t)c0 * T + t];
+        w1 = (c0 + 1 < s.K) ? (double)base[(size_t)(c0 + 1) * T + t] : 0.0;
+    } else if (s.mode == 1) {
+        w0 = (double)s.m0[bf * T + t];
+        w1 = (double)s.m1[bf * T + t];
+    } else {
+        const int sc = s.start_ctx ? s.start_ctx[b] : 0;
+        const int ec = s.end_ctx ? s.end_ctx[b] : 0;
+        w0 = 0.0; w1 = 0.0;
+        if (t >= sc && t < T - ec) {            // masks[:, :sc] = 0 ; masks[:, -ec:] = 0 (core.py:545-547)
+            const float* base = s.w + (bf * s.K) * T;
+            const int ti = s.target_index[b];
+            for (int k = 0; k < s.K; ++k) {
+                const double v = (double)base[(size_t)k * T + t];
+                if (k == ti) w0 = v; else w1 += v;
+            }
+        }
+    }
+}
+
+// One CTA per (bin, class pair).  Phi (.., K, D, D) complex128 full Hermitian.
+template <int DP, int NT, int TM>
+__global__ void __launch_bounds__(NT) weighted_cov_kernel(const float2* __restrict__ Y, WeightSrc src,
+                                                          cd* __restrict__ Phi, double* __restrict__ wsum_out,
+                                                          int F, int D, int T, int Kout, int normalize) {
+    constexpr int NB = DP / 2, G = NB * (NB + 1) / 2, NG = NT / G, YLD = DP + 1;
+    static_assert(NG >= 1, "block too small");
+    __shared__ __align__(16) cd ysm[TM * YLD];
+    __shared__ double wsm[TM * 2];
+    __shared__ __align__(16) cd acc_sm[2 * DP * (DP + 1) / 2];
+    __shared__ double wred[2 * (NT / 32)];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const size_t bf = blockIdx.x;
+    const int b = (int)(bf / F);
+    const int c0 = blockIdx.y * 2;
+    const float2* __restrict__ Yg = Y + bf * D * T;
+    const int m_g = tid / G, m_l = tid - m_g * G;
+    const bool m_active = m_g < NG;
+    int bi = 0;
+    while ((bi + 1) * (bi + 2) / 2 <= m_l) ++bi;
+    const int bj = m_l - bi * (bi + 1) / 2;
+    const int r0 = 2 * bi, cc0 = 2 * bj;
+    cd macc[4][2];
+#pragma unroll
+    for (int a = 0; a < 4; ++a) { macc[a][0] = cmake(0.0, 0.0); macc[a][1] = cmake(0.0, 0.0); }
+    double ws0 = 0.0, ws1 = 0.0;
+    for (int t0 = 0; t0 < T; t0 += TM) {
+        for (int i = tid; i < DP * TM; i += NT) {
+            const int d = i / TM, t = i - d * TM;
+            float2 v = make_float2(0.f, 0.f);
+            if (d < D && t0 + t < T) v = __ldg(&Yg[(size_t)d * T + t0 + t]);
+            ysm[t * YLD + d] = cmake((double)v.x, (double)v.y);
+        }
+        for (int t = tid; t < TM; t += NT) {
+            double w0 = 0.0, w1 = 0.0;
+            if (t0 + t < T) frame_weights(src, b, bf, T, t0 + t, c0, w0, w1);
+            wsm[2 * t] = w0; wsm[2 * t + 1] = w1;
+            ws0 += w0; ws1 += w1;
+        }
+        __syncthreads();
+        if (m_active) {
+            const int tn = min(TM, T - t0);
+            for (int t = m_g; t < tn; t += NG) {
+                const cd* yrow = ysm + t * YLD;
+                const cd a0 = yrow[r0], a1 = yrow[r0 + 1], b0 = yrow[cc0], b1 = yrow[cc0 + 1];
+                cd P[4];
+                P[0] = cmulc(a0, b0); P[1] = cmulc(a0, b1);
+                P[2] = cmulc(a1, b0); P[3] = cmulc(a1, b1);
+                const double w0 = wsm[2 * t], w1 = wsm[2 * t + 1];
+#pragma unroll
+                for (int a = 0; a < 4; ++a) {
+                    macc[a][0].x = fma(w0, P[a].x, macc[a][0].x); macc[a][0].y = fma(w0, P[a].y, macc[a][0].y);
+                    macc[a][1].x = fma(w1, P[a].x, macc[a][1].x); macc[a][1].y = fma(w1, P[a].y, macc[a][1].y);
+                }
+            }
+        }
+        __syncthreads();
+    }
+    constexpr int NP = DP * (DP + 1) / 2;
+    for (int g = 0; g < NG; ++g) {
+        if (m_active && m_g == g) {
+#pragma unroll
+            for (int a = 0; a < 4; ++a) {
+                const int d = r0 + (a >> 1), e = cc0 + (a & 1);
+                if (e <= d) {
+#pragma unroll
+                    for (int k = 0; k < 2; ++k) {
+                        cd* dst = &acc_sm[k * NP + tri(d, e)];
+                        if (g == 0) *dst = macc[a][k];
+                        else { cd v = *dst; v.x += macc[a][k].x; v.y += macc[a][k].y; *dst = v; }
+                    }
+                }
+            }
+        }
+        __syncthreads();
+    }
+    ws0 = warp_sum(ws0); ws1 = warp_sum(ws1);
+    if (lane == 0) { wred[2 * warp] = ws0; wred[2 * warp + 1] = ws1; }
+    __syncthreads();
+    double tot[2] = {0.0, 0.0};
+    for (int w = 0; w < NT / 32; ++w) { tot[0] += wred[2 * w]; tot[1] += wred[2 * w + 1]; }
+    for (int k = 0; k < 2; ++k) {
+        if (c0 + k >= Kout) break;
+        const double sc = normalize ? 1.0 / fmax(tot[k], 1e-10) : 1.0;     // beamformer.py:124
+        cd* out = Phi + (bf * Kout + c0 + k) * D * D;
+        for (int i = tid; i < D * D; i += NT) {
+            const int r = i / D, c = i - r * D;
+            cd v;
+            if (r == c) v = cmake(acc_sm[k * NP + tri(r, r)].x, 0.0);
+            else if (r > c) v = acc_sm[k * NP + tri(r, c)];
+            else v = cconj(acc_sm[k * NP + tri(c, r)]);
+            out[i] = cscale(v, sc);
+        }
+        if (wsum_out && tid == 0) wsum_out[bf * Kout + c0 + k] = tot[k];
+    }
+}
+
+template <int DP>
+static int launch_weighted_cov(const float2* Y, const WeightSrc& src, cd* Phi, double* wsum,
+                               int B, int F, int D, int T, int Kout, int normalize, cudaStream_t st) {
+    constexpr int NT = 256, TM = 64;
+    dim3 grid(B * F, (Kout + 1) / 2);
+    weighted_cov_kernel<DP, NT, TM><<<grid, NT, 0, st>>>(Y, src, Phi, wsum, F, D, T, Kout, normalize);
+    GSS_LAUNCH_CHECK("weighted_cov_kernel");
+    return GSS_OK;
+}
+
+int weighted_cov_dispatch(const float2* Y, const WeightSrc& src, cd* Phi, double* wsum,
+                          int B, int F, int D, int T, int Kout, int normalize, cudaStream_t st) {
+    const int DP = (D + 1) & ~1;
+    switch (DP) {
+#define GSS_CASE(dp) case dp: return launch_weighted_cov<dp>(Y, src, Phi, wsum, B, F, D, T, Kout, normalize, st);
+        GSS_DP_LIST
+#undef GSS_CASE
+        default: return fail(GSS_ERR_UNSUPPORTED, "weighted covariance: D=%d not built", D);
+    }
+}
+
+__global__ void c128_to_c64_kernel(const cd* __restrict__ src, float2* __restrict__ dst, size_t n) {
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+        dst[i] = make_float2((float)src[i].x, (float)src[i].y);
+}
+
+// ---------------------------------------------------------------------------
+// Per-bin beamforming matrices.  One CTA (128 threads) per (b, f).
+//   MVDR:  mat = Phi_N^{-1} Phi_X / max(Re tr, eps)   (D x D, all candidate
+//          reference columns) + per-column SNR numerators / denominators.
+//   GEV:   principal generalised eigenvector (phase-normalised) in column 0.
+// ---------------------------------------------------------------------------
+constexpr int BFW_NT = 128;
+
+struct BfwSmem {
+    static __host__ __device__ size_t bytes(int D) {
+        const int ld = D + 1;
+        return size_t(4) * D * ld * sizeof(cd) + 64 * sizeof(double) + 16 * sizeof(JacobiRot) + 64 * sizeof(double) + 64;
+    }
+};
+
+__global__ void __launch_bounds__(BFW_NT) bf_weights_kernel(const cd* __restrict__ Phi /*(B,F,2,D,D)*/,
+                                                            cd* __restrict__ mat /*(B,F,D,D)*/,
+                                                            double* __restrict__ numden /*(B,F,2,D)*/,
+                                                            int* __restrict__ info, int F, int D,
+                                                            int gev, double eps) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int ld = D + 1;
+    cd* PX = reinterpret_cast<cd*>(smem_raw);         // Phi_X
+    cd* PN = PX + D * ld;                              // Phi_N
+    cd* A = PN + D * ld;                               // work
+    cd* Bm = A + D * ld;                               // work / result
+    double* red = reinterpret_cast<double*>(Bm + D * ld);     // [64]
+    JacobiRot* rot = reinterpret_cast<JacobiRot*>(red + 64);  // [16]
+    double* lam = reinterpret_cast<double*>(rot + 16);        // [64]
+    int* iscr = reinterpret_cast<int*>(lam + 64);             // [16]
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const size_t bf = blockIdx.x;
+    const int b = (int)(bf / F), f = (int)(bf - (size_t)b * F);
+    const cd* gx = Phi + bf * 2 * D * D;
+    const cd* gn = gx + D * D;
+    for (int i = tid; i < D * D; i += BFW_NT) {
+        const int r = i / D, c = i - r * D;
+        PX[r * ld + c] = gx[i]; PN[r * ld + c] = gn[i];
+    }
+    __syncthreads();
+    cd* out = mat + bf * D * D;
+
+    if (!gev) {
+        // ---- phi = solve(Phi_N, Phi_X) with LAPACK-like partial pivoting ----
+        for (int i = tid; i < D * D; i += BFW_NT) {
+            const int r = i / D, c = i - r * D;
+            A[r * ld + c] = PN[r * ld + c]; Bm[r * ld + c] = PX[r * ld + c];
+        }
+        __syncthreads();
+        const bool ok = block_lu_solve(A, ld, Bm, ld, D, D, iscr, tid, BFW_NT);
+        if (!ok) {
+            // ---- lstsq fallback (solve.py:108-113): minimum-norm solution through the
+            //      eigendecomposition of the Hermitian Phi_N, rcond = eps * D (numpy default)
+            for (int i = tid; i < D * D; i += BFW_NT) {
+                const int r = i / D, c = i - r * D;
+                A[r * ld + c] = PN[r * ld + c];
+            }
+            __syncthreads();
+            cd* V = Bm;
+            block_jacobi_eigh(A, V, D, ld, rot, red, tid, BFW_NT);
+            if (tid == 0) {
+                double mx = 0.0;
+                for (int i = 0; i < D; ++i) mx = fmax(mx, fabs(A[i * ld + i].x));
+                const double cut = mx * 2.220446049250313e-16 * D;
+                for (int i = 0; i < D; ++i) {
+                    const double l = A[i * ld + i].x;
+                    lam[i] = (fabs(l) > cut) ? 1.0 / l : 0.0;
+                }
+            }
+            __syncthreads();
+            // A <- V diag(lam) V^H  (pseudo inverse), then Bm <- A Phi_X
+            for (int i = tid; i < D * D; i += BFW_NT) {
+                const int r = i / D, c = i - r * D;
+                cd s = cmake(0.0, 0.0);
+                for (int j = 0; j < D; ++j) cfmac(s, cscale(V[r * ld + j], lam[j]), V[c * ld + j]);
+                A[r * ld + c] = s;
+            }
+            __syncthreads();
+            for (int i = tid; i < D * D; i += BFW_NT) {
+                const int r = i / D, c = i - r * D;
+                cd s = cmake(0.0, 0.0);
+                for (int j = 0; j < D; ++j) cfma(s, A[r * ld + j], PX[j * ld + c]);
+                Bm[r * ld + c] = s;
+            }
+            __syncthreads();
+        }
+        // ---- mat = phi / max(Re tr(phi), eps) ----
+        double tr = 0.0;
+        if (tid < D) tr = Bm[tid * ld + tid].x;
+        tr = block_sum(tr, red, tid, BFW_NT);
+        const double sc = 1.0 / fmax(tr, eps);
+        for (int i = tid; i < D * D; i += BFW_NT) {
+            const int r = i / D, c = i - r * D;
+            const cd v = cscale(Bm[r * ld + c], sc);
+            Bm[r * ld + c] = v;
+            out[i] = v;
+        }
+        __syncthreads();
+        // ---- per candidate reference r:  w_r^H Phi_X w_r  and  w_r^H Phi_N w_r ----
+        for (int i = tid; i < 2 * D; i += BFW_NT) {
+            const int which = i / D, r = i - which * D;
+            const cd* Pm = which ? PN : PX;
+            cd s = cmake(0.0, 0.0);
+            for (int d = 0; d < D; ++d) {
+                cd u = cmake(0.0, 0.0);
+                for (int e = 0; e < D; ++e) cfma(u, Pm[d * ld + e], Bm[e * ld + r]);
+                cfma(s, cconj(Bm[d * ld + r]), u);
+            }
+            numden[(bf * 2 + which) * D + r] = s.x;
+        }
+    } else {
+        // ---- GEV: Cholesky Phi_N = L L^H ; C = L^-1 Phi_X L^-H ; eigh(C) ; v = L^-H u ----
+        cd* Lp = A;                                    // packed lower
+        for (int i = tid; i < D * D; i += BFW_NT) {
+            const int r = i / D, c = i - r * D;
+            if (c <= r) Lp[tri(r, c)] = (r == c) ? cmake(PN[r * ld + r].x, 0.0) : PN[r * ld + c];
+        }
+        __syncthreads();
+        if (warp == 0) {
+            const bool ok = warp_cholesky_packed(Lp, D, lane);
+            if (ok) warp_tri_inverse_inplace(Lp, D, lane);
+            if (lane == 0) iscr[1] = ok ? 1 : 0;
+        }
+        __syncthreads();
+        if (!iscr[1]) {
+            if (tid == 0 && info) atomicMax(&info[b], GSS_INFO_NOT_POSDEF | (f << 8));
+            for (int i = tid; i < D * D; i += BFW_NT) out[i] = cmake(0.0, 0.0);
+            return;
+        }
+        // Bm <- M Phi_X  (M lower triangular packed in Lp)
+        for (int i = tid; i < D * D; i += BFW_NT) {
+            const int r = i / D, c = i - r * D;
+            cd s = cmake(0.0, 0.0);
+            for (int j = 0; j <= r; ++j) cfma(s, Lp[tri(r, j)], PX[j * ld + c]);
+            Bm[r * ld + c] = s;
+        }
+        __syncthreads();
+        // PX <- Bm M^H  (Hermitian C), reuse PX storage after a barrier
+        cd cval[ (32 * 32 + BFW_NT - 1) / BFW_NT ];
+        {
+            int n = 0;
+            for (int i = tid; i < D * D; i += BFW_NT, ++n) {
+                const int r = i / D, c = i - r * D;
+                cd s = cmake(0.0, 0.0);
+                for (int j = 0; j <= c; ++j) cfmac(s, Bm[r * ld + j], Lp[tri(c, j)]);
+                cval[n] = s;
+            }
+        }
+        __syncthreads();
+        {
+            int n = 0;
+            for (int i = tid; i < D * D; i += BFW_NT, ++n) {
+                const int r = i / D, c = i - r * D;
+                PX[r * ld + c] = cval[n];
+            }
+        }
+        __syncthreads();
+        // hermitise C exactly
+        for (int i = tid; i < D * D; i += BFW_NT) {
+            const int r = i / D, c = i - r * D;
+            if (r == c) Bm[r * ld + c] = cmake(PX[r * ld + r].x, 0.0);
+            else {
+                const cd u = PX[r * ld + c], v = PX[c * ld + r];
+                Bm[r * ld + c] = cmake(0.5 * (u.x + v.x), 0.5 * (u.y - v.y));
+            }
+        }
+        __syncthreads();
+        cd* V = PX;
+        const int sweeps = block_jacobi_eigh(Bm, V, D, ld, rot, red, tid, BFW_NT);
+        if (sweeps < 0 && tid == 0 && info) atomicMax(&info[b], GSS_INFO_NO_CONVERGE | (f << 8));
+        if (tid == 0) {
+            int best = 0; double bv = Bm[0].x;
+            for (int i = 1; i < D; ++i) if (Bm[i * ld + i].x > bv) { bv = Bm[i * ld + i].x; best = i; }
+            iscr[2] = best;
+        }
+        __syncthreads();
+        const int best = iscr[2];
+        // v = M^H u ; then canonical phase: (Phi_N v)[0] real, non-negative
+        cd* vv = reinterpret_cast<cd*>(lam);           // needs D*16 bytes <= 64*8
+        if (tid < D) {
+            cd s = cmake(0.0, 0.0);
+            for (int j = tid; j < D; ++j) cfma(s, cconj(Lp[tri(j, tid)]), V[j * ld + best]);
+            vv[tid] = s;
+        }
+        __syncthreads();
+        if (tid == 0) {
+            cd z = cmake(0.0, 0.0);
+            for (int e = 0; e < D; ++e) cfma(z, PN[0 * ld + e], vv[e]);
+            const double az = sqrt(cabs2(z));
+            red[0] = az > 0.0 ? z.x / az : 1.0;
+            red[1] = az > 0.0 ? -z.y / az : 0.0;        // conj(phase)
+        }
+        __syncthreads();
+        const cd ph = cmake(red[0], red[1]);
+        for (int i = tid; i < D * D; i += BFW_NT) {
+            const int r = i / D, c = i - r * D;
+            out[i] = (c == 0) ? cmul(vv[r], ph) : cmake(0.0, 0.0);
+        }
+    }
+}
+
+// One CTA per utterance: SNR_r = sum_f num / max(sum_f den, eps); argmax (first max wins, np.argmax).
+__global__ void bf_refchan_kernel(const double* __restrict__ numden, int* __restrict__ ref, int* __restrict__ info,
+                                  int F, int D, double eps) {
+    __shared__ double snr[64];
+    const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int nw = blockDim.x / 32;
+    for (int r = warp; r < D; r += nw) {
+        double n = 0.0, d = 0.0;
+        for (int f = lane; f < F; f += 32) {
+            n += numden[(((size_t)b * F + f) * 2 + 0) * D + r];
+            d += numden[(((size_t)b * F + f) * 2 + 1) * D + r];
+        }
+        n = warp_sum(n); d = warp_sum(d);
+        if (lane == 0) snr[r] = n / fmax(d, eps);
+    }
+    __syncthreads();
+    if (tid == 0) {
+        int best = 0; bool finite = true;
+        for (int r = 0; r < D; ++r) {
+            if (!isfinite(snr[r])) finite = false;
+            if (snr[r] > snr[best]) best = r;
+        }
+        if (!finite && info) atomicMax(&info[b], GSS_INFO_NONFINITE);
+        ref[b] = best;
+    }
+}
+
+// One CTA per (b, f): pick column, BAN, apply, postfilter.
+__global__ void __launch_bounds__(256) bf_apply_kernel(const float2* __restrict__ Y, const cd* __restrict__ Phi,
+                                                       const cd* __restrict__ mat, const int* __restrict__ ref,
+                                                       WeightSrc src, float2* __restrict__ Xhat,
+                                                       cd* __restrict__ weights_out,
+                                                       int F, int D, int T, int fixed_col, int ban, int postfilter) {
+    __shared__ cd w[32];
+    __shared__ cd pw[32];
+    __shared__ double scal[2];
+    const int tid = threadIdx.x;
+    const size_t bf = blockIdx.x;
+    const int b = (int)(bf / F);
+    const int col = fixed_col >= 0 ? fixed_col : ref[b];
+    if (tid < D) w[tid] = mat[bf * D * D + (size_t)tid * D + col];
+    __syncthreads();
+    if (ban) {
+        const cd* PN = Phi + (bf * 2 + 1) * D * D;
+        if (tid < D) {
+            cd s = cmake(0.0, 0.0);
+            for (int e = 0; e < D; ++e) cfma(s, PN[tid * D + e], w[e]);
+            pw[tid] = s;                                 // (Phi_N w)[tid]
+        }
+        __syncthreads();
+        if (tid == 0) {
+            double nom = 0.0; cd den = cmake(0.0, 0.0);
+            for (int d = 0; d < D; ++d) { nom += cabs2(pw[d]); cfma(den, cconj(w[d]), pw[d]); }
+            const double ad = sqrt(cabs2(den));
+            scal[0] = ad != 0.0 ? sqrt(nom) / ad : 0.0;  // beamformer.py:406-417
+        }
+        __syncthreads();
+        if (tid < D) w[tid] = cscale(w[tid], scal[0]);
+        __syncthreads();
+    }
+    if (weights_out && tid < D) weights_out[bf * D + tid] = w[tid];
+    const float2* __restrict__ Yg = Y + bf * D * T;
+    for (int t = tid; t < T; t += blockDim.x) {
+        cd s = cmake(0.0, 0.0);
+        for (int d = 0; d < D; ++d) {
+            const float2 v = __ldg(&Yg[(size_t)d * T + t]);
+            cfma(s, cconj(w[d]), cmake((double)v.x, (double)v.y));
+        }
+        if (postfilter == GSS_POSTFILTER_MASK_MUL) {
+            double w0, w1;
+            frame_weights(src, b, bf, T, t, 0, w0, w1);
+            s = cscale(s, w0);
+        }
+        Xhat[bf * T + t] = make_float2((float)s.x, (float)s.y);
+    }
+}
+
+// 'ch' / 'sum' (core.py:259-262)
+__global__ void bf_simple_kernel(const float2* __restrict__ Y, WeightSrc src, float2* __restrict__ Xhat,
+                                 int F, int D, int T, int ch, int postfilter) {
+    const size_t bf = blockIdx.x;
+    const int b = (int)(bf / F);
+    const float2* __restrict__ Yg = Y + bf * D * T;
+    for (int t = threadIdx.x; t < T; t += blockDim.x) {
+        double re = 0.0, im = 0.0;
+        if (ch >= 0) { const float2 v = Yg[(size_t)ch * T + t]; re = v.x; im = v.y; }
+        else for (int d = 0; d < D; ++d) { const float2 v = Yg[(size_t)d * T + t]; re += v.x; im += v.y; }
+        if (postfilter == GSS_POSTFILTER_MASK_MUL) {
+            double w0, w1;
+            frame_weights(src, b, bf, T, t, 0, w0, w1);
+            re *= w0; im *= w0;
+        }
+        Xhat[bf * T + t] = make_float2((float)re, (float)im);
+    }
+}
+
+static size_t bf_ws_layout(int B, int F, int D, cd** Phi, cd** mat, double** numden, int** ref, void* ws) {
+    Arena a(ws, ~size_t(0));
+    cd* p1 = a.take<cd>((size_t)B * F * 2 * D * D);
+    cd* p2 = a.take<cd>((size_t)B * F * D * D);
+    double* p3 = a.take<double>((size_t)B * F * 2 * D);
+    int* p4 = a.take<int>(B);
+    if (Phi) *Phi = p1; if (mat) *mat = p2; if (numden) *numden = p3; if (ref) *ref = p4;
+    return a.off;
+}
+
+size_t beamform_ws_bytes(int B, int F, int D) { return bf_ws_layout(B, F, D, nullptr, nullptr, nullptr, nullptr, nullptr); }
+size_t weighted_cov_ws_bytes(int B, int F, int D, int K) { return align_up((size_t)B * F * K * D * D * sizeof(cd)); }
+
+static int beamform_impl(const float2* Y, const WeightSrc& src, float2* Xhat, int bf_type, int bf_arg,
+                         int postfilter, int B, int F, int D, int T, int* ref_out, double* weights_out,
+                         int* info, void* ws, size_t ws_bytes, cudaStream_t st) {
+    GSS_REQUIRE(Y && Xhat, GSS_ERR_ARG, "beamform: null pointer");
+    GSS_REQUIRE(B >= 0 && F >= 0 && D > 0 && T > 0, GSS_ERR_ARG, "beamform: bad dims");
+    GSS_REQUIRE(postfilter == GSS_POSTFILTER_NONE || postfilter == GSS_POSTFILTER_MASK_MUL, GSS_ERR_UNSUPPORTED,
+                "postfilter %d (core.py:272-273)", postfilter);
+    if (B == 0 || F == 0) return GSS_OK;
+    if (bf_type == GSS_BF_CH || bf_type == GSS_BF_SUM) {
+        if (bf_type == GSS_BF_CH) GSS_REQUIRE(bf_arg >= 0 && bf_arg < D, GSS_ERR_ARG, "channel %d out of range for D=%d", bf_arg, D);
+        bf_simple_kernel<<<B * F, 256, 0, st>>>(Y, src, Xhat, F, D, T, bf_type == GSS_BF_CH ? bf_arg : -1, postfilter);
+        GSS_LAUNCH_CHECK("bf_simple_kernel");
+        return GSS_OK;
+    }
+    const bool gev = bf_type == GSS_BF_GEV_BAN || bf_type == GSS_BF_GEV;
+    const bool mvdr = bf_type == GSS_BF_MVDR_SOUDEN_BAN || bf_type == GSS_BF_MVDR_SOUDEN;
+    GSS_REQUIRE(gev || mvdr, GSS_ERR_UNSUPPORTED, "beamformer type %d (core.py:263-264)", bf_type);
+    const bool ban = bf_type == GSS_BF_MVDR_SOUDEN_BAN || bf_type == GSS_BF_GEV_BAN;
+    GSS_REQUIRE(D < 30, GSS_ERR_ARG, "D=%d: beamformer needs D < 30 (beamforming_wrapper.py:44)", D);
+    cd *Phi, *mat; double* numden; int* ref;
+    const size_t need = bf_ws_layout(B, F, D, &Phi, &mat, &numden, &ref, ws);
+    GSS_REQUIRE(ws && ws_bytes >= need, GSS_ERR_WORKSPACE, "beamform: workspace %zu < %zu", ws_bytes, need);
+    int rc = weighted_cov_dispatch(Y, src, Phi, nullptr, B, F, D, T, 2, 1, st);
+    if (rc) return rc;
+    const size_t smem = BfwSmem::bytes(D);
+    GSS_CUDA(cudaFuncSetAttribute(bf_weights_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    bf_weights_kernel<<<B * F, BFW_NT, smem, st>>>(Phi, mat, numden, info, F, D, gev ? 1 : 0, 1e-10);
+    GSS_LAUNCH_CHECK("bf_weights_kernel");
+    if (mvdr) {
+        bf_refchan_kernel<<<B, 256, 0, st>>>(numden, ref, info, F, D, 1e-10);
+        GSS_LAUNCH_CHECK("bf_refchan_kernel");
+        if (ref_out) GSS_CUDA(cudaMemcpyAsync(ref_out, ref, sizeof(int) * B, cudaMemcpyDeviceToDevice, st));
+    }
+    bf_apply_kernel<<<B * F, 256, 0, st>>>(Y, Phi, mat, ref, src, Xhat, reinterpret_cast<cd*>(weights_out),
+                                           F, D, T, gev ? 0 : -1, ban ? 1 : 0, postfilter);
+    GSS_LAUNCH_CHECK("bf_apply_kernel");
+    return GSS_OK;
+}
+
+}  // namespace gss
+
+extern "C" {
+
+int gss_weighted_cov_c64(const gss_c64* Y, const float* w, gss_c64* Phi, int normalize_mode,
+                         int B, int F, int D, int T, int K, void* ws, size_t ws_bytes, void* stream) {
+    using namespace gss;
+    GSS_REQUIRE(Y && w && Phi, GSS_ERR_ARG, "gss_weighted_cov_c64: null pointer");
+    GSS_REQUIRE(B >= 0 && F >= 0 && D > 0 && T > 0 && K > 0, GSS_ERR_ARG, "gss_weighted_cov_c64: bad dims");
+    GSS_REQUIRE(D <= 32, GSS_ERR_UNSUPPORTED, "gss_weighted_cov_c64: D=%d > 32 not built", D);
+    GSS_REQUIRE(normalize_mode == 0 || normalize_mode == 1, GSS_ERR_ARG, "normalize_mode %d", normalize_mode);
+    if (B == 0 || F == 0) return GSS_OK;
+    const size_t need = weighted_cov_ws_bytes(B, F, D, K);
+    GSS_REQUIRE(ws && ws_bytes >= need, GSS_ERR_WORKSPACE, "gss_weighted_cov_c64: workspace %zu < %zu", ws_bytes, need);
+    WeightSrc src{}; src.mode = 0; src.w = w; src.K = K;
+    cudaStream_t st = (cudaStream_t)stream;
+    int rc = weighted_cov_dispatch((const float2*)Y, src, (cd*)ws, nullptr, B, F, D, T, K, normalize_mode, st);
+    if (rc) return rc;
+    const size_t n = (size_t)B * F * K * D * D;
+    c128_to_c64_kernel<<<(unsigned)std::min<size_t>((n + 255) / 256, 148 * 8), 256, 0, st>>>((const cd*)ws, (float2*)Phi, n);
+    GSS_LAUNCH_CHECK("c128_to_c64_kernel");
+    return GSS_OK;
+}
+
+int gss_beamform_c64(const gss_c64* Y, const float* target_mask, const float* distortion_mask, gss_c64* X_hat,
+                     int bf_type, int bf_arg, int postfilter, int B, int F, int D, int T,
+                     int* ref_channel_out, double* weights_out, int* info, void* ws, size_t ws_bytes, void* stream) {
+    using namespace gss;
+    GSS_REQUIRE(target_mask && distortion_mask, GSS_ERR_ARG, "gss_beamform_c64: null mask");
+    WeightSrc src{}; src.mode = 1; src.m0 = target_mask; src.m1 = distortion_mask; src.K = 2;
+    return beamform_impl((const float2*)Y, src, (float2*)X_hat, bf_type, bf_arg, postfilter, B, F, D, T,
+                         ref_channel_out, weights_out, info, ws, ws_bytes, (cudaStream_t)stream);
+}
+
+int gss_beamform_from_posterior_c64(const gss_c64* Y, const float* posterior, const int* target_index,
+                                    const int* start_ctx, const int* end_ctx, gss_c64* X_hat,
+                                    int bf_type, int bf_arg, int postfilter, int B, int F, int D, int T, int K,
+                                    int* ref_channel_out, double* weights_out, int* info,
+                                    void* ws, size_t ws_bytes, void* stream) {
+    using namespace gss;
+    GSS_REQUIRE(posterior && target_index, GSS_ERR_ARG, "gss_beamform_from_posterior_c64: null pointer");
+    GSS_REQUIRE(K > 1 && K < 20, GSS_ERR_ARG, "K=%d", K);
+    WeightSrc src{}; src.mode = 2; src.w = posterior; src.target_index = target_index;
+    src.start_ctx = start_ctx; src.end_ctx = end_ctx; src.K = K;
+    return beamform_impl((const float2*)Y, src, (float2*)X_hat, bf_type, bf_arg, postfilter, B, F, D, T,
+                         ref_channel_out, weights_out, info, ws, ws_bytes, (cudaStream_t)stream);
+}
+
+}  // extern "C"

@@ -1,0 +1,434 @@
+// WPE dereverberation on the device (float64 arithmetic on complex64 input).
+// Restates nara_wpe.wpe.wpe_v8 -> wpe_v6 (third party, un-vendored; call sites
+// pb_chime5/core.py:52-58; algorithm per SURVEY.md appendix A):
+//   repeat `iterations`:
+//     inv_t = 1 / max(mean_d |X[d,t]|^2 (smoothed over +-psd_context), 1e-10 max_t)   wpe_invpower_kernel
+//     R = (Yt*inv) Yt^H , P = (Yt*inv) Y^H                                            wpe_corr_kernel
+//     G = solve(R, P)                                                                 wpe_solve_kernel
+//     X = Y - G^H Yt   (+ raw power of X for the next iteration)                      wpe_apply_kernel
+// Yt row (k, d) at frame t is Y[d, t - delay - k] (zero history).
+//
+// Storage per bin: augmented matrix Raug ((LD + D) x LD, row-major complex128):
+// rows [0, LD) = R (lower triangle valid), rows [LD, LD + D) = P^H.  The blocked
+// left-looking Cholesky factors R in place and, because the P^H rows ride along
+// as extra sub-diagonal rows, leaves Z^H = (L^{-1} P)^H in them (forward
+// substitution for free).
+#include "common.cuh"
+#include "smallmat.cuh"
+
+namespace gss {
+
+struct WpeDims { int F, D, T, L, delay, LD; };
+
+__device__ __forceinline__ cd wpe_row_value(const float2* __restrict__ Yg, const WpeDims& m, int idx, int t) {
+    // idx < LD : tap row (k, d) ; LD <= idx < LD + D : the unshifted observation
+    if (t >= m.T) return cmake(0.0, 0.0);
+    int d, ts;
+    if (idx < m.LD) { const int k = idx / m.D; d = idx - k * m.D; ts = t - m.delay - k; }
+    else if (idx < m.LD + m.D) { d = idx - m.LD; ts = t; }
+    else return cmake(0.0, 0.0);
+    if (ts < 0) return cmake(0.0, 0.0);
+    const float2 v = __ldg(&Yg[(size_t)d * m.T + ts]);
+    return cmake((double)v.x, (double)v.y);
+}
+
+// raw power[t] = mean_d |Y[d,t]|^2   (first iteration: X = Y)
+__global__ void wpe_power_kernel(const float2* __restrict__ Y, double* __restrict__ power, int D, int T) {
+    const size_t bf = blockIdx.x;
+    const float2* Yg = Y + bf * D * T;
+    for (int t = threadIdx.x; t < T; t += blockDim.x) {
+        double s = 0.0;
+        for (int d = 0; d < D; ++d) { const float2 v = Yg[(size_t)d * T + t]; s = fma((double)v.x, (double)v.x, fma((double)v.y, (double)v.y, s)); }
+        power[bf * T + t] = s / D;
+    }
+}
+
+// inv[t] = 1 / max(smooth(power)[t], 1e-10 * max_t smooth(power))
+__global__ void wpe_invpower_kernel(const double* __restrict__ power, double* __restrict__ inv, int T, int ctx) {
+    __shared__ double red[32];
+    const size_t bf = blockIdx.x;
+    const double* p = power + bf * T;
+    double* o = inv + bf * T;
+    double mx = 0.0;
+    for (int t = threadIdx.x; t < T; t += blockDim.x) {
+        double v;
+        if (ctx > 0) {
+            const int lo = max(t - ctx, 0), hi = min(t + ctx, T - 1);
+            double s = 0.0;
+            for (int u = lo; u <= hi; ++u) s += p[u];
+            v = s / (double)(hi - lo + 1);
+        } else v = p[t];
+        o[t] = v;
+        mx = fmax(mx, v);
+    }
+    for (int of = 16; of > 0; of >>= 1) mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, of));
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = mx;
+    __syncthreads();
+    mx = 0.0;
+    for (int w = 0; w < (int)(blockDim.x + 31) / 32; ++w) mx = fmax(mx, red[w]);
+    const double eps = 1e-10 * mx;
+    for (int t = threadIdx.x; t < T; t += blockDim.x) o[t] = 1.0 / fmax(o[t], eps);
+}
+
+// ---------------------------------------------------------------------------
+// Weighted Gram matrix of the augmented data matrix, lower trapezoid.
+// 48 x 48 complex tile per CTA, 12 x 12 threads, 4 x 4 register block each.
+// ---------------------------------------------------------------------------
+constexpr int CT_BM = 48, CT_BK = 16, CT_NT = 144;
+
+__global__ void __launch_bounds__(CT_NT) wpe_corr_kernel(const float2* __restrict__ Y, const double* __restrict__ inv,
+                                                         cd* __restrict__ Raug, WpeDims m) {
+    const int rt = blockIdx.y, ct = blockIdx.z;
+    if (ct > rt || ct * CT_BM >= m.LD || rt * CT_BM >= m.LD + m.D) return;
+    __shared__ __align__(16) cd As[CT_BK][CT_BM];
+    __shared__ __align__(16) cd Bs[CT_BK][CT_BM];
+    const size_t bf = blockIdx.x;
+    const float2* __restrict__ Yg = Y + bf * m.D * m.T;
+    const double* __restrict__ iv = inv + bf * m.T;
+    const int tid = threadIdx.x;
+    const int ty = tid / 12, tx = tid - ty * 12;
+    const int i0 = rt * CT_BM, j0 = ct * CT_BM;
+    cd acc[4][4];
+#pragma unroll
+    for (int a = 0; a < 4; ++a)
+#pragma unroll
+        for (int b = 0; b < 4; ++b) acc[a][b] = cmake(0.0, 0.0);
+    for (int t0 = 0; t0 < m.T; t0 += CT_BK) {
+        for (int e = tid; e < CT_BM * CT_BK; e += CT_NT) {
+            const int r = e / CT_BK, tt = e - r * CT_BK;
+            const int t = t0 + tt;
+            const double w = t < m.T ? iv[t] : 0.0;
+            As[tt][r] = cscale(wpe_row_value(Yg, m, i0 + r, t), w);
+            Bs[tt][r] = wpe_row_value(Yg, m, j0 + r, t);
+        }
+        __syncthreads();
+#pragma unroll
+        for (int tt = 0; tt < CT_BK; ++tt) {
+            cd a[4], b[4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) { a[q] = As[tt][4 * ty + q]; b[q] = Bs[tt][4 * tx + q]; }
+#pragma unroll
+            for (int x = 0; x < 4; ++x)
+#pragma unroll
+                for (int y = 0; y < 4; ++y) cfmac(acc[x][y], a[x], b[y]);
+        }
+        __syncthreads();
+    }
+    cd* out = Raug + bf * (size_t)(m.LD + m.D) * m.LD;
+#pragma unroll
+    for (int x = 0; x < 4; ++x) {
+        const int i = i0 + 4 * ty + x;
+        if (i >= m.LD + m.D) continue;
+#pragma unroll
+        for (int y = 0; y < 4; ++y) {
+            const int j = j0 + 4 * tx + y;
+            if (j >= m.LD) continue;
+            if (i < m.LD && j > i) continue;
+            cd v = acc[x][y];
+            if (i == j) v.y = 0.0;
+            out[(size_t)i * m.LD + j] = v;
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------
+// Blocked left-looking Cholesky of R (in place, lower) with the P^H rows riding
+// along, then blocked back substitution  L^H G = Z.  One CTA per bin, one thread
+// per matrix row.  A non-positive pivot (dead channel) zeroes that unknown,
+// which is the minimum-norm solution the reference's lstsq fallback returns for
+// an exactly-zero row/column.
+// ---------------------------------------------------------------------------
+constexpr int WS_NB = 24;
+
+template <int NT>
+__global__ void __launch_bounds__(NT) wpe_solve_kernel(cd* __restrict__ Raug, cd* __restrict__ G,
+                                                       int* __restrict__ info, WpeDims m) {
+    __shared__ __align__(16) cd Lj[WS_NB][WS_NB + 1];        // L[j-block rows][p-block cols]
+    __shared__ __align__(16) cd Dg[WS_NB * (WS_NB + 1) / 2]; // packed diagonal block / its inverse
+    __shared__ __align__(16) cd Sm[WS_NB][33];               // back substitution block [i][d], d < 32
+    __shared__ int bad[WS_NB];
+    const size_t bf = blockIdx.x;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int n = m.LD, nrows = m.LD + m.D;
+    cd* A = Raug + bf * (size_t)nrows * n;
+    for (int j0 = 0; j0 < n; j0 += WS_NB) {
+        const int nb = min(WS_NB, n - j0);
+        for (int rbase = j0; rbase < nrows; rbase += NT) {
+            const int r = rbase + tid;
+            const bool have = r < nrows;
+            cd acc[WS_NB];
+            if (have) {
+#pragma unroll
+                for (int c = 0; c < WS_NB; ++c) acc[c] = (c < nb && (r >= n || j0 + c <= r)) ? A[(size_t)r * n + j0 + c] : cmake(0.0, 0.0);
+            }
+            for (int p0 = 0; p0 < j0; p0 += WS_NB) {
+                __syncthreads();
+                for (int e = tid; e < nb * WS_NB; e += NT) {
+                    const int c = e / WS_NB, q = e - c * WS_NB;
+                    Lj[c][q] = A[(size_t)(j0 + c) * n + p0 + q];
+                }
+                __syncthreads();
+                if (have) {
+                    cd lr[WS_NB];
+#pragma unroll
+                    for (int q = 0; q < WS_NB; ++q) lr[q] = A[(size_t)r * n + p0 + q];
+#pragma unroll
+                    for (int c = 0; c < WS_NB; ++c) {
+                        if (c < nb) {
+#pragma unroll
+                            for (int q = 0; q < WS_NB; ++q) cfmsc(acc[c], lr[q], Lj[c][q]);
+                        }
+                    }
+                }
+            }
+            if (rbase == j0) {
+                // ---- factor the diagonal block (rows j0 .. j0+nb-1 live in threads 0..nb-1) ----
+                __syncthreads();
+                if (tid < nb) {
+#pragma unroll
+                    for (int c = 0; c < WS_NB; ++c)
+                        if (c <= tid) Dg[tri(tid, c)] = (c == tid) ? cmake(acc[c].x, 0.0) : acc[c];
+                }
+                __syncthreads();
+                if (warp == 0) {
+                    // Cholesky with zero-pivot deflation
+                    for (int j = 0; j < nb; ++j) {
+                        cd s = cmake(0.0, 0.0);
+                        if (lane >= j && lane < nb) {
+                            s = Dg[tri(lane, j)];
+                            for (int pp = 0; pp < j; ++pp) cfmsc(s, Dg[tri(lane, pp)], Dg[tri(j, pp)]);
+                        }
+                        const double djj = __shfl_sync(0xffffffffu, s.x, j);
+                        const bool okp = djj > 0.0 && isfinite(djj);
+                        const double rr = okp ? sqrt(djj) : 0.0;
+                        const double ri = okp ? 1.0 / rr : 0.0;
+                        if (lane == j) { Dg[tri(j, j)] = cmake(rr, 0.0); bad[j] = okp ? 0 : 1; }
+                        else if (lane > j && lane < nb) Dg[tri(lane, j)] = cscale(s, ri);
+                        __syncwarp();
+                    }
+                }
+                __syncthreads();
+                // write L_jj rows, then invert the block in place (zero pivots -> zero rows/cols)
+                if (tid < nb) {
+                    for (int c = 0; c <= tid; ++c) A[(size_t)(j0 + tid) * n + j0 + c] = Dg[tri(tid, c)];
+                }
+                __syncthreads();
+                if (warp == 0) {
+                    for (int j = nb - 1; j >= 0; --j) {
+                        const double dj = Dg[tri(j, j)].x;
+                        const double mjj = dj > 0.0 ? 1.0 / dj : 0.0;
+                        cd s = cmake(0.0, 0.0);
+                        if (lane > j && lane < nb) {
+                            for (int pp = j + 1; pp <= lane; ++pp) cfma(s, Dg[tri(lane, pp)], Dg[tri(pp, j)]);
+                        }
+                        __syncwarp();
+                        if (lane > j && lane < nb) Dg[tri(lane, j)] = cscale(s, -mjj);
+                        else if (lane == j) Dg[tri(j, j)] = cmake(mjj, 0.0);
+                        __syncwarp();
+                    }
+                }
+                __syncthreads();
+                if (tid == 0 && info) {
+                    int any = 0;
+                    for (int j = 0; j < nb; ++j) any |= bad[j];
+                    if (any) atomicMax(&info[bf / m.F], GSS_INFO_SINGULAR | ((int)(bf % m.F) << 8));
+                }
+            }
+            // ---- panel rows below the diagonal block:  L[r, jblock] = acc * Ljj^{-H} ----
+            if (have && r >= j0 + nb) {
+                cd o[WS_NB];
+#pragma unroll
+                for (int c = 0; c < WS_NB; ++c) {
+                    o[c] = cmake(0.0, 0.0);
+                    if (c < nb) {
+#pragma unroll
+                        for (int q = 0; q < WS_NB; ++q)
+                            if (q <= c) cfmac(o[c], acc[q], Dg[tri(c, q)]);
+                    }
+                }
+#pragma unroll
+                for (int c = 0; c < WS_NB; ++c)
+                    if (c < nb) A[(size_t)r * n + j0 + c] = o[c];
+            }
+        }
+        __syncthreads();
+    }
+    // ---- back substitution  L^H G = Z ,  Z^H sits in rows [n, n + D) ----
+    cd* Gb = G + bf * (size_t)n * m.D;
+    const int nblk = (n + WS_NB - 1) / WS_NB;
+    for (int jb = nblk - 1; jb >= 0; --jb) {
+        const int j0 = jb * WS_NB, nb = min(WS_NB, n - j0);
+        // S[i][d] = Z[j0+i][d] - sum_{r >= j0+nb} conj(L[r][j0+i]) G[r][d]
+        for (int e = tid; e < nb * m.D; e += NT) {
+            const int d = e / nb, i = e - d * nb;
+            cd s = cconj(A[(size_t)(n + d) * n + j0 + i]);
+            cd s2 = cmake(0.0, 0.0);
+            int r = j0 + nb;
+            for (; r + 1 < n; r += 2) {
+                cfma(s, cconj(A[(size_t)r * n + j0 + i]), cscale(Gb[(size_t)r * m.D + d], -1.0));
+                cfma(s2, cconj(A[(size_t)(r + 1) * n + j0 + i]), cscale(Gb[(size_t)(r + 1) * m.D + d], -1.0));
+            }
+            if (r < n) cfma(s, cconj(A[(size_t)r * n + j0 + i]), cscale(Gb[(size_t)r * m.D + d], -1.0));
+            Sm[i][d] = cadd(s, s2);
+        }
+        // inverse of the diagonal block again (packed, in shared memory)
+        for (int e = tid; e < nb * (nb + 1) / 2; e += NT) {
+            int rr = 0;
+            while ((rr + 1) * (rr + 2) / 2 <= e) ++rr;
+            const int c = e - rr * (rr + 1) / 2;
+            Dg[e] = A[(size_t)(j0 + rr) * n + j0 + c];
+        }
+        __syncthreads();
+        if (warp == 0) {
+            for (int j = nb - 1; j >= 0; --j) {
+                const double dj = Dg[tri(j, j)].x;
+                const double mjj = dj > 0.0 ? 1.0 / dj : 0.0;
+                cd s = cmake(0.0, 0.0);
+                if (lane > j && lane < nb) {
+                    for (int pp = j + 1; pp <= lane; ++pp) cfma(s, Dg[tri(lane, pp)], Dg[tri(pp, j)]);
+                }
+                __syncwarp();
+                if (lane > j && lane < nb) Dg[tri(lane, j)] = cscale(s, -mjj);
+                else if (lane == j) Dg[tri(j, j)] = cmake(mjj, 0.0);
+                __syncwarp();
+            }
+        }
+        __syncthreads();
+        // G[j0+i][d] = sum_{q >= i} conj(Minv[q][i]) S[q][d]
+        for (int e = tid; e < nb * m.D; e += NT) {
+            const int d = e / nb, i = e - d * nb;
+            cd s = cmake(0.0, 0.0);
+            for (int q = i; q < nb; ++q) cfma(s, cconj(Dg[tri(q, i)]), Sm[q][d]);
+            Gb[(size_t)(j0 + i) * m.D + d] = s;
+        }
+        __syncthreads();
+    }
+}
+
+// ---------------------------------------------------------------------------
+// X = Y - G^H Yt ; one thread per frame, all D outputs in registers.
+// ---------------------------------------------------------------------------
+template <int DMAX, int NT>
+__global__ void __launch_bounds__(NT) wpe_apply_kernel(const float2* __restrict__ Y, const cd* __restrict__ G,
+                                                       float2* __restrict__ X, double* __restrict__ power, WpeDims m) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    cd* Gs = reinterpret_cast<cd*>(smem_raw);                         // [LD][D]
+    const size_t bf = blockIdx.x;
+    const int tid = threadIdx.x;
+    const float2* __restrict__ Yg = Y + bf * m.D * m.T;
+    const cd* Gb = G + bf * (size_t)m.LD * m.D;
+    for (int i = tid; i < m.LD * m.D; i += NT) Gs[i] = Gb[i];
+    __syncthreads();
+    const int t = blockIdx.y * NT + tid;
+    if (t >= m.T) return;
+    cd acc[DMAX];
+#pragma unroll
+    for (int d = 0; d < DMAX; ++d) {
+        acc[d] = cmake(0.0, 0.0);
+        if (d < m.D) { const float2 v = Yg[(size_t)d * m.T + t]; acc[d] = cmake((double)v.x, (double)v.y); }
+    }
+    for (int k = 0; k < m.L; ++k) {
+        const int ts = t - m.delay - k;
+        if (ts < 0) break;
+        for (int dp = 0; dp < m.D; ++dp) {
+            const float2 v = __ldg(&Yg[(size_t)dp * m.T + ts]);
+            const cd y = cmake((double)v.x, (double)v.y);
+            const cd* g = Gs + (size_t)(k * m.D + dp) * m.D;
+#pragma unroll
+            for (int d = 0; d < DMAX; ++d)
+                if (d < m.D) cfms(acc[d], cconj(g[d]), y);
+        }
+    }
+    double pw = 0.0;
+#pragma unroll
+    for (int d = 0; d < DMAX; ++d) {
+        if (d < m.D) {
+            const float2 o = make_float2((float)acc[d].x, (float)acc[d].y);
+            X[bf * m.D * m.T + (size_t)d * m.T + t] = o;
+            // the reference iterates on the float64 X; use the unrounded value for the power
+            pw += cabs2(acc[d]);
+        }
+    }
+    power[bf * m.T + t] = pw / m.D;
+}
+
+struct WpeWs { double* power; double* inv; cd* Raug; cd* G; size_t bytes; };
+
+static WpeWs wpe_ws_layout(void* ws, int Bc, int F, int D, int T, int LD) {
+    Arena a(ws, ~size_t(0));
+    WpeWs w;
+    w.power = a.take<double>((size_t)Bc * F * T);
+    w.inv = a.take<double>((size_t)Bc * F * T);
+    w.Raug = a.take<cd>((size_t)Bc * F * (LD + D) * LD);
+    w.G = a.take<cd>((size_t)Bc * F * LD * D);
+    w.bytes = a.off;
+    return w;
+}
+
+size_t wpe_ws_bytes(int Bc, int F, int D, int T, int L) { return wpe_ws_layout(nullptr, Bc, F, D, T, L * D).bytes; }
+
+template <int DMAX>
+static int launch_apply(const float2* Y, const cd* G, float2* X, double* power, const WpeDims& m, int BF, cudaStream_t st) {
+    constexpr int NT = 128;
+    const size_t smem = (size_t)m.LD * m.D * sizeof(cd);
+    auto kern = wpe_apply_kernel<DMAX, NT>;
+    GSS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    dim3 grid(BF, (m.T + NT - 1) / NT);
+    kern<<<grid, NT, smem, st>>>(Y, G, X, power, m);
+    GSS_LAUNCH_CHECK("wpe_apply_kernel");
+    return GSS_OK;
+}
+
+}  // namespace gss
+
+extern "C" int gss_wpe_c64(const gss_c64* Y, gss_c64* X, int taps, int delay, int iterations, int psd_context,
+                           int B, int F, int D, int T, int* info, void* ws, size_t ws_bytes, void* stream) {
+    using namespace gss;
+    GSS_REQUIRE(Y && X && Y != X, GSS_ERR_ARG, "gss_wpe_c64: null or aliased pointers");
+    GSS_REQUIRE(B >= 0 && F >= 0 && D > 0 && T > 0, GSS_ERR_ARG, "gss_wpe_c64: bad dims");
+    GSS_REQUIRE(taps > 0 && delay >= 0 && iterations >= 0 && psd_context >= 0, GSS_ERR_ARG,
+                "gss_wpe_c64: taps=%d delay=%d iterations=%d psd_context=%d", taps, delay, iterations, psd_context);
+    GSS_REQUIRE(D <= 32, GSS_ERR_UNSUPPORTED, "gss_wpe_c64: D=%d > 32 not built", D);
+    const int LD = taps * D;
+    GSS_REQUIRE((size_t)LD * D * sizeof(cd) <= 200 * 1024, GSS_ERR_UNSUPPORTED,
+                "gss_wpe_c64: taps*D*D=%d too large for the filter tile", LD * D);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (B == 0 || F == 0) return GSS_OK;
+    if (iterations == 0) {
+        GSS_CUDA(cudaMemcpyAsync(X, Y, sizeof(float2) * (size_t)B * F * D * T, cudaMemcpyDeviceToDevice, st));
+        return GSS_OK;
+    }
+    const size_t per_utt = wpe_ws_bytes(1, F, D, T, taps);
+    GSS_REQUIRE(ws && ws_bytes >= per_utt, GSS_ERR_WORKSPACE, "gss_wpe_c64: workspace %zu < %zu (one utterance)", ws_bytes, per_utt);
+    int Bc = (int)std::min<size_t>((size_t)B, ws_bytes / per_utt);
+    while (Bc > 1 && wpe_ws_bytes(Bc, F, D, T, taps) > ws_bytes) --Bc;
+    WpeDims m{F, D, T, taps, delay, LD};
+    for (int b0 = 0; b0 < B; b0 += Bc) {
+        const int bn = std::min(Bc, B - b0);
+        const int BF = bn * F;
+        const float2* Yc = (const float2*)Y + (size_t)b0 * F * D * T;
+        float2* Xc = (float2*)X + (size_t)b0 * F * D * T;
+        int* infoc = info ? info + b0 : nullptr;
+        WpeWs w = wpe_ws_layout(ws, bn, F, D, T, LD);
+        wpe_power_kernel<<<BF, 256, 0, st>>>(Yc, w.power, D, T);
+        GSS_LAUNCH_CHECK("wpe_power_kernel");
+        for (int it = 0; it < iterations; ++it) {
+            wpe_invpower_kernel<<<BF, 256, 0, st>>>(w.power, w.inv, T, psd_context);
+            GSS_LAUNCH_CHECK("wpe_invpower_kernel");
+            dim3 grid(BF, (LD + D + CT_BM - 1) / CT_BM, (LD + CT_BM - 1) / CT_BM);
+            wpe_corr_kernel<<<grid, CT_NT, 0, st>>>(Yc, w.inv, w.Raug, m);
+            GSS_LAUNCH_CHECK("wpe_corr_kernel");
+            if (LD + D <= 288) wpe_solve_kernel<288><<<BF, 288, 0, st>>>(w.Raug, w.G, infoc, m);
+            else wpe_solve_kernel<512><<<BF, 512, 0, st>>>(w.Raug, w.G, infoc, m);
+            GSS_LAUNCH_CHECK("wpe_solve_kernel");
+            int rc;
+            if (D <= 4) rc = launch_apply<4>(Yc, w.G, Xc, w.power, m, BF, st);
+            else if (D <= 8) rc = launch_apply<8>(Yc, w.G, Xc, w.power, m, BF, st);
+            else if (D <= 16) rc = launch_apply<16>(Yc, w.G, Xc, w.power, m, BF, st);
+            else if (D <= 24) rc = launch_apply<24>(Yc, w.G, Xc, w.power, m, BF, st);
+            else rc = launch_apply<32>(Yc, w.G, Xc, w.power, m, BF, st);
+            if (rc) return rc;
+        }
+    }
+    return GSS_OK;
+}

@@ -1,0 +1,32 @@
+"""Ad-hoc GPU probe: timing of the main kernels at config-2 shape."""
+import time
+import numpy as np
+import torch
+from pb_chime5_b200 import ops, synth
+
+dev = torch.device('cuda:0')
+print(torch.cuda.get_device_name(0))
+B = 2
+obs, act = synth.make_batch(1000, B, D=24, T=941, F=513, K=5)
+Y = ops.pack_dtf_to_fdt(torch.from_numpy(obs).to(dev))
+A = torch.from_numpy(act).to(dev)
+
+def timeit(fn, n=3):
+    fn(); torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(True), torch.cuda.Event(True)
+    e0.record()
+    for _ in range(n): r = fn()
+    e1.record(); torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / n, r
+
+for it in (20, 100):
+    ms, post = timeit(lambda: ops.cacgmm(Y, A, it), 2)
+    print(f'cacgmm B={B} it={it}: {ms:.2f} ms  ({ms/B:.2f} ms/utt)')
+ms, X = timeit(lambda: ops.wpe(Y, 10, 2, 3), 2)
+print(f'wpe B={B}: {ms:.2f} ms ({ms/B:.2f} ms/utt)')
+ti = torch.zeros(B, dtype=torch.int32, device=dev)
+ms, Xh = timeit(lambda: ops.beamform_from_posterior(Y, post, ti, None, None), 3)
+print(f'beamform B={B}: {ms:.2f} ms')
+ms, Xh = timeit(lambda: ops.beamform_from_posterior(Y, post, ti, None, None, bf='gev_ban'), 3)
+print(f'beamform gev B={B}: {ms:.2f} ms')
+print('post sum', float(post.sum()), 'finite', bool(torch.isfinite(post).all()), bool(torch.isfinite(torch.view_as_real(X)).all()))
