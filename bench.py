@@ -1,0 +1,321 @@
+#!/usr/bin/env python
+"""Benchmark of the Enhancer hot path (WPE -> guided CACGMM EM -> MVDR-Souden+BAN).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+
+Metric (BASELINE.json): utterances/sec for 15 s, 24-channel, 513-bin STFT
+segments.  Workload = BASELINE.json configs[1] ("cfg2"): D=24, T=941, F=513,
+K=5 classes, WPE taps=10 delay=2 iterations=3, 100 EM iterations, MVDR-Souden
++ BAN -- `--batch` such utterances per GPU and step.
+
+One JSON line on stdout (rank 0).  See DESIGN.md "Measurement" for the meaning
+of every field.  A "step" is one pass of the hot path over one batch.
+"""
+import os
+
+os.environ.setdefault('OMP_NUM_THREADS', '1')      # the reference pins BLAS to 1 thread (pb_chime5/__init__.py:4-14)
+os.environ.setdefault('MKL_NUM_THREADS', '1')
+os.environ.setdefault('OPENBLAS_NUM_THREADS', '1')
+
+import argparse
+import json
+import statistics
+import subprocess
+import sys
+import threading
+import time
+from pathlib import Path
+
+import numpy as np
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+
+CFG = dict(D=24, T=941, F=513, K=5, taps=10, delay=2, wpe_iterations=3, em_iterations=100,
+           bf='mvdrSouden_ban', ctx_frames=3)
+WORKLOAD = ('cfg2: 15 s utterances, 6 arrays x 4 mics (D=24), T=941 frames, F=513 bins, K=5 classes, '
+            'WPE taps=10 delay=2 it=3 + CACGMM 100 EM it + MVDR-Souden+BAN')
+METRIC = 'utterances/sec (15 s, 24-ch, 513-bin STFT)'
+
+
+# ---------------------------------------------------------------------------
+# CPU side: the oracle port timed like the reference runs (one process per core,
+# one BLAS thread each, a Python loop over frequency bins)
+# ---------------------------------------------------------------------------
+
+def _cpu_worker(args):
+    seed, bins = args
+    from oracle import gss_oracle as oracle
+    from pb_chime5_b200 import synth
+    c = CFG
+    Obs, act = synth.make_utterance(seed, D=c['D'], T=c['T'], F=bins, K=c['K'])
+    Obs = Obs.astype(np.complex128)
+    t0 = time.perf_counter()
+    oracle.enhance_stft(Obs, act, 0,
+                        wpe=dict(taps=c['taps'], delay=c['delay'], iterations=c['wpe_iterations'], psd_context=0),
+                        gss_iterations=c['em_iterations'], bf=c['bf'],
+                        start_context_frames=c['ctx_frames'], end_context_frames=c['ctx_frames'],
+                        loop_over_bins=True)
+    return time.perf_counter() - t0
+
+
+def cpu_sample(pool, procs, bins_per_proc, seed0):
+    """One bounded CPU sample: every process enhances `bins_per_proc` bins of one
+    utterance over ALL iterations.  Returns utterances/sec of the whole host."""
+    times = pool.map(_cpu_worker, [(seed0 + i, bins_per_proc) for i in range(procs)])
+    wall = max(times)                 # synthetic-data generation is outside the workers' timers
+    return procs * bins_per_proc / CFG['F'] / wall, wall
+
+
+def run_reference(args):
+    """--impl reference: the reference's CPU algorithm (oracle port; the Python
+    reference cannot travel to the GPU box) on all host cores."""
+    rank = int(os.environ.get('RANK', 0))
+    if rank != 0:
+        return
+    import multiprocessing as mp
+    procs = os.cpu_count() or 1
+    bins = args.cpu_bins
+    ctx = mp.get_context('fork')
+    with ctx.Pool(procs) as pool:
+        for i in range(args.warmup):
+            cpu_sample(pool, procs, bins, 10_000 + 100 * i)
+        wall = 0.0
+        for i in range(args.steps):
+            wall += cpu_sample(pool, procs, bins, 20_000 + 100 * i)[1]
+    value = args.steps * procs * bins / CFG['F'] / wall
+    sample = (f'{procs} processes x {bins} of 513 bins per step, all iterations of WPE+CACGMM+MVDR, '
+              f'scaled by 513/{bins}; per-bin Python loop as pb_chime5/core.py:172')
+    line = {
+        'impl': 'reference', 'metric': METRIC, 'value': value, 'unit': 'utterances/s',
+        'n_gpus': args.gpus, 'steps': args.steps, 'warmup': args.warmup,
+        'ms_per_step': 1e3 * wall / max(args.steps, 1), 'higher_is_better': True, 'scaling': 'weak',
+        'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
+        'config': {'workload': WORKLOAD, 'batch_per_gpu': None},
+        'cpu_baseline': {'value': value, 'unit': 'utterances/s', 'cores': procs, 'kind': 'port', 'sample': sample},
+        'e2e': {'value': value, 'unit': 'utterances/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ---------------------------------------------------------------------------
+# clocks
+# ---------------------------------------------------------------------------
+
+class ClockSampler:
+    Q = ('clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,'
+         'clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,'
+         'clocks_event_reasons.sw_power_cap')
+
+    def __init__(self, index):
+        self.rows, self.proc, self.thread, self.index = [], None, None, index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ['nvidia-smi', f'--id={self.index}', f'--query-gpu={self.Q}', '--format=csv,noheader,nounits', '-lms', '100'],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except OSError:
+            return
+        self.thread = threading.Thread(target=self._read, daemon=True)
+        self.thread.start()
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return None
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
+        for r in self.rows:
+            p = [x.strip() for x in r.split(',')]
+            if len(p) < 7:
+                continue
+            try:
+                sm.append(float(p[0])); mx.append(float(p[1]))
+            except ValueError:
+                continue
+            for n, v in zip(names, p[3:7]):
+                if v.lower().startswith('active'):
+                    reasons.add(n)
+        if not sm:
+            return None
+        return {'sm_mhz': statistics.median(sm), 'sm_max_mhz': max(mx), 'reasons': sorted(reasons),
+                'samples': len(sm)}
+
+
+# ---------------------------------------------------------------------------
+# GPU side
+# ---------------------------------------------------------------------------
+
+def algorithmic_bytes_em(B):
+    """SURVEY.md section 8d, per launch of the fused EM kernel: per-iteration
+    covariance + E-step streams x iterations (c = 8 B complex64, r = 4 B float32)."""
+    c, r = 8, 4
+    D, T, F, K, it = CFG['D'], CFG['T'], CFG['F'], CFG['K'], CFG['em_iterations']
+    cov = F * (D * T * c + 2 * K * T * r + K * D * D * c)
+    est = F * (D * T * c + K * D * D * c + K * D * r + K * T * 1 + 2 * K * T * r)
+    fused_min = F * D * T * c + K * T + F * K * T * r
+    return B * it * (cov + est), B * fused_min
+
+
+def run_gpu(args):
+    import torch
+    from pb_chime5_b200 import _lib, core, ops, sharding, synth
+
+    rank, world = sharding.init_process_group()
+    local = int(os.environ.get('LOCAL_RANK', 0))
+    torch.cuda.set_device(local)
+    dev = torch.device('cuda', local)
+    c = CFG
+    B = args.batch
+    enh = core.get_enhancer(wpe=True, wpe_tabs=c['taps'], wpe_delay=c['delay'], wpe_iterations=c['wpe_iterations'],
+                            bss_iterations=c['em_iterations'], bf=c['bf'])
+
+    # two distinct host batches (pinned), alternated between steps; each is B*93 MB >> L2
+    nsets = 2
+    host_obs, host_act = [], []
+    for s in range(nsets):
+        obs, act = synth.make_batch(1000 * (rank + 1) + 100 * s, B, D=c['D'], T=c['T'], F=c['F'], K=c['K'])
+        host_obs.append(torch.from_numpy(obs).pin_memory())
+        host_act.append(torch.from_numpy(act.astype(np.uint8)))
+    dev_obs = [h.to(dev) for h in host_obs]
+    dev_act = [h.to(dev) for h in host_act]
+    ti = torch.zeros(B, dtype=torch.int32, device=dev)
+    ctx = torch.full((B,), c['ctx_frames'], dtype=torch.int32, device=dev)
+    out_host = {'X_hat': torch.empty((B, c['T'], c['F']), dtype=torch.complex64, pin_memory=True),
+                'masks': torch.empty((B, c['K'], c['T'], c['F']), dtype=torch.float32, pin_memory=True)}
+
+    em_events = []
+
+    def step_device(i, time_em=False):
+        """Whole hot path, inputs resident in HBM in the reference layout (B,D,T,F)."""
+        s = i % nsets
+        Y = ops.pack_dtf_to_fdt(dev_obs[s])
+        if enh.wpe_block is not None:
+            Y = enh.wpe_block._run(Y)
+        if time_em:
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+        post = enh.gss_block._run(Y, dev_act[s])
+        if time_em:
+            e1.record()
+            em_events.append((e0, e1))
+        X = enh.bf_block._run_from_posterior(Y, post, ti, ctx, ctx)
+        return ops.unpack_ft_to_tf(X), ops.unpack_fkt_to_ktf(post)
+
+    def step_e2e(i):
+        s = i % nsets
+        return enh.enhance_stft_host(host_obs[s], host_act[s], ti, ctx, ctx, out=out_host)
+
+    def timed(fn, steps, **kw):
+        sharding.barrier()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(steps):
+            fn(i, **kw)
+        e1.record()
+        torch.cuda.synchronize()
+        sharding.barrier()
+        return sharding.max_over_ranks(e0.elapsed_time(e1) * 1e-3, dev)
+
+    for i in range(args.warmup):
+        step_device(i)
+    torch.cuda.synchronize()
+    sampler = ClockSampler(local) if rank == 0 else None
+    if sampler:
+        sampler.start()
+    l0 = _lib.lib().gss_launch_count()
+    sec = timed(step_device, args.steps, time_em=True)
+    launches = _lib.lib().gss_launch_count() - l0
+    clocks = sampler.stop() if sampler else None
+    em_ms = statistics.mean(a.elapsed_time(b) for a, b in em_events)
+
+    for i in range(min(args.warmup, 2)):
+        step_e2e(i)
+    sec_e2e = timed(step_e2e, args.steps)
+
+    total_utts = world * B * args.steps
+    value = total_utts / sec
+    e2e_value = total_utts / sec_e2e
+    h2d = host_obs[0].numel() * 8 + host_act[0].numel() + 3 * 4 * B
+    d2h = out_host['X_hat'].numel() * 8 + out_host['masks'].numel() * 4
+
+    peaks_file = ROOT / 'MEASURED_PEAKS.json'
+    if peaks_file.exists():
+        peak, peak_src = json.loads(peaks_file.read_text())['hbm_gbs'], 'measured (MEASURED_PEAKS.json hbm_gbs)'
+    else:
+        peak, peak_src = 6650.0, 'fallback (B200_PROFILING.md)'
+    alg_bytes, fused_min = algorithmic_bytes_em(B)
+    achieved = alg_bytes / (em_ms * 1e-3) / 1e9
+    traffic = None
+    tfile = ROOT / 'profiles' / 'em_kernel_traffic.json'
+    if tfile.exists():
+        try:
+            traffic = json.loads(tfile.read_text()).get('dram_bytes_per_launch')
+        except Exception:
+            traffic = None
+
+    if rank != 0:
+        return
+    line = {
+        'metric': METRIC, 'value': value, 'unit': 'utterances/s', 'n_gpus': world,
+        'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': 1e3 * sec / args.steps,
+        'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f64',
+        'data': 'synthetic',
+        'config': {'workload': WORKLOAD, 'batch_per_gpu': B,
+                   'l2': f'inputs {B * 93} MB per step per GPU > 126 MB L2, two input sets alternated',
+                   'value_region': 'inputs resident in HBM in the reference layout (B,D,T,F); timed: pack, WPE, EM, beamformer, unpack',
+                   'arithmetic': 'complex64 storage, float64 arithmetic'},
+        'e2e': {'value': e2e_value, 'unit': 'utterances/s', 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h,
+                'ms_per_step': 1e3 * sec_e2e / args.steps,
+                'api': 'Enhancer.enhance_stft_host (pinned host STFT in, X_hat + masks out)'},
+        'gpu_launches': int(launches),
+        'roofline': {'kernel': 'cacgmm_em_kernel (fused EM, all iterations)', 'bound': 'hbm',
+                     'achieved': achieved, 'peak': peak, 'unit': 'GB/s', 'frac': achieved / peak,
+                     'traffic': traffic, 'peak_source': peak_src,
+                     'algorithmic_bytes_per_launch': alg_bytes,
+                     'fused_minimum_bytes_per_launch': fused_min,
+                     'kernel_ms': em_ms,
+                     'note': 'declared variant: per-iteration covariance+E-step streams x 100 iterations (SURVEY 8d); '
+                             'the kernel is FP64-pipe bound at D=24, see DESIGN.md'},
+        'clocks': clocks,
+    }
+    if world == 1 and not args.no_cpu:
+        import multiprocessing as mp
+        procs = os.cpu_count() or 1
+        with mp.get_context('fork').Pool(procs) as pool:
+            v, wall = cpu_sample(pool, procs, args.cpu_bins, 30_000)
+        line['cpu_baseline'] = {
+            'value': v, 'unit': 'utterances/s', 'cores': procs, 'kind': 'port',
+            'sample': f'{procs} processes x {args.cpu_bins} of 513 bins, all iterations, scaled by 513/{args.cpu_bins}; '
+                      f'{wall:.1f} s wall'}
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=4)
+    ap.add_argument('--warmup', type=int, default=3)
+    ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
+    ap.add_argument('--batch', type=int, default=4, help='utterances per GPU per step')
+    ap.add_argument('--cpu-bins', type=int, default=1, help='frequency bins per process in a CPU sample')
+    ap.add_argument('--no-cpu', action='store_true')
+    args = ap.parse_args()
+    if args.impl == 'reference':
+        run_reference(args)
+    else:
+        run_gpu(args)
+
+
+if __name__ == '__main__':
+    main()

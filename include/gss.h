@@ -71,6 +71,8 @@ typedef struct { float re, im; } gss_c64;
 
 int gss_version(void);
 const char* gss_last_error(void);
+/* Number of libgss kernels launched by this process so far (bench bookkeeping). */
+long long gss_launch_count(void);
 
 /* Scratch size for one call of `op` with these dimensions (L = WPE taps). */
 int gss_workspace_bytes(int op, int B, int F, int D, int T, int K, int L, size_t* out);

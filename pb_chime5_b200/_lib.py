@@ -35,6 +35,7 @@ _sz = C.c_size_t
 _SIGNATURES = {
     'gss_version': (_i, []),
     'gss_last_error': (C.c_char_p, []),
+    'gss_launch_count': (C.c_longlong, []),
     'gss_workspace_bytes': (_i, [_i, _i, _i, _i, _i, _i, _i, C.POINTER(_sz)]),
     'gss_pack_dtf_to_fdt_c64': (_i, [_p, _p, _i, _i, _i, _i, _p]),
     'gss_unpack_fdt_to_dtf_c64': (_i, [_p, _p, _i, _i, _i, _i, _p]),

@@ -1,0 +1,550 @@
+"""Host-side mirror of the reference's block interface (pb_chime5/core.py:41-637).
+
+Same class names, constructor fields, call signatures, defaults and error
+behaviour as the reference, so that ``pb_chime5/scripts/run.py`` works with only
+its import target changed.  Every numeric step is a libgss
+CUDA kernel reached through ``pb_chime5_b200.ops``; nothing here computes on the
+CPU except the boolean activity framing (a4 in SURVEY.md section 8) and shape
+bookkeeping.
+
+Array conventions at this boundary are the reference's:  ``Obs`` (D, T, F)
+complex, ``acitivity_freq`` (K, T) bool, masks (K, T, F) / (T, F) float,
+``X_hat`` (T, F) complex.  NumPy in -> NumPy out (complex128 / float64 like the
+reference); ``torch`` CUDA tensors in -> CUDA tensors out (complex64 / float32,
+no host round trip).
+"""
+from __future__ import annotations
+
+import inspect
+from dataclasses import dataclass
+from functools import cached_property
+from pathlib import Path
+
+import numpy as np
+import torch
+
+from . import ops
+
+JSON_PATH = Path(__file__).resolve().parent.parent / 'cache'
+
+
+# ---------------------------------------------------------------------------
+# host <-> device plumbing
+# ---------------------------------------------------------------------------
+
+def _device():
+    if not torch.cuda.is_available():
+        raise RuntimeError('pb_chime5_b200 needs a CUDA device (there is no CPU fallback)')
+    return torch.device('cuda', torch.cuda.current_device())
+
+
+def _to_device(x, dtype):
+    """NumPy / torch (any device) -> contiguous CUDA tensor of `dtype`; returns (tensor, was_numpy)."""
+    if isinstance(x, torch.Tensor):
+        return x.to(device=_device(), dtype=dtype).contiguous(), False
+    a = np.asarray(x)
+    if dtype == torch.complex64:
+        a = a.astype(np.complex64, copy=False)
+    elif dtype == torch.float32:
+        a = a.astype(np.float32, copy=False)
+    return torch.from_numpy(np.ascontiguousarray(a)).to(_device()), True
+
+
+def _from_device(t, was_numpy, np_dtype):
+    if not was_numpy:
+        return t
+    return t.cpu().numpy().astype(np_dtype, copy=False)
+
+
+def samples_to_stft_frames(samples, size, shift, *, pad=True, fading=False):
+    """nara_wpe.utils._samples_to_stft_frames (call site core.py:224-237)."""
+    if fading:
+        samples = samples + 2 * (size - shift)
+    frames = (samples - size + shift) / shift
+    return int(np.ceil(frames)) if pad else int(np.floor(frames))
+
+
+def activity_time_to_frequency(time_activity, stft_window_length, stft_shift, stft_fading, stft_pad=True):
+    """Sample-level activity -> frame-level activity ("any sample of the frame").
+    Host-side boolean bookkeeping; pb_chime5/database/chime5/database.py:409-472."""
+    a = np.asarray(time_activity)
+    assert a.dtype != object, (type(time_activity), a.dtype)
+    a = a != 0
+    if stft_fading:
+        p = stft_window_length - stft_shift
+        a = np.pad(a, [(0, 0)] * (a.ndim - 1) + [(p, p)], mode='constant')
+    n = a.shape[-1]
+    if stft_pad:
+        extra = (stft_window_length - n) if n < stft_window_length else (-(n - stft_window_length)) % stft_shift
+        if extra:
+            a = np.pad(a, [(0, 0)] * (a.ndim - 1) + [(0, extra)], mode='constant')
+        n = a.shape[-1]
+    count = (n - stft_window_length) // stft_shift + 1
+    # any() over each frame through a cumulative count (no (T, size) gather)
+    c = np.concatenate([np.zeros(a.shape[:-1] + (1,), dtype=np.int64), np.cumsum(a, axis=-1)], axis=-1)
+    starts = stft_shift * np.arange(count)
+    return (c[..., starts + stft_window_length] - c[..., starts]) > 0
+
+
+# ---------------------------------------------------------------------------
+# blocks
+# ---------------------------------------------------------------------------
+
+@dataclass
+class WPE:
+    """Dereverberation block.  Reference: pb_chime5/core.py:41-88."""
+    taps: int
+    delay: int
+    iterations: int
+    psd_context: int
+
+    def _run(self, Y):
+        """Y (B,F,D,T) complex64 on the device -> same shape."""
+        return ops.wpe(Y, self.taps, self.delay, self.iterations, self.psd_context)
+
+    def __call__(self, Obs, stack=None, debug=False):
+        ndim = Obs.ndim
+        if ndim == 3:
+            assert stack is None, stack
+            x, was_np = _to_device(Obs, torch.complex64)                 # (D,T,F)
+            out = ops.unpack_fdt_to_dtf(self._run(ops.pack_dtf_to_fdt(x[None])))[0]
+        elif ndim == 4:
+            x, was_np = _to_device(Obs, torch.complex64)                 # (A,C,T,F)
+            A, C, T, F = x.shape
+            if stack is True:
+                merged = x.reshape(1, A * C, T, F)
+                out = ops.unpack_fdt_to_dtf(self._run(ops.pack_dtf_to_fdt(merged)))[0].reshape(A, C, T, F)
+            elif stack is False:
+                out = ops.unpack_fdt_to_dtf(self._run(ops.pack_dtf_to_fdt(x)))   # arrays are independent batches
+            else:
+                raise NotImplementedError(stack)
+        else:
+            raise NotImplementedError(Obs.shape)
+        out = _from_device(out, was_np, np.complex128)
+        if debug:
+            self.locals = dict(Obs=Obs, stack=stack, out=out)
+        return out
+
+
+@dataclass
+class Activity:
+    """Where the per-session speaker activity comes from (metadata, not on the
+    numeric path).  Reference: pb_chime5/core.py:91-141.  The CHiME-5 database
+    code is out of scope here and is taken from the reference package when it is
+    importable."""
+    type: str = 'annotation'
+    garbage_class: bool = False
+    database_path: str = str(JSON_PATH / 'chime5.json')
+    path: str = None
+
+    @cached_property
+    def db(self):
+        try:
+            from pb_chime5.database.chime5 import Chime5
+        except ImportError as e:   # pragma: no cover - needs the reference package
+            raise RuntimeError(
+                'Activity.db needs the CHiME-5 database classes of the reference package '
+                '(pb_chime5.database); install fgnt/pb_chime5 next to pb_chime5_b200.') from e
+        return Chime5(self.database_path)
+
+    def __getitem__(self, session_id):
+        if self.type == 'annotation':
+            return _annotation_activity(session_id, self.db, self.garbage_class)
+        if self.type == 'path':
+            import pickle
+            with open(Path(self.path) / f'{session_id}.pkl', 'rb') as fd:
+                return pickle.load(fd)
+        raise ValueError(self.type)
+
+
+_ACTIVITY_CACHE = {}
+
+
+def _annotation_activity(session_id, db, garbage_class):
+    key = (session_id, id(db), garbage_class)
+    if key not in _ACTIVITY_CACHE:
+        from pb_chime5.activity import get_activity   # reference metadata code
+        _ACTIVITY_CACHE.clear()                        # keep one session, like lru_cache(1)
+        _ACTIVITY_CACHE[key] = get_activity(
+            iterator=db.get_datasets(session_id), perspective='array',
+            garbage_class=garbage_class, dtype=bool, non_sil_alignment_fn=None,
+            debug=False, use_ArrayIntervall=True)[session_id]
+    return _ACTIVITY_CACHE[key]
+
+
+@dataclass
+class GSS:
+    """Guided source separation: activity-initialised and -constrained CACGMM EM
+    per frequency bin.  Reference: pb_chime5/core.py:144-214."""
+    iterations: int
+    iterations_post: int
+    verbose: bool = True
+
+    def _run(self, Y, activity):
+        """Y (B,F,D,T) c64, activity (B,K,T_act) uint8/bool -> posterior (B,F,K,T) f32."""
+        return ops.cacgmm(Y, activity, self.iterations, self.iterations_post)
+
+    def __call__(self, Obs, acitivity_freq, debug=False):
+        x, was_np = _to_device(Obs, torch.complex64)                     # (D,T,F)
+        assert x.ndim == 3, x.shape
+        act = torch.as_tensor(np.asarray(acitivity_freq) != 0 if not isinstance(acitivity_freq, torch.Tensor)
+                              else acitivity_freq != 0).to(device=x.device, dtype=torch.uint8)
+        assert act.ndim == 2, act.shape
+        if self.iterations_post == 0:
+            # the reference passes an unsupported keyword to CACGMM.predict here (core.py:198-202)
+            raise TypeError("predict() got an unexpected keyword argument 'source_activity_mask'")
+        Y = ops.pack_dtf_to_fdt(x[None])
+        post = self._run(Y, act[None])
+        out = ops.unpack_fkt_to_ktf(post)[0]                              # (K,T,F)
+        out = _from_device(out, was_np, np.float64)
+        if debug:
+            self.locals = dict(Obs=Obs, acitivity_freq=acitivity_freq, posterior=out)
+        return out
+
+
+def start_end_context_frames(ex, stft_size, stft_shift, stft_fading):
+    """Context length of an example in STFT frames.  Reference: core.py:217-238."""
+    start_context_samples = ex['start_orig']['original'] - ex['start']['original']
+    end_context_samples = ex['end']['original'] - ex['end_orig']['original']
+    assert start_context_samples >= 0, (start_context_samples, ex)
+    assert end_context_samples >= 0, (end_context_samples, ex)
+    return (samples_to_stft_frames(start_context_samples, stft_size, stft_shift, fading=stft_fading),
+            samples_to_stft_frames(end_context_samples, stft_size, stft_shift, fading=stft_fading))
+
+
+@dataclass
+class Beamformer:
+    """Mask-based beamformer.  Reference: pb_chime5/core.py:241-278.  In addition
+    to the reference's 'mvdrSouden_ban' | 'ch2' | 'sum' the wrapper-level GEV of
+    beamforming_wrapper.py:192-208 is selectable as 'gev_ban'."""
+    type: str
+    postfilter: str
+
+    def _bf_args(self):
+        bf = self.type
+        if bf in ('mvdrSouden_ban', 'gev_ban', 'mvdrSouden', 'gev'):
+            return bf, 0
+        if bf == 'ch2':
+            return 'ch', 2
+        if bf == 'sum':
+            return 'sum', 0
+        raise NotImplementedError(bf)
+
+    def _check_postfilter(self):
+        if self.postfilter not in (None, 'mask_mul'):
+            raise NotImplementedError(self.postfilter)
+
+    def _run(self, Y, target_mask, distortion_mask):
+        """Y (B,F,D,T); masks (B,F,T) f32 -> X_hat (B,F,T) c64."""
+        bf, arg = self._bf_args()
+        self._check_postfilter()
+        return ops.beamform(Y, target_mask, distortion_mask, bf=bf, postfilter=self.postfilter, bf_arg=arg)
+
+    def _run_from_posterior(self, Y, posterior, target_index, start_ctx, end_ctx):
+        bf, arg = self._bf_args()
+        self._check_postfilter()
+        return ops.beamform_from_posterior(Y, posterior, target_index, start_ctx, end_ctx, bf=bf,
+                                           postfilter=self.postfilter, bf_arg=arg)
+
+    def __call__(self, Obs, target_mask, distortion_mask, debug=False):
+        self._bf_args()
+        self._check_postfilter()
+        x, was_np = _to_device(Obs, torch.complex64)
+        if x.ndim == 4:                       # '1DTF' (beamforming_wrapper.py:21-22)
+            assert x.shape[0] == 1, x.shape
+            x = x[0]
+        D, T, F = x.shape
+
+        def mask_ft(m):
+            m, _ = _to_device(m, torch.float32)
+            if m.ndim == 4:
+                assert m.shape[0] == 1, m.shape
+                m = m[0]
+            if m.ndim == 3:                   # (D,T,F): median over the channels (beamforming_wrapper.py:28-30)
+                m = m.median(dim=0).values if m.shape[0] % 2 else \
+                    0.5 * (m.kthvalue(m.shape[0] // 2, dim=0).values + m.kthvalue(m.shape[0] // 2 + 1, dim=0).values)
+            assert m.shape == (T, F), (m.shape, T, F)
+            return m.t().contiguous()[None]   # (1,F,T)
+
+        Y = ops.pack_dtf_to_fdt(x[None])
+        X = self._run(Y, mask_ft(target_mask), mask_ft(distortion_mask))
+        out = ops.unpack_ft_to_tf(X)[0]
+        out = _from_device(out, was_np, np.complex128)
+        if debug:
+            self.locals = dict(Obs=Obs, target_mask=target_mask, distortion_mask=distortion_mask, X_hat=out)
+        return out
+
+
+@dataclass
+class Enhancer:
+    """STFT -> WPE -> GSS -> context drop -> beamformer -> iSTFT.
+    Reference: pb_chime5/core.py:281-571."""
+    wpe_block: WPE
+    activity: Activity
+    gss_block: GSS
+    bf_block: Beamformer
+
+    bf_drop_context: bool
+
+    stft_size: int
+    stft_shift: int
+    stft_fading: bool
+
+    context_samples: int
+    multiarray: bool
+    reference_array: [None, str]
+
+    @property
+    def db(self):
+        return self.activity.db
+
+    # ---- transforms (reference layout) -------------------------------------
+    def stft(self, x):
+        """(..., N) real -> (..., T, F) complex.  core.py:305-312."""
+        t, was_np = _to_device(x, torch.float32)
+        lead = t.shape[:-1]
+        Y = ops.stft(t.reshape(1, -1, t.shape[-1]), self.stft_size, self.stft_shift, self.stft_fading)
+        out = Y[0].permute(1, 2, 0).reshape(*lead, Y.shape[3], Y.shape[1])
+        return _from_device(out.contiguous(), was_np, np.complex128)
+
+    def istft(self, X):
+        """(..., T, F) complex -> (..., samples).  core.py:314-321."""
+        t, was_np = _to_device(X, torch.complex64)
+        lead = t.shape[:-2]
+        Xb = t.reshape(-1, t.shape[-2], t.shape[-1]).permute(0, 2, 1).contiguous()      # (B,F,T)
+        out = ops.istft(Xb, self.stft_size, self.stft_shift, self.stft_fading)
+        return _from_device(out.reshape(*lead, out.shape[-1]), was_np, np.float64)
+
+    # ---- the device-resident hot path ---------------------------------------
+    def enhance_stft_batch(self, Y, activity_freq, target_index, start_ctx, end_ctx, return_masks=False):
+        """Y (B,F,D,T) complex64 CUDA (bin-major), activity_freq (B,K,T_act) uint8,
+        target_index / start_ctx / end_ctx (B) int32 -> X_hat (B,F,T) complex64
+        [, posterior (B,F,K,T) float32].  core.py:524-564 without host round trips."""
+        if self.wpe_block is not None:
+            Y = self.wpe_block._run(Y)
+        post = self.gss_block._run(Y, activity_freq)
+        if not self.bf_drop_context:
+            start_ctx = end_ctx = None
+        X = self.bf_block._run_from_posterior(Y, post, target_index, start_ctx, end_ctx)
+        return (X, post) if return_masks else X
+
+    def enhance_stft_host(self, Obs, acitivity_freq, target_index, start_ctx=None, end_ctx=None,
+                          out=None, return_masks=True):
+        """Batched hot path on HOST buffers in the reference layout: Obs (B,D,T,F)
+        complex64 (pinned torch tensor or NumPy), acitivity_freq (B,K,T_act) bool,
+        target_index / start_ctx / end_ctx (B) ints.  Returns host tensors
+        X_hat (B,T,F) complex64 and, optionally, masks (B,K,T,F) float32 (context
+        frames NOT zeroed, i.e. the posterior as GSS returns it).  Copies in and out
+        are issued on the current stream; the call returns after the results landed.
+        `out` = optional dict of preallocated pinned host tensors {'X_hat', 'masks'}."""
+        dev = _device()
+        obs_h = Obs if isinstance(Obs, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(Obs))
+        assert obs_h.dtype == torch.complex64 and obs_h.ndim == 4, (obs_h.dtype, obs_h.shape)
+        B, D, T, F = obs_h.shape
+        x = obs_h.to(dev, non_blocking=True)
+        act = torch.as_tensor(acitivity_freq).to(torch.uint8).to(dev, non_blocking=True)
+        ivec = lambda v: None if v is None else torch.as_tensor(v, dtype=torch.int32).to(dev, non_blocking=True)
+        Y = ops.pack_dtf_to_fdt(x)
+        X, post = self.enhance_stft_batch(Y, act, ivec(target_index), ivec(start_ctx), ivec(end_ctx),
+                                          return_masks=True)
+        X_tf = ops.unpack_ft_to_tf(X)
+        if out is None:
+            out = {}
+        xh = out.get('X_hat')
+        if xh is None:
+            xh = torch.empty(X_tf.shape, dtype=X_tf.dtype, pin_memory=True)
+        xh.copy_(X_tf, non_blocking=True)
+        res = {'X_hat': xh}
+        if return_masks:
+            m_ktf = ops.unpack_fkt_to_ktf(post)
+            mh = out.get('masks')
+            if mh is None:
+                mh = torch.empty(m_ktf.shape, dtype=m_ktf.dtype, pin_memory=True)
+            mh.copy_(m_ktf, non_blocking=True)
+            res['masks'] = mh
+        torch.cuda.current_stream().synchronize()
+        return res
+
+    def enhance_observation(self, obs, ex_array_activity, speaker_id, ex=None, debug=False):
+        """obs (D, N) samples, ex_array_activity {speaker: (N,) bool} -> x_hat (N',).
+        core.py:514-571."""
+        t, was_np = _to_device(obs, torch.float32)
+        assert t.ndim == 2, t.shape
+        Y = ops.stft(t[None], self.stft_size, self.stft_shift, self.stft_fading)        # (1,F,D,T)
+        T = Y.shape[3]
+        acitivity_freq = activity_time_to_frequency(
+            np.array([np.asarray(v) for v in ex_array_activity.values()]),
+            stft_window_length=self.stft_size, stft_shift=self.stft_shift,
+            stft_fading=self.stft_fading, stft_pad=True)
+        act = torch.from_numpy(acitivity_freq.astype(np.uint8))[None].to(Y.device)
+        target_speaker_index = tuple(ex_array_activity.keys()).index(speaker_id)
+        sc = ec = 0
+        if self.bf_drop_context:
+            sc, ec = start_end_context_frames(ex, stft_size=self.stft_size, stft_shift=self.stft_shift,
+                                              stft_fading=self.stft_fading)
+        ivec = lambda v: torch.tensor([v], dtype=torch.int32, device=Y.device)
+        X, post = self.enhance_stft_batch(Y, act, ivec(target_speaker_index), ivec(sc), ivec(min(ec, T)),
+                                          return_masks=True)
+        x_hat = ops.istft(X, self.stft_size, self.stft_shift, self.stft_fading)[0]
+        if debug:
+            masks = ops.unpack_fkt_to_ktf(post)[0].cpu().numpy().astype(np.float64)
+            if self.bf_drop_context:
+                masks[:, :sc, :] = 0
+                if ec > 0:
+                    masks[:, -ec:, :] = 0
+            self.enhance_observation_locals = dict(
+                acitivity_freq=acitivity_freq, masks=masks,
+                target_mask=masks[target_speaker_index],
+                distortion_mask=np.sum(np.delete(masks, target_speaker_index, axis=0), axis=0),
+                X_hat=ops.unpack_ft_to_tf(X)[0].cpu().numpy(), x_hat=x_hat.cpu().numpy())
+        return _from_device(x_hat, was_np, np.float64)
+
+    # ---- data plumbing (out of the hot path; uses the reference's I/O code) --
+    def get_iterator(self, session_id):
+        return self.db.get_iterator_for_session(
+            session_id, audio_read=False, adjust_times=True, drop_unknown_target_speaker=True,
+            context_samples=self.context_samples, equal_start_context=True)
+
+    def enhance_session(self, session_ids, audio_dir, dataset_slice=False, audio_dir_exist_ok=False):
+        """core.py:333-394.  Work distribution: one process per GPU; rank r of W takes
+        the examples i with i % W == r (the task farm of dlp_mpi.split_managed becomes
+        a static shard, see pb_chime5_b200/sharding.py)."""
+        from pb_chime5 import mapping
+        from pb_chime5.io import dump_audio
+        from . import sharding
+
+        audio_dir = Path(audio_dir)
+        it = self.get_iterator(session_ids)
+        rank, world = sharding.rank_world()
+        if rank == 0:
+            audio_dir.mkdir(exist_ok=audio_dir_exist_ok)
+            for dataset in set(mapping.session_to_dataset.values()):
+                (audio_dir / dataset).mkdir(exist_ok=audio_dir_exist_ok)
+        sharding.barrier()
+        if dataset_slice is not False:
+            if dataset_slice is True:
+                it = it[:2]
+            elif isinstance(dataset_slice, int):
+                it = it[:dataset_slice]
+            elif isinstance(dataset_slice, slice):
+                it = it[dataset_slice]
+            else:
+                raise ValueError(dataset_slice)
+        for i in sharding.shard_indices(len(it), rank, world):
+            ex = it[i]
+            x_hat = self.enhance_example(ex)
+            dataset = mapping.session_to_dataset[ex['session_id']]
+            if x_hat.ndim == 1:
+                dump_audio(x_hat, audio_dir / f'{dataset}' / f'{ex["example_id"]}.wav')
+            else:
+                raise NotImplementedError(x_hat.shape)
+
+    def enhance_example(self, ex, debug=False):
+        """core.py:396-512: slice the activity, load the audio of the selected arrays,
+        enhance, cut the context."""
+        from pb_chime5.io import load_audio
+
+        session_id = ex['session_id']
+        reference_array = self.reference_array
+        if reference_array is None:
+            try:
+                reference_array = ex['reference_array']
+            except KeyError:
+                raise RuntimeError(
+                    'Failed to get the "reference_array" from the example.\n'
+                    'Probably you tried to enhance the "train" dataset.\n'
+                    'Train has no "reference_array".\n'
+                    'You can set a "reference_array" from the commandline with\n'
+                    '\tpython -m ... with ... reference_array=U06\n'
+                    'In case of multiarray, the reference array is used for the'
+                    'projection of the human annotations.') from None
+        speaker_id = ex['speaker_id']
+        array_start = ex['start']['observation'][reference_array]
+        array_end = ex['end']['observation'][reference_array]
+        ex_array_activity = {
+            k: arr[array_start:min(array_end, len(arr))]
+            for k, arr in self.activity[session_id][reference_array].items()}
+
+        def load(array):
+            return load_audio(ex['audio_path']['observation'][array],
+                              start=ex['start']['observation'][array],
+                              stop=ex['end']['observation'][array])
+
+        selectors = {True: slice(None), 'outer_array_mics': (0, -1), 'first_array_mics': (0,)}
+        if self.multiarray is False:
+            obs = load(reference_array)
+        elif self.multiarray in selectors and self.multiarray is not False:
+            arrays = [load(a) for a in sorted(ex['audio_path']['observation'].keys())]
+            assert {v.ndim for v in arrays} == {2}, [v.shape for v in arrays]
+            n = min(v.shape[-1] for v in arrays)       # arrays may differ in length by a few samples
+            sel = selectors[self.multiarray]
+            obs = np.concatenate([v[sel, :n] for v in arrays], axis=0)     # 'ACN->A*CN'
+        else:
+            raise ValueError(self.multiarray)
+
+        x_hat = self.enhance_observation(obs, ex_array_activity=ex_array_activity,
+                                         speaker_id=speaker_id, ex=ex, debug=debug)
+        if self.context_samples > 0:
+            start_orig = ex['start_orig']['observation'][reference_array]
+            start = ex['start']['observation'][reference_array]
+            start_context = start_orig - start
+            num_samples_orig = ex['num_samples_orig']['observation'][reference_array]
+            x_hat = x_hat[..., start_context:start_context + num_samples_orig]
+        if debug:
+            self.enhance_example_locals = dict(obs=obs, ex_array_activity=ex_array_activity, x_hat=x_hat)
+        return x_hat
+
+
+def get_enhancer(
+    multiarray=False,
+    reference_array=None,
+    context_samples=240000,
+
+    wpe=True,
+    wpe_tabs=10,
+    wpe_delay=2,
+    wpe_iterations=3,
+    wpe_psd_context=0,
+
+    activity_type='annotation',
+    activity_path=None,
+    activity_garbage_class=True,
+
+    stft_size=1024,
+    stft_shift=256,
+    stft_fading=True,
+
+    bss_iterations=20,
+    bss_iterations_post=1,
+
+    bf_drop_context=True,
+
+    bf='mvdrSouden_ban',
+    postfilter=None,
+
+    database_path=str(JSON_PATH / 'chime5.json'),
+):
+    """Factory with the reference's keyword names and defaults (core.py:574-637);
+    sacred builds its config from this signature (scripts/run.py:19-27)."""
+    assert wpe is True or wpe is False, wpe
+    assert activity_path is None or activity_type == 'path', (activity_path, activity_type)
+    return Enhancer(
+        multiarray=multiarray,
+        reference_array=reference_array,
+        context_samples=context_samples,
+        wpe_block=WPE(taps=wpe_tabs, delay=wpe_delay, iterations=wpe_iterations,
+                      psd_context=wpe_psd_context) if wpe else None,
+        activity=Activity(type=activity_type, garbage_class=activity_garbage_class,
+                          path=activity_path, database_path=database_path),
+        gss_block=GSS(iterations=bss_iterations, iterations_post=bss_iterations_post, verbose=False),
+        bf_drop_context=bf_drop_context,
+        bf_block=Beamformer(type=bf, postfilter=postfilter),
+        stft_size=stft_size,
+        stft_shift=stft_shift,
+        stft_fading=stft_fading,
+    )
+
+
+def signature_defaults():
+    """{kwarg: default} of get_enhancer, as scripts/run.py:23-25 reads it."""
+    return {k: v.default for k, v in inspect.signature(get_enhancer).parameters.items()}

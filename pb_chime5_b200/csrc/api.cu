@@ -2,6 +2,7 @@
 // dispatch.  No torch types, no exceptions across the boundary.
 #include "common.cuh"
 #include <cstring>
+#include <atomic>
 
 namespace gss {
 
@@ -20,6 +21,10 @@ int check_cuda(cudaError_t e, const char* what) {
     if (e == cudaSuccess) return GSS_OK;
     return fail(GSS_ERR_CUDA, "%s: %s", what, cudaGetErrorString(e));
 }
+
+static std::atomic<long long> g_launches{0};
+void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
+long long launches() { return g_launches.load(); }
 
 int num_sms() {
     static int n = 0;
@@ -62,6 +67,7 @@ int gss_workspace_bytes(int op, int B, int F, int D, int T, int K, int L, size_t
 }
 
 int gss_version(void) { return 100; }   // 0.1.0
+long long gss_launch_count(void) { return gss::launches(); }
 const char* gss_last_error(void) { return gss::last_error_buf(); }
 
 }  // extern "C"

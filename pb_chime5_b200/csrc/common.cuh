@@ -13,13 +13,14 @@ namespace gss {
 char* last_error_buf();
 int fail(int code, const char* fmt, ...);
 int check_cuda(cudaError_t e, const char* what);
+void count_launch();   // kernel launch counter (gss_launch_count)
 
 #define GSS_REQUIRE(cond, code, ...) \
     do { if (!(cond)) return ::gss::fail((code), __VA_ARGS__); } while (0)
 #define GSS_CUDA(expr) \
     do { int _rc = ::gss::check_cuda((expr), #expr); if (_rc) return _rc; } while (0)
 #define GSS_LAUNCH_CHECK(name) \
-    do { int _rc = ::gss::check_cuda(cudaGetLastError(), name); if (_rc) return _rc; } while (0)
+    do { ::gss::count_launch(); int _rc = ::gss::check_cuda(cudaGetLastError(), name); if (_rc) return _rc; } while (0)
 
 static inline size_t align_up(size_t x, size_t a = 256) { return (x + a - 1) / a * a; }
 

@@ -1,0 +1,215 @@
+"""GPU: the reference-shaped block interface (pb_chime5_b200.core) against the
+reference fixtures / the oracle, including the edge cases of SURVEY.md 7.3-8."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import gss_oracle as oracle
+from pb_chime5_b200 import core, ops, synth
+
+pytestmark = pytest.mark.gpu
+
+
+def rel_err(a, b):
+    return float(np.abs(a - b).max() / max(np.abs(b).max(), 1e-30))
+
+
+@pytest.fixture(autouse=True)
+def _need_cuda(cuda):
+    torch.cuda.set_device(cuda)
+
+
+def test_blocks_numpy_in_numpy_out(golden_dir):
+    g = np.load(golden_dir / 'gss_d8_k4.npz')
+    Obs = g['Obs'].astype(np.complex128)
+    post = core.GSS(iterations=int(g['iterations']), iterations_post=1, verbose=False)(Obs, g['activity'])
+    assert isinstance(post, np.ndarray) and post.dtype == np.float64 and post.shape == g['posterior'].shape
+    assert np.abs(post - g['posterior']).max() < 1e-4
+    X = core.Beamformer('mvdrSouden_ban', None)(Obs, g['target_mask'], g['distortion_mask'])
+    assert X.dtype == np.complex128 and rel_err(X, g['X_mvdr_ban']) < 1e-4
+    Xm = core.Beamformer('mvdrSouden_ban', 'mask_mul')(Obs, g['target_mask'], g['distortion_mask'])
+    assert rel_err(Xm, g['X_mvdr_ban'] * g['target_mask']) < 1e-4
+    assert rel_err(core.Beamformer('ch2', None)(Obs, g['target_mask'], g['distortion_mask']), Obs[2]) < 1e-6
+    assert rel_err(core.Beamformer('sum', None)(Obs, g['target_mask'], g['distortion_mask']), Obs.sum(0)) < 1e-6
+    # torch CUDA in -> CUDA out
+    Xt = core.Beamformer('mvdrSouden_ban', None)(torch.from_numpy(g['Obs']).cuda(),
+                                                  torch.from_numpy(g['target_mask']).cuda(),
+                                                  torch.from_numpy(g['distortion_mask']).cuda())
+    assert Xt.is_cuda and rel_err(Xt.cpu().numpy(), g['X_mvdr_ban']) < 1e-4
+
+
+def test_wpe_block_layouts():
+    Obs, _ = synth.make_utterance(21, D=6, T=160, F=4, K=3)
+    Obs[:, 3:, :] += 0.5 * Obs[:, :-3, :]
+    wpe = core.WPE(taps=4, delay=2, iterations=3, psd_context=0)
+    ref = oracle.wpe_dtf(Obs.astype(np.complex128), 4, 2, 3)
+    assert rel_err(wpe(Obs.astype(np.complex128)), ref) < 1e-4
+    # 4-D (A,C,T,F): stack=True merges arrays, stack=False treats them independently (core.py:60-78)
+    Obs4 = Obs.reshape(2, 3, 160, 4)
+    assert rel_err(wpe(Obs4, stack=True), ref.reshape(2, 3, 160, 4)) < 1e-4
+    ref_ind = np.stack([oracle.wpe_dtf(Obs4[a].astype(np.complex128), 4, 2, 3) for a in range(2)])
+    assert rel_err(wpe(Obs4, stack=False), ref_ind) < 1e-4
+    with pytest.raises(NotImplementedError):
+        wpe(Obs4, stack=None)
+    # psd_context > 0
+    ref_c = oracle.wpe_dtf(Obs.astype(np.complex128), 4, 2, 2, psd_context=2)
+    assert rel_err(core.WPE(4, 2, 2, 2)(Obs.astype(np.complex128)), ref_c) < 1e-4
+
+
+@pytest.mark.parametrize('name', ['enh_nowpe', 'enh_wpe'])
+def test_enhance_observation_matches_reference(golden_dir, name):
+    g = np.load(golden_dir / f'{name}.npz')
+    taps, delay, its, ctx = (int(v) for v in g['wpe'])
+    enh = core.get_enhancer(wpe=bool(taps), wpe_tabs=max(taps, 1), wpe_delay=delay, wpe_iterations=its,
+                            bss_iterations=10, context_samples=4000, reference_array='U01')
+    ex = {'start': {'original': 0}, 'start_orig': {'original': 4000},
+          'end': {'original': 20000}, 'end_orig': {'original': 16000}}
+    sact = g['sample_activity']
+    x_hat = enh.enhance_observation(g['obs'].astype(np.float64), {'P01': sact[0], 'P02': sact[1], 'Noise': sact[2]},
+                                    'P01', ex=ex, debug=True)
+    loc = enh.enhance_observation_locals
+    assert np.array_equal(loc['acitivity_freq'], g['activity_freq'])
+    assert np.abs(loc['masks'] - g['masks']).max() < 2e-4
+    assert rel_err(loc['X_hat'], g['X_hat']) < 2e-4
+    assert x_hat.shape == g['x_hat'].shape and rel_err(x_hat, g['x_hat']) < 2e-4
+    # stft / istft methods in the reference layout
+    S = enh.stft(g['obs'].astype(np.float64))
+    assert S.shape == (4, loc['masks'].shape[1], 513)
+    assert rel_err(S, oracle.stft(g['obs'].astype(np.float64))) < 1e-6
+    back = enh.istft(S)
+    assert np.abs(back[:, :20000] - g['obs']).max() < 1e-4
+
+
+def _gss_both(Obs, act, iters, post_iters=1):
+    ref = oracle.gss_posteriors(Obs.astype(np.complex128), act, iters, post_iters)
+    got = core.GSS(iters, post_iters, verbose=False)(Obs.astype(np.complex128), act)
+    return got, ref
+
+
+@pytest.mark.parametrize('D,K', [(2, 2), (3, 3), (5, 4), (6, 6), (7, 3), (12, 5), (16, 3)])
+def test_gss_channel_and_class_counts(D, K):
+    Obs, act = synth.make_utterance(100 + D, D=D, T=140, F=3, K=K)
+    got, ref = _gss_both(Obs, act, 6)
+    assert np.abs(got - ref).max() < 1e-4
+
+
+def test_gss_edge_cases():
+    Obs, act = synth.make_utterance(5, D=4, T=200, F=4, K=3)
+    # digital silence frames stay zero vectors (utils.py:257-258) and must not produce NaN
+    Obs[:, 10:14, :] = 0
+    # activity longer than the observation is sliced (core.py:182-184)
+    act_long = np.concatenate([act, np.ones((3, 17), bool)], axis=1)
+    got, ref = _gss_both(Obs, act_long, 8)
+    assert np.isfinite(got).all() and np.abs(got - ref).max() < 1e-4
+    # a speaker that is never active (only the 1e-10 initialisation floor keeps it alive)
+    act2 = act.copy(); act2[1] = False
+    got, ref = _gss_both(Obs, act2, 8)
+    assert np.isfinite(got).all() and np.abs(got - ref).max() < 1e-4
+    # unguided refinement iterations (core.py:188-194)
+    got, ref = _gss_both(Obs, act, 5, post_iters=3)
+    assert np.abs(got - ref).max() < 1e-4
+    # iterations_post == 0 raises TypeError in the reference (core.py:198-202)
+    with pytest.raises(TypeError):
+        core.GSS(3, 0, verbose=False)(Obs.astype(np.complex128), act)
+    # too short activity -> AssertionError (cacgmm.py:216-218)
+    with pytest.raises(AssertionError):
+        core.GSS(3, 1, verbose=False)(Obs.astype(np.complex128), act[:, :100])
+
+
+def test_gss_dead_channel_uses_floored_eigenvalues():
+    """A silent microphone makes every class covariance singular: the reference floors the
+    eigenvalue at 1e-10 (complex_angular_central_gaussian.py:118-121) -> Jacobi slow path."""
+    Obs, act = synth.make_utterance(9, D=4, T=180, F=3, K=3)
+    Obs[2] = 0
+    got, ref = _gss_both(Obs, act, 8)
+    assert np.isfinite(got).all() and np.abs(got - ref).max() < 1e-4
+
+
+def test_beamformer_degenerate_masks():
+    Obs, act = synth.make_utterance(13, D=4, T=100, F=5, K=3)
+    Obs = Obs.astype(np.complex128)
+    rng = np.random.default_rng(0)
+    tm, dm = rng.random((100, 5)), rng.random((100, 5))
+    # zero PSDs -> lstsq fallback -> zero weights (test_beamformer.py:206-226)
+    for a, b in [(tm * 0, dm), (tm, dm * 0), (tm * 0, dm * 0)]:
+        X = core.Beamformer('mvdrSouden_ban', None)(Obs, a, b)
+        ref = oracle.beamform(Obs, a.astype(np.float32).astype(np.float64), b.astype(np.float32).astype(np.float64))
+        assert np.isfinite(X).all()
+        assert np.abs(X - ref).max() < 1e-4 * max(np.abs(ref).max(), 1.0)
+    # one silent bin among healthy ones does not disturb the others (test_beamformer.py:282-312)
+    tm2 = tm.copy(); tm2[:, 1] = 0
+    X = core.Beamformer('mvdrSouden_ban', None)(Obs, tm2, dm)
+    ref = oracle.beamform(Obs, tm2.astype(np.float32).astype(np.float64), dm.astype(np.float32).astype(np.float64))
+    assert rel_err(X, ref) < 1e-4 and np.abs(X[:, 1]).max() == 0
+    # non-finite input -> AssertionError (beamformer.py:542)
+    bad = Obs.copy(); bad[0, 0, 0] = np.inf
+    with pytest.raises(AssertionError):
+        core.Beamformer('mvdrSouden_ban', None)(bad, tm, dm)
+    # GEV with a singular noise PSD -> ValueError like zhegvd INFO > N (get_gev_vector.pyx:139-147)
+    with pytest.raises(ValueError):
+        core.Beamformer('gev_ban', None)(Obs, tm, dm * 0)
+
+
+def test_dead_channel_wpe_and_mvdr():
+    Obs, act = synth.make_utterance(17, D=4, T=150, F=3, K=3)
+    Obs[:, 2:, :] += 0.5 * Obs[:, :-2, :]
+    Obs[1] = 0
+    Obs = Obs.astype(np.complex128)
+    ref = oracle.wpe_dtf(Obs, 3, 2, 2)
+    got = core.WPE(3, 2, 2, 0)(Obs)
+    assert np.isfinite(got).all() and rel_err(got, ref) < 1e-4 and np.abs(got[1]).max() == 0
+    rng = np.random.default_rng(1)
+    tm, dm = rng.random((150, 3)).astype(np.float32), rng.random((150, 3)).astype(np.float32)
+    refX = oracle.beamform(Obs, tm.astype(np.float64), dm.astype(np.float64))
+    X = core.Beamformer('mvdrSouden_ban', None)(Obs, tm, dm)
+    assert rel_err(X, refX) < 1e-4
+
+
+def test_host_batch_api_matches_blocks():
+    B = 2
+    obs, act = synth.make_batch(300, B, D=4, T=130, F=9, K=3)
+    enh = core.get_enhancer(wpe_tabs=3, wpe_iterations=2, bss_iterations=6)
+    res = enh.enhance_stft_host(torch.from_numpy(obs).pin_memory(), act, [0, 1], [3, 3], [3, 3])
+    assert res['X_hat'].shape == (B, 130, 9) and res['masks'].shape == (B, 3, 130, 9)
+    for b in range(B):
+        ref = oracle.enhance_stft(obs[b].astype(np.complex128), act[b], b,
+                                  wpe=dict(taps=3, delay=2, iterations=2, psd_context=0), gss_iterations=6,
+                                  start_context_frames=3, end_context_frames=3)
+        m = res['masks'][b].numpy().copy(); m[:, :3] = 0; m[:, -3:] = 0
+        assert np.abs(m - ref['masks']).max() < 1e-4
+        assert rel_err(res['X_hat'][b].numpy(), ref['X_hat']) < 1e-4
+
+
+def test_full_size_properties_and_spot_parity():
+    """BASELINE cfg2 size (D=24, T=941, F=513, K=5; fewer EM iterations to bound the
+    oracle): size-independent properties on all bins + oracle parity on 3 bins."""
+    Obs, act = synth.make_utterance(2024, D=24, T=941, F=513, K=5)
+    dev = torch.device('cuda')
+    Y = ops.pack_dtf_to_fdt(torch.from_numpy(Obs).to(dev)[None])
+    A = torch.from_numpy(act)[None].to(dev)
+    post, model = ops.cacgmm(Y, A, 30, return_model=True)
+    p = post[0]
+    assert torch.isfinite(p).all() and float(p.min()) >= 0 and float(p.max()) <= 1
+    assert float((p.sum(dim=1) - 1).abs().max()) < 1e-5            # posteriors sum to one over classes
+    w = model['weight'][0]
+    assert float((w.sum(dim=1) - 1).abs().max()) < 1e-6            # mixture weights sum to one
+    bins = [0, 257, 512]
+    ref = oracle.gss_posteriors(Obs[:, :, bins].astype(np.complex128), act, 30)
+    got = ops.unpack_fkt_to_ktf(post)[0].cpu().numpy()[:, :, bins]
+    assert np.abs(got - ref).max() < 1e-4
+    # beamformer: scaling the observation scales the output, masks only matter up to scale
+    ti = torch.zeros(1, dtype=torch.int32, device=dev)
+    c3 = torch.full((1,), 3, dtype=torch.int32, device=dev)
+    X1 = ops.beamform_from_posterior(Y, post, ti, c3, c3)
+    X2 = ops.beamform_from_posterior(Y * 2, post, ti, c3, c3)
+    assert float((X2 - 2 * X1).abs().max() / X1.abs().max()) < 1e-5
+    X3 = ops.beamform(Y, 0.5 * post[:, :, 0].contiguous(), post[:, :, 1:].sum(dim=2))
+    tm = post[:, :, 0].clone(); tm[:, :, :3] = 0; tm[:, :, -3:] = 0
+    dm = post[:, :, 1:].sum(dim=2); dm[:, :, :3] = 0; dm[:, :, -3:] = 0
+    X4 = ops.beamform(Y, tm.contiguous(), dm.contiguous())
+    assert float((X4 - X1).abs().max() / X1.abs().max()) < 1e-5
+    assert torch.isfinite(torch.view_as_real(X3)).all()
+    # WPE on 2 bins at full T, taps=10 against the oracle
+    Yw = ops.wpe(Y[:, :2].contiguous(), 10, 2, 3)
+    refw = oracle.wpe_dtf(Obs[:, :, :2].astype(np.complex128), 10, 2, 3)
+    assert rel_err(ops.unpack_fdt_to_dtf(Yw)[0].cpu().numpy(), refw) < 1e-4

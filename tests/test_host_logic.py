@@ -1,0 +1,190 @@
+"""CPU: host-side mirror of the reference interface, the C-ABI surface and the
+utterance sharding (no kernels are launched here)."""
+import ctypes
+import inspect
+import os
+import re
+import subprocess
+import sys
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+from oracle import gss_oracle as oracle
+from pb_chime5_b200 import _lib, core, sharding, synth
+
+ROOT = Path(__file__).resolve().parent.parent
+
+
+def test_abi_exports_every_declared_symbol():
+    header = (ROOT / 'include' / 'gss.h').read_text()
+    declared = set(re.findall(r'\b(gss_[a-z0-9_]+)\s*\(', header))
+    assert declared, 'no prototypes found in include/gss.h'
+    assert declared == set(_lib.exported_symbols()), declared ^ set(_lib.exported_symbols())
+    handle = ctypes.CDLL(str(_lib.LIB_PATH))
+    for name in declared:
+        getattr(handle, name)            # raises AttributeError if not exported
+    assert _lib.lib().gss_version() >= 100
+
+
+def test_abi_argument_errors_map_to_reference_exceptions():
+    L = _lib.lib()
+    n = ctypes.c_size_t(0)
+    assert L.gss_workspace_bytes(_lib.OP_WPE, 1, 513, 24, 941, 5, 10, ctypes.byref(n)) == 0
+    assert n.value > 513 * 240 * 240 * 16
+    # null pointers / limits never reach a launch
+    with pytest.raises(AssertionError):
+        _lib.check(L.gss_cacgmm_c64(None, None, None, 1, 1, 1e-10, 1e-10, 1, 1, 4, 10, 3, 10,
+                                    None, None, None, None, None, 0, None))
+    one = ctypes.c_void_p(16)            # dummy non-null, never dereferenced on the host
+    with pytest.raises(AssertionError, match='sure'):      # cacgmm.py:248  D < 35
+        _lib.check(L.gss_cacgmm_c64(one, one, one, 1, 1, 1e-10, 1e-10, 1, 1, 35, 10, 3, 10,
+                                    None, None, None, None, None, 0, None))
+    with pytest.raises(AssertionError, match='sure'):      # cacgmm.py:247  K < 20
+        _lib.check(L.gss_cacgmm_c64(one, one, one, 1, 1, 1e-10, 1e-10, 1, 1, 4, 10, 20, 10,
+                                    None, None, None, None, None, 0, None))
+    with pytest.raises(NotImplementedError):               # iterations_post == 0 (core.py:198-202)
+        _lib.check(L.gss_cacgmm_c64(one, one, one, 1, 0, 1e-10, 1e-10, 1, 1, 4, 10, 3, 10,
+                                    None, None, None, None, None, 0, None))
+    with pytest.raises(AssertionError):                    # beamforming_wrapper.py:44  D < 30
+        _lib.check(L.gss_beamform_c64(one, one, one, one, 0, 0, 0, 1, 1, 30, 10, None, None, None, one, 1 << 30, None))
+    with pytest.raises(NotImplementedError):               # unknown beamformer type
+        _lib.check(L.gss_beamform_c64(one, one, one, one, 17, 0, 0, 1, 1, 4, 10, None, None, None, one, 1 << 30, None))
+    with pytest.raises(RuntimeError, match='workspace'):
+        _lib.check(L.gss_beamform_c64(one, one, one, one, 0, 0, 0, 1, 1, 4, 10, None, None, None, one, 8, None))
+
+
+def test_get_enhancer_signature_matches_reference():
+    expect = dict(
+        multiarray=False, reference_array=None, context_samples=240000, wpe=True, wpe_tabs=10,
+        wpe_delay=2, wpe_iterations=3, wpe_psd_context=0, activity_type='annotation',
+        activity_path=None, activity_garbage_class=True, stft_size=1024, stft_shift=256,
+        stft_fading=True, bss_iterations=20, bss_iterations_post=1, bf_drop_context=True,
+        bf='mvdrSouden_ban', postfilter=None)
+    got = core.signature_defaults()
+    got.pop('database_path')
+    assert got == expect                                   # names, order-insensitive defaults
+    assert list(inspect.signature(core.get_enhancer).parameters)[:len(expect)] == list(expect)
+    e = core.get_enhancer()
+    assert e.wpe_block == core.WPE(taps=10, delay=2, iterations=3, psd_context=0)
+    assert e.gss_block == core.GSS(iterations=20, iterations_post=1, verbose=False)
+    assert e.bf_block == core.Beamformer(type='mvdrSouden_ban', postfilter=None)
+    assert e.activity.garbage_class is True and e.bf_drop_context is True
+    assert core.get_enhancer(wpe=False).wpe_block is None
+    with pytest.raises(AssertionError):
+        core.get_enhancer(wpe=1)
+    with pytest.raises(AssertionError):
+        core.get_enhancer(activity_path='x')
+
+
+def test_reference_signature_if_available():
+    from oracle import refboot
+    if not refboot.available():
+        pytest.skip('reference tree not present (GPU box)')
+    code = ("import warnings; warnings.filterwarnings('ignore');"
+            "from oracle import refboot; refboot.boot();"
+            "import inspect, pb_chime5.core as c, json;"
+            "print(json.dumps({k: repr(v.default) for k, v in inspect.signature(c.get_enhancer).parameters.items() if k != 'database_path'}));"
+            "print(json.dumps([f.name for f in __import__('dataclasses').fields(c.Enhancer)]))")
+    out = subprocess.run([sys.executable, '-c', code], cwd=ROOT, capture_output=True, text=True, check=True).stdout.splitlines()
+    import json, dataclasses
+    ref_defaults = json.loads(out[-2])
+    mine = {k: repr(v) for k, v in core.signature_defaults().items() if k != 'database_path'}
+    assert mine == ref_defaults
+    assert [f.name for f in dataclasses.fields(core.Enhancer)] == json.loads(out[-1])
+
+
+def test_activity_framing_matches_oracle_and_doctest():
+    vad = np.array([0, 0, 0, 0, 0, 1, 1, 0, 1, 0, 0, 0, 0, 0])
+    assert core.activity_time_to_frequency(vad, 4, 2, True).tolist() == \
+        [False, False, True, True, True, True, False, False]          # database.py:432-433
+    assert core.activity_time_to_frequency([vad, vad], 4, 2, False).tolist() == \
+        [[False, True, True, True, True, False]] * 2                  # database.py:447-449
+    assert core.activity_time_to_frequency(np.zeros(200000), 1024, 256, False, False).shape == (778,)
+    rng = np.random.default_rng(0)
+    for n in (1, 700, 1024, 1025, 5000, 20001):
+        sa = rng.random((3, n)) < 0.002
+        for fading in (True, False):
+            for pad in (True, False):
+                if not pad and n + 2 * 768 * fading < 1024:
+                    continue
+                a = core.activity_time_to_frequency(sa, 1024, 256, fading, pad)
+                b = oracle.activity_time_to_frequency(sa, 1024, 256, fading, pad)
+                assert np.array_equal(a, b), (n, fading, pad)
+
+
+def test_context_frames():
+    ex = {'start': {'original': 0}, 'start_orig': {'original': 240000},
+          'end': {'original': 720000}, 'end_orig': {'original': 480000}}
+    assert core.start_end_context_frames(ex, 1024, 256, True) == (941, 941)
+    assert core.samples_to_stft_frames(240000, 1024, 256, fading=True) == 941
+    assert core.samples_to_stft_frames(0, 1024, 256, fading=True) == 3
+    ex['start_orig']['original'] = -1
+    with pytest.raises(AssertionError):
+        core.start_end_context_frames(ex, 1024, 256, True)
+
+
+def test_block_argument_errors_without_gpu():
+    bf = core.Beamformer(type='lcmv', postfilter=None)
+    with pytest.raises(NotImplementedError):
+        bf(np.zeros((4, 10, 3), complex), np.zeros((10, 3)), np.zeros((10, 3)))
+    bf = core.Beamformer(type='sum', postfilter='wiener')
+    with pytest.raises(NotImplementedError):
+        bf(np.zeros((4, 10, 3), complex), np.zeros((10, 3)), np.zeros((10, 3)))
+    w = core.WPE(10, 2, 3, 0)
+    with pytest.raises(NotImplementedError):
+        w(np.zeros((4, 10), complex))
+    with pytest.raises(AssertionError):
+        w(np.zeros((4, 10, 3), complex), stack=True)
+
+
+def test_shard_indices():
+    assert sharding.shard_indices(10, 1, 4) == [1, 5, 9]                       # kaldi_run.py:73-76
+    allidx = sorted(sum((sharding.shard_indices(23, r, 4) for r in range(4)), []))
+    assert allidx == list(range(23))
+    lengths = [900, 100, 100, 100, 500, 400, 50, 50]
+    parts = [sharding.shard_indices(8, r, 2, lengths) for r in range(2)]
+    assert sorted(parts[0] + parts[1]) == list(range(8))
+    loads = [sum(lengths[i] for i in p) for p in parts]
+    assert abs(loads[0] - loads[1]) <= 100
+    assert sharding.shard_indices(0, 0, 2) == []
+    assert sharding.shard_indices(1, 1, 2) == []
+
+
+def test_two_rank_gloo_sharding(tmp_path):
+    """world_size 2 on CPU (gloo): broadcast of the work list + strided shards +
+    max-over-ranks timing reduction."""
+    script = tmp_path / 'w.py'
+    script.write_text('''
+import os, sys, json
+sys.path.insert(0, %r)
+from pb_chime5_b200 import sharding
+rank, world = sharding.init_process_group('gloo')
+work = sharding.broadcast_work_list([f"utt{i}" for i in range(7)] if rank == 0 else None)
+mine = [work[i] for i in sharding.shard_indices(len(work), rank, world)]
+t = sharding.max_over_ranks(1.0 + rank)
+n = sharding.sum_over_ranks(len(mine))
+sharding.barrier()
+print(json.dumps({"rank": rank, "mine": mine, "t": t, "n": n}), flush=True)
+''' % str(ROOT))
+    env = dict(os.environ, MASTER_ADDR='127.0.0.1', MASTER_PORT='29531', WORLD_SIZE='2')
+    procs = [subprocess.Popen([sys.executable, str(script)], env=dict(env, RANK=str(r), LOCAL_RANK=str(r)),
+                              stdout=subprocess.PIPE, text=True) for r in range(2)]
+    import json
+    outs = [json.loads(p.communicate(timeout=120)[0].strip().splitlines()[-1]) for p in procs]
+    assert all(p.returncode == 0 for p in procs)
+    outs.sort(key=lambda o: o['rank'])
+    assert outs[0]['mine'] == ['utt0', 'utt2', 'utt4', 'utt6']
+    assert outs[1]['mine'] == ['utt1', 'utt3', 'utt5']
+    assert outs[0]['t'] == outs[1]['t'] == 2.0
+    assert outs[0]['n'] == 7
+
+
+def test_synth_is_seeded_and_shaped():
+    a1, m1 = synth.make_utterance(3, D=4, T=50, F=5, K=3)
+    a2, m2 = synth.make_utterance(3, D=4, T=50, F=5, K=3)
+    assert a1.dtype == np.complex64 and a1.shape == (4, 50, 5) and m1.shape == (3, 50)
+    assert np.array_equal(a1, a2) and np.array_equal(m1, m2)
+    assert m1[-1].all()                              # 'Noise' garbage class always active
+    assert (m1[:-1].sum(axis=1) >= 8).all()          # >= 2*D active frames per speaker
