@@ -44,59 +44,39 @@ constexpr size_t cmax(size_t a, size_t b) { return a > b ? a : b; }
 __host__ __device__ constexpr int sub_block(int DP) {
     return DP < 12 ? DP : (DP % 6 == 0 ? 6 : 4);
 }
-__host__ __device__ constexpr int sb_pairs(int SB, int I, int J) { return I == J ? SB * (SB + 1) / 2 : SB * SB; }
-// Which of the ES threads of a frame handles sub-block idx.  Part 0 also runs the
-// softmax, so it gets a smaller share (~40 % for ES = 2).
-__host__ __device__ constexpr int sb_part(int DP, int ES, int idx) {
-    if (ES == 1) return 0;
-    const int SB = sub_block(DP), NS = DP / SB, NPAIR = DP * (DP + 1) / 2;
-    const double share0 = 0.8 / (0.8 + 1.2 * (ES - 1));
-    int cum = 0, i = 0;
-    for (int I = 0; I < NS; ++I)
-        for (int J = 0; J <= I; ++J, ++i) {
-            if (i == idx) {
-                const double mid = cum + 0.5 * sb_pairs(SB, I, J);
-                if (mid < share0 * NPAIR) return 0;
-                const double rest = (mid - share0 * NPAIR) / ((1.0 - share0) * NPAIR);
-                int h = 1 + int(rest * (ES - 1));
-                return h > ES - 1 ? ES - 1 : h;
-            }
-            cum += sb_pairs(SB, I, J);
-        }
-    return 0;
-}
 
-template <int DP, int K, int NT, int ES>
+template <int DP, int K, int NT>
 struct CacgmmCfg {
     static constexpr int NP = DP * (DP + 1) / 2;          // packed Hermitian pairs
     static constexpr int NB = DP / 2;                     // 2x2 block rows
     static constexpr int G = NB * (NB + 1) / 2;           // lanes per M-phase group
     static constexpr int NG = NT / G;                     // M-phase groups
     static constexpr int YLD = DP + 1;                    // padded smem row (elements)
-    static constexpr int KP = (K + 1) & ~1;               // padded class count (16 B rows)
+    static constexpr int KP = K;                          // row of the weight tile (unpadded: 2 CTAs/SM need every KB)
     static constexpr int NW = NT / 32;
     static constexpr int JLD = DP + 1;                    // leading dim of Jacobi matrices
-    static constexpr int TE = NT / ES;                    // frames per E step (complex64 tile)
-    static constexpr int TM = TE / 2;                     // frames per M step (complex128 tile)
-    static constexpr int ST = 4 * TE;                     // frames per super tile (w buffer)
+    static constexpr int TE = NT;                         // frames per E step = super tile (complex64 tile)
+    static constexpr int TM = 64;                         // frames per M step (complex128 tile + complex64 staging)
     static constexpr int SB = sub_block(DP);
     static constexpr int NS = DP / SB;
     static constexpr int NSB = NS * (NS + 1) / 2;
-    static constexpr size_t Y_BYTES = size_t(TE) * YLD * sizeof(float2);   // == TM * YLD * sizeof(cd)
-    static constexpr size_t CHOL_BYTES = size_t(K) * NP * sizeof(cd);
+    static constexpr size_t E_BYTES = size_t(TE) * YLD * sizeof(float2);
+    static constexpr size_t MT_BYTES = size_t(TM) * YLD * sizeof(cd);       // complex128 M tile
+    static constexpr size_t MS_BYTES = size_t(TM) * YLD * sizeof(float2);   // complex64 staging (cp.async)
+    static constexpr size_t SWEEP_BYTES = size_t(K) * NP * sizeof(cd);
     static constexpr size_t JAC_BYTES = size_t(2) * DP * JLD * sizeof(cd);
-    static constexpr size_t YS_BYTES = cmax(Y_BYTES, cmax(CHOL_BYTES, JAC_BYTES));
-    static constexpr size_t W_BYTES = size_t(ST) * KP * sizeof(double);
+    static constexpr size_t YS_BYTES = cmax(cmax(E_BYTES, MT_BYTES + MS_BYTES), cmax(SWEEP_BYTES, JAC_BYTES));
+    static constexpr size_t W_BYTES = size_t(TE) * KP * sizeof(double);
     static constexpr size_t B_BYTES = size_t(NP) * K * sizeof(cd);
     static constexpr size_t ACC_BYTES = size_t(K) * NP * sizeof(cd);
-    static constexpr size_t QP_BYTES = (ES > 1) ? size_t(ES - 1) * K * TE * sizeof(double) : 0;
-    static constexpr int MISC_DOUBLES = 4 * 32 + NW * K + 64;
-    static constexpr size_t MISC_BYTES = size_t(MISC_DOUBLES) * 8 + 16 * sizeof(JacobiRot) + 64 * sizeof(int);
-    static constexpr size_t SMEM = YS_BYTES + W_BYTES + B_BYTES + ACC_BYTES + QP_BYTES + MISC_BYTES;
+    // misc: logdet[32] pi[32] tr[32] | gred[NW*K] | jred[64] | col[K*DP] cd | piv[K*DP] | rot[16] | flags[32] | table[NP] u16
+    static constexpr size_t MISC_BYTES = (96 + NW * K + 64) * 8 + size_t(K) * DP * 16 + size_t(K) * DP * 8
+                                         + 16 * sizeof(JacobiRot) + 32 * 4 + ((NP * 2 + 15) / 16) * 16;
+    static constexpr size_t SMEM = YS_BYTES + W_BYTES + B_BYTES + ACC_BYTES + MISC_BYTES;
     static_assert(DP % 2 == 0 && DP <= 32, "padded channel count must be even and <= 32");
     static_assert(DP % SB == 0, "sub-block must divide DP");
     static_assert(NG >= 1, "block too small for the M-phase mapping");
-    static_assert(NT % (32 * ES) == 0, "E parts must be warp aligned");
+    static_assert(TE % TM == 0, "M tiles must tile the super tile");
     static_assert(K < 20, "cacgmm.py:247");
 };
 
@@ -130,43 +110,52 @@ __device__ __forceinline__ void quad_subblock(const float2* __restrict__ yrow, c
     }
 }
 
-template <int DP, int K, int ES, int IDX, int NSB>
+template <int DP, int K, int IDX, int NSB>
 struct QuadAll {
-    static __device__ __forceinline__ void run(int h, const float2* yrow, const cd* Bsm,
-                                               double (&qa)[K], double (&qb)[K]) {
+    static __device__ __forceinline__ void run(const float2* yrow, const cd* Bsm, double (&qa)[K], double (&qb)[K]) {
         constexpr int SB = sub_block(DP);
-        // idx -> (I, J), row-major lower triangle
         constexpr int I = [] { int r = 0; while ((r + 1) * (r + 2) / 2 <= IDX) ++r; return r; }();
         constexpr int J = IDX - I * (I + 1) / 2;
-        if (h == sb_part(DP, ES, IDX)) quad_subblock<DP, K, SB, I, J>(yrow, Bsm, qa, qb);
-        QuadAll<DP, K, ES, IDX + 1, NSB>::run(h, yrow, Bsm, qa, qb);
+        quad_subblock<DP, K, SB, I, J>(yrow, Bsm, qa, qb);
+        QuadAll<DP, K, IDX + 1, NSB>::run(yrow, Bsm, qa, qb);
     }
 };
-template <int DP, int K, int ES, int NSB>
-struct QuadAll<DP, K, ES, NSB, NSB> {
-    static __device__ __forceinline__ void run(int, const float2*, const cd*, double (&)[K], double (&)[K]) {}
+template <int DP, int K, int NSB>
+struct QuadAll<DP, K, NSB, NSB> {
+    static __device__ __forceinline__ void run(const float2*, const cd*, double (&)[K], double (&)[K]) {}
 };
 
-template <int DP, int K, int NT, int ES, int MINB>
+__device__ __forceinline__ void cp_async8(void* smem_dst, const void* gsrc) {
+    const unsigned s = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"(s), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit_wait_all() {
+    asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;\n" ::: "memory");
+}
+
+template <int DP, int K, int NT, int MINB>
 __global__ void __launch_bounds__(NT, MINB) cacgmm_em_kernel(const CacgmmParams p) {
-    using C = CacgmmCfg<DP, K, NT, ES>;
-    constexpr int TE = C::TE, TM = C::TM, ST = C::ST;
+    using C = CacgmmCfg<DP, K, NT>;
+    constexpr int TE = C::TE, TM = C::TM;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     unsigned char* sp = smem_raw;
-    unsigned char* ys_raw = sp;                     sp += C::YS_BYTES;   // frame tile / matrix scratch
-    double* wsm = reinterpret_cast<double*>(sp);    sp += C::W_BYTES;    // [ST][KP]
+    unsigned char* ys_raw = sp;                     sp += C::YS_BYTES;   // frame tiles / matrix scratch
+    double* wsm = reinterpret_cast<double*>(sp);    sp += C::W_BYTES;    // [TE][KP]
     cd* Bsm = reinterpret_cast<cd*>(sp);            sp += C::B_BYTES;    // [NP][K]
     cd* acc_sm = reinterpret_cast<cd*>(sp);         sp += C::ACC_BYTES;  // [K][NP]
-    double* qpart = reinterpret_cast<double*>(sp);  sp += C::QP_BYTES;   // [ES-1][K][TE]
     double* logdet_s = reinterpret_cast<double*>(sp);                    // [32]
     double* pi_s = logdet_s + 32;                                        // [32]
     double* tr_s = logdet_s + 64;                                        // [32]
-    double* gred = logdet_s + 128;                                       // [NW][K]
+    double* gred = logdet_s + 96;                                        // [NW][K]
     double* jred = gred + C::NW * K;                                     // [64]
-    JacobiRot* jrot = reinterpret_cast<JacobiRot*>(jred + 64);           // [16]
-    int* flags_s = reinterpret_cast<int*>(jrot + 16);                    // [K] slow-path flags
+    cd* colbuf = reinterpret_cast<cd*>(jred + 64);                       // [K][DP] sweep column
+    double* pivbuf = reinterpret_cast<double*>(colbuf + K * DP);         // [K][DP] sweep pivots
+    JacobiRot* jrot = reinterpret_cast<JacobiRot*>(pivbuf + K * DP);     // [16]
+    int* flags_s = reinterpret_cast<int*>(jrot + 16);                    // [K] slow-path flags, [31] exact flag
+    unsigned short* tri_tab = reinterpret_cast<unsigned short*>(flags_s + 32);   // [NP] (i << 8 | c)
     float2* yf = reinterpret_cast<float2*>(ys_raw);                      // E tile [TE][YLD] complex64
     cd* yd = reinterpret_cast<cd*>(ys_raw);                              // M tile [TM][YLD] complex128
+    float2* ystage = reinterpret_cast<float2*>(ys_raw + C::MT_BYTES);    // M staging [TM][YLD] complex64
 
     const int tid = threadIdx.x;
     const int lane = tid & 31, warp = tid >> 5;
@@ -176,9 +165,6 @@ __global__ void __launch_bounds__(NT, MINB) cacgmm_em_kernel(const CacgmmParams 
     const float2* __restrict__ Yg = p.Y + (size_t)bf * D * T;
     const uint8_t* __restrict__ act = p.activity + (size_t)b * K * p.T_act;
 
-    // E-phase role: thread (frame e_t, part e_h); e_h is warp-uniform
-    const int e_h = tid / TE;
-    const int e_t = tid - e_h * TE;
     // M-phase role: group m_g, lane m_l -> 2x2 block (bi >= bj)
     const int m_g = tid / C::G;
     const int m_l = tid - m_g * C::G;
@@ -189,8 +175,15 @@ __global__ void __launch_bounds__(NT, MINB) cacgmm_em_kernel(const CacgmmParams 
     const int r0 = 2 * bi, c0 = 2 * bj;
 
     const int total_iters = p.iterations + (p.iterations_post - 1);
+    const int NPD = D * (D + 1) / 2;
 
     for (int i = tid; i < C::NP * K; i += NT) Bsm[i] = cmake(0.0, 0.0);
+    for (int i = tid; i < NPD; i += NT) {
+        int d = 0;
+        while ((d + 1) * (d + 2) / 2 <= i) ++d;
+        tri_tab[i] = (unsigned short)((d << 8) | (i - d * (d + 1) / 2));
+    }
+    if (tid == 0) flags_s[31] = 0;
     __syncthreads();
 
     // pass i < total_iters : (E-step if i > 0) + M-step.   pass == total_iters :
@@ -202,106 +195,109 @@ __global__ void __launch_bounds__(NT, MINB) cacgmm_em_kernel(const CacgmmParams 
         double gsum[K];
 #pragma unroll
         for (int k = 0; k < K; ++k) gsum[k] = 0.0;
+        int zero_frames = 0;
 
-        for (int s0 = 0; s0 < T; s0 += ST) {
-            const int s1 = min(s0 + ST, T);
-            // ================= E sweep over the super tile =================
-            for (int t0 = s0; t0 < s1; t0 += TE) {
-                for (int i = tid; i < DP * TE; i += NT) {
-                    const int d = i / TE, t = i - d * TE;
-                    float2 v = make_float2(0.f, 0.f);
-                    if (d < D && t0 + t < T) v = __ldg(&Yg[(size_t)d * T + t0 + t]);
-                    yf[t * C::YLD + d] = v;
-                }
-                __syncthreads();
-                const float2* yrow = yf + e_t * C::YLD;
+        for (int s0 = 0; s0 < T; s0 += TE) {
+            const int s1 = min(s0 + TE, T);
+            // ================= E step on the super tile (thread owns a frame) =================
+            for (int i = tid; i < DP * TE; i += NT) {
+                const int d = i / TE, t = i - d * TE;
+                float2 v = make_float2(0.f, 0.f);
+                if (d < D && s0 + t < T) v = __ldg(&Yg[(size_t)d * T + s0 + t]);
+                yf[t * C::YLD + d] = v;
+            }
+            __syncthreads();
+            {
+                const float2* yrow = yf + tid * C::YLD;
                 double qa[K], qb[K];
 #pragma unroll
                 for (int k = 0; k < K; ++k) { qa[k] = 0.0; qb[k] = 0.0; }
-                if (pass > 0) {
-                    QuadAll<DP, K, ES, 0, C::NSB>::run(e_h, yrow, Bsm, qa, qb);
-                    if (ES > 1 && e_h > 0) {
+                if (pass > 0) QuadAll<DP, K, 0, C::NSB>::run(yrow, Bsm, qa, qb);
+                const int t = s0 + tid;
+                if (t < s1) {
+                    double n2 = 0.0;
 #pragma unroll
-                        for (int k = 0; k < K; ++k) qpart[((e_h - 1) * K + k) * TE + e_t] = qa[k] + qb[k];
+                    for (int d = 0; d < DP; ++d) {
+                        const float2 v = yrow[d];
+                        n2 = fma((double)v.x, (double)v.x, fma((double)v.y, (double)v.y, n2));
                     }
-                }
-                if (ES > 1) __syncthreads();
-                if (e_h == 0) {
-                    const int t = t0 + e_t;
-                    if (t < s1) {
-                        double n2 = 0.0;
+                    const double s = n2 > 0.0 ? 1.0 / n2 : 0.0;
+                    if (!(n2 > 0.0)) ++zero_frames;
+                    double g[K], w[K];
+                    if (pass == 0) {
+                        // initialisation from the activity (core.py:156-160); q == 1
+                        double tot = 0.0;
 #pragma unroll
-                        for (int d = 0; d < DP; ++d) {
-                            const float2 v = yrow[d];
-                            n2 = fma((double)v.x, (double)v.x, fma((double)v.y, (double)v.y, n2));
+                        for (int k = 0; k < K; ++k) { g[k] = act[(size_t)k * p.T_act + t] ? 1.0 : 1e-10; tot += g[k]; }
+#pragma unroll
+                        for (int k = 0; k < K; ++k) { g[k] /= tot; w[k] = g[k] * s; }
+                    } else {
+                        double lp[K], qn[K];
+                        double mx = -INFINITY;
+#pragma unroll
+                        for (int k = 0; k < K; ++k) {
+                            const double q = fmax(fabs(qa[k] + qb[k]) * s, GSS_F64_TINY);
+                            qn[k] = q;
+                            lp[k] = -(double)D * log(q) - logdet_s[k];
+                            mx = fmax(mx, lp[k]);
                         }
-                        const double s = n2 > 0.0 ? 1.0 / n2 : 0.0;
-                        double g[K], w[K];
-                        if (pass == 0) {
-                            // initialisation from the activity (core.py:156-160); q == 1
-                            double tot = 0.0;
+                        double den = 0.0;
 #pragma unroll
-                            for (int k = 0; k < K; ++k) { g[k] = act[(size_t)k * p.T_act + t] ? 1.0 : 1e-10; tot += g[k]; }
-#pragma unroll
-                            for (int k = 0; k < K; ++k) { g[k] /= tot; w[k] = g[k] * s; }
-                        } else {
-                            double lp[K], qn[K];
-                            double mx = -INFINITY;
-#pragma unroll
-                            for (int k = 0; k < K; ++k) {
-                                double q = qa[k] + qb[k];
-                                if (ES > 1) {
-#pragma unroll
-                                    for (int h = 1; h < ES; ++h) q += qpart[((h - 1) * K + k) * TE + e_t];
-                                }
-                                q = fmax(fabs(q) * s, GSS_F64_TINY);
-                                qn[k] = q;
-                                lp[k] = -(double)D * log(q) - logdet_s[k];
-                                mx = fmax(mx, lp[k]);
-                            }
-                            double den = 0.0;
-#pragma unroll
-                            for (int k = 0; k < K; ++k) {
-                                double a = exp(lp[k] - mx) * pi_s[k];
-                                if (guided && !act[(size_t)k * p.T_act + t]) a = 0.0;
-                                g[k] = a; den += a;
-                            }
-                            den = fmax(den, GSS_F64_TINY);
-#pragma unroll
-                            for (int k = 0; k < K; ++k) {
-                                double v = g[k] / den;
-                                if (eps != 0.0) v = fmin(fmax(v, eps), 1.0 - eps);
-                                g[k] = v;
-                                w[k] = v * s / qn[k];
-                            }
+                        for (int k = 0; k < K; ++k) {
+                            double a = exp(lp[k] - mx) * pi_s[k];
+                            if (guided && !act[(size_t)k * p.T_act + t]) a = 0.0;
+                            g[k] = a; den += a;
                         }
-                        if (is_final) {
+                        den = fmax(den, GSS_F64_TINY);
 #pragma unroll
-                            for (int k = 0; k < K; ++k)
-                                p.posterior[((size_t)bf * K + k) * T + t] = (float)g[k];
+                        for (int k = 0; k < K; ++k) {
+                            double v = g[k] / den;
+                            if (eps != 0.0) v = fmin(fmax(v, eps), 1.0 - eps);
+                            g[k] = v;
+                            w[k] = v * s / qn[k];
                         }
-#pragma unroll
-                        for (int k = 0; k < K; ++k) { gsum[k] += g[k]; wsm[(t - s0) * C::KP + k] = w[k]; }
                     }
+                    if (is_final) {
+#pragma unroll
+                        for (int k = 0; k < K; ++k)
+                            p.posterior[((size_t)bf * K + k) * T + t] = (float)g[k];
+                    }
+#pragma unroll
+                    for (int k = 0; k < K; ++k) { gsum[k] += g[k]; wsm[tid * C::KP + k] = w[k]; }
                 }
-                __syncthreads();
             }
+            __syncthreads();
             if (is_final) continue;
 
-            // ================= M sweep over the super tile =================
+            // ================= M step on the super tile (lane owns a 2x2 block) =================
             cd macc[4][K];
 #pragma unroll
             for (int a = 0; a < 4; ++a)
 #pragma unroll
                 for (int k = 0; k < K; ++k) macc[a][k] = cmake(0.0, 0.0);
+            // stage tile 0
+            for (int i = tid; i < DP * TM; i += NT) {
+                const int d = i / TM, t = i - d * TM;
+                if (d < D && s0 + t < T) cp_async8(&ystage[t * C::YLD + d], &Yg[(size_t)d * T + s0 + t]);
+                else ystage[t * C::YLD + d] = make_float2(0.f, 0.f);
+            }
             for (int t0 = s0; t0 < s1; t0 += TM) {
+                cp_async_commit_wait_all();
+                __syncthreads();
+                // convert the staged complex64 tile once
                 for (int i = tid; i < DP * TM; i += NT) {
-                    const int d = i / TM, t = i - d * TM;
-                    float2 v = make_float2(0.f, 0.f);
-                    if (d < D && t0 + t < T) v = __ldg(&Yg[(size_t)d * T + t0 + t]);
+                    const int t = i / DP, d = i - t * DP;
+                    const float2 v = ystage[t * C::YLD + d];
                     yd[t * C::YLD + d] = cmake((double)v.x, (double)v.y);
                 }
                 __syncthreads();
+                if (t0 + TM < s1) {           // stage the next tile while this one is consumed
+                    for (int i = tid; i < DP * TM; i += NT) {
+                        const int d = i / TM, t = i - d * TM;
+                        if (d < D && t0 + TM + t < T) cp_async8(&ystage[t * C::YLD + d], &Yg[(size_t)d * T + t0 + TM + t]);
+                        else ystage[t * C::YLD + d] = make_float2(0.f, 0.f);
+                    }
+                }
                 if (m_active) {
                     const int tn = min(TM, s1 - t0);
                     for (int t = m_g; t < tn; t += C::NG) {
@@ -322,8 +318,8 @@ __global__ void __launch_bounds__(NT, MINB) cacgmm_em_kernel(const CacgmmParams 
                         }
                     }
                 }
-                __syncthreads();
             }
+            __syncthreads();
             // ---- flush: reduce over the M-phase groups in fixed order (deterministic) ----
             for (int g = 0; g < C::NG; ++g) {
                 if (m_active && m_g == g) {
@@ -344,6 +340,12 @@ __global__ void __launch_bounds__(NT, MINB) cacgmm_em_kernel(const CacgmmParams 
             }
         }
         if (is_final) break;
+        if (pass == 0) {
+            // all-zero frames make q = tiny, where the eigenvalue normalisation of the reference
+            // does not cancel any more -> this bin needs the exact (eigh) class matrices.
+            const int any_zero = __syncthreads_or(zero_frames);
+            if (tid == 0) flags_s[31] = any_zero ? 1 : 0;
+        }
 
         // ---- mixture weights  pi_k = mean_t gamma_kt  (mixture_model_utils.py:187) ----
 #pragma unroll
@@ -357,47 +359,86 @@ __global__ void __launch_bounds__(NT, MINB) cacgmm_em_kernel(const CacgmmParams 
             for (int w = 0; w < C::NW; ++w) v += gred[w * K + tid];
             pi_s[tid] = v / (double)T;
         }
-
-        // ---- class matrices: fast path = Cholesky inverse, one warp per class ----
-        cd* chol = reinterpret_cast<cd*>(ys_raw);      // [K][NP] scaled copy -> L -> L^{-1}
-        const int NPD = D * (D + 1) / 2;
+        // ---- traces ----
         for (int k = warp; k < K; k += C::NW) {
-            const cd* src = acc_sm + k * C::NP;
             double tr = 0.0;
-            if (lane < D) tr = src[tri(lane, lane)].x;
+            if (lane < D) tr = acc_sm[k * C::NP + tri(lane, lane)].x;
             tr = warp_sum(tr);
-            bool slow = !(tr > 0.0) || !isfinite(tr);
-            cd* L = chol + k * C::NP;
-            if (!slow) {
-                const double itr = 1.0 / tr;
-                for (int i = lane; i < NPD; i += 32) L[i] = cscale(src[i], itr);
-                __syncwarp();
-                if (lane < D) L[tri(lane, lane)].y = 0.0;   // force_hermitian (utils.py:323-334)
-                __syncwarp();
-                slow = !warp_cholesky_packed(L, D, lane);
-            }
-            double ld = 0.0, trb = 0.0;
-            if (!slow) {
-                if (lane < D) ld = 2.0 * log(L[tri(lane, lane)].x);
-                ld = warp_sum(ld);
-                warp_tri_inverse_inplace(L, D, lane);
-                // B = M^H M, row `lane`
-                if (lane < D) {
-                    const int d = lane;
-                    for (int e = 0; e <= d; ++e) {
-                        cd v = mhm_entry(L, D, d, e);
-                        if (e == d) { trb = v.x; Bsm[tri(d, e) * K + k] = cmake(v.x, 0.0); }
-                        else Bsm[tri(d, e) * K + k] = cmake(2.0 * v.x, 2.0 * v.y);
-                    }
-                }
-                trb = warp_sum(trb);
-                // lambda_min >= 1/tr(B), lambda_max <= tr(Phi)=1  => no eigenvalue is floored
-                // if 1/tr(B) >= floor  (complex_angular_central_gaussian.py:118-121)
-                if (!(trb * p.floor_ <= 1.0) || !isfinite(trb) || !isfinite(ld)) slow = true;
-            }
-            if (lane == 0) { flags_s[k] = slow ? 1 : 0; logdet_s[k] = ld; tr_s[k] = tr; }
+            if (lane == 0) { tr_s[k] = tr; flags_s[k] = (!(tr > 0.0) || !isfinite(tr) || flags_s[31]) ? 1 : 0; }
         }
         __syncthreads();
+
+        // ---- fast path: B_k = (Phi_k / tr)^-1 for all classes at once with the symmetric sweep
+        //      operator (in place, packed lower; pivots = Cholesky pivots^2, logdet = sum log pivots)
+        cd* S = reinterpret_cast<cd*>(ys_raw);            // [K][NPD]
+        const bool need_exact = flags_s[31] != 0;
+        if (!need_exact) {
+            for (int e = tid; e < K * NPD; e += NT) {
+                const int k = e / NPD, r = e - k * NPD;
+                const double tr = tr_s[k];
+                const double itr = (tr > 0.0 && isfinite(tr)) ? 1.0 / tr : 0.0;
+                cd v = cscale(acc_sm[k * C::NP + r], itr);
+                const unsigned ic = tri_tab[r];
+                if ((ic >> 8) == (ic & 255)) v.y = 0.0;       // force_hermitian (utils.py:323-334)
+                S[e] = v;
+            }
+            __syncthreads();
+            for (int j = 0; j < D; ++j) {
+                for (int e = tid; e < K * D; e += NT) {
+                    const int k = e / D, i = e - k * D;
+                    const cd* Sk = S + k * NPD;
+                    const cd u = (i >= j) ? Sk[tri(i, j)] : cconj(Sk[tri(j, i)]);
+                    colbuf[k * DP + i] = u;
+                    if (i == j) pivbuf[k * DP + j] = u.x;
+                }
+                __syncthreads();
+                for (int e = tid; e < K * NPD; e += NT) {
+                    const int k = e / NPD, r = e - k * NPD;
+                    const unsigned ic = tri_tab[r];
+                    const int i = ic >> 8, c = ic & 255;
+                    const double piv = pivbuf[k * DP + j];
+                    const double d = (piv > 0.0 && isfinite(piv)) ? 1.0 / piv : 0.0;
+                    cd v;
+                    if (i == j && c == j) v = cmake(-d, 0.0);
+                    else if (c == j) v = cscale(colbuf[k * DP + i], d);
+                    else if (i == j) v = cscale(cconj(colbuf[k * DP + c]), d);
+                    else {
+                        v = S[e];
+                        cd ud = cscale(colbuf[k * DP + i], d);
+                        cfmsc(v, ud, colbuf[k * DP + c]);
+                    }
+                    S[e] = v;
+                }
+                __syncthreads();
+            }
+            // logdet, trace of the inverse, validity of the fast path
+            for (int k = warp; k < K; k += C::NW) {
+                double ld = 0.0, trb = 0.0;
+                bool bad = false;
+                if (lane < D) {
+                    const double piv = pivbuf[k * DP + lane];
+                    bad = !(piv > 0.0) || !isfinite(piv);
+                    ld = bad ? 0.0 : log(piv);
+                    trb = -S[k * NPD + tri(lane, lane)].x;
+                }
+                ld = warp_sum(ld); trb = warp_sum(trb);
+                bad = __any_sync(0xffffffffu, bad);
+                // lambda_min >= 1/tr(B), lambda_max <= tr(Phi) = 1  =>  nothing is floored if
+                // 1/tr(B) >= floor  (complex_angular_central_gaussian.py:118-121)
+                if (bad || !(trb * p.floor_ <= 1.0) || !isfinite(trb) || !isfinite(ld)) { if (lane == 0) flags_s[k] = 1; }
+                else if (lane == 0) logdet_s[k] = ld;
+            }
+            __syncthreads();
+            for (int e = tid; e < K * NPD; e += NT) {
+                const int k = e / NPD, r = e - k * NPD;
+                if (flags_s[k]) continue;
+                const unsigned ic = tri_tab[r];
+                const int i = ic >> 8, c = ic & 255;
+                const cd v = S[e];
+                Bsm[tri(i, c) * K + k] = (i == c) ? cmake(-v.x, 0.0) : cmake(-2.0 * v.x, -2.0 * v.y);
+            }
+            __syncthreads();
+        }
 
         // ---- slow path: Jacobi eigh with normalise-by-max + floor, whole CTA per class ----
         for (int k = 0; k < K; ++k) {
@@ -435,9 +476,8 @@ __global__ void __launch_bounds__(NT, MINB) cacgmm_em_kernel(const CacgmmParams 
             }
             __syncthreads();
             for (int i = tid; i < NPD; i += NT) {
-                int d = 0;
-                while ((d + 1) * (d + 2) / 2 <= i) ++d;
-                const int e = i - d * (d + 1) / 2;
+                const unsigned ic = tri_tab[i];
+                const int d = ic >> 8, e = ic & 255;
                 cd s = cmake(0.0, 0.0);
                 for (int j = 0; j < D; ++j) {
                     cd t1 = cscale(V[d * C::JLD + j], lam[j]);
@@ -474,20 +514,15 @@ __global__ void __launch_bounds__(NT, MINB) cacgmm_em_kernel(const CacgmmParams 
 // ---------------------------------------------------------------------------
 // Host dispatch
 // ---------------------------------------------------------------------------
-template <int DP, int K, int NT, int ES, int MINB>
-static int launch_cacgmm(const CacgmmParams& p, cudaStream_t st) {
-    using C = CacgmmCfg<DP, K, NT, ES>;
-    auto kern = cacgmm_em_kernel<DP, K, NT, ES, MINB>;
+template <int DP, int K>
+static int launch_cacgmm_dk(const CacgmmParams& p, cudaStream_t st) {
+    constexpr int NT = 256;
+    using C = CacgmmCfg<DP, K, NT>;
+    auto kern = cacgmm_em_kernel<DP, K, NT, 2>;
     GSS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM));
     kern<<<p.B * p.F, NT, C::SMEM, st>>>(p);
     GSS_LAUNCH_CHECK("cacgmm_em_kernel");
     return GSS_OK;
-}
-
-template <int DP, int K>
-static int launch_cacgmm_dk(const CacgmmParams& p, cudaStream_t st) {
-    if constexpr (DP >= 12) return launch_cacgmm<DP, K, 256, 2, 2>(p, st);
-    else                    return launch_cacgmm<DP, K, 256, 1, 2>(p, st);
 }
 
 template <int DP>

@@ -69,9 +69,32 @@ def test_enhance_observation_matches_reference(golden_dir, name):
                                     'P01', ex=ex, debug=True)
     loc = enh.enhance_observation_locals
     assert np.array_equal(loc['acitivity_freq'], g['activity_freq'])
-    assert np.abs(loc['masks'] - g['masks']).max() < 2e-4
-    assert rel_err(loc['X_hat'], g['X_hat']) < 2e-4
-    assert x_hat.shape == g['x_hat'].shape and rel_err(x_hat, g['x_hat']) < 2e-4
+    # (1) tight, stage by stage on identical complex64 inputs (this toy segment is so
+    # ill-conditioned -- WPE normal equations with cond ~1e10 -- that even the float64 oracle
+    # moves by 5e-5 under a 1e-12 rescaling of its input, so errors must not be chained):
+    Y = ops.stft(torch.from_numpy(g['obs']).cuda()[None])                       # (1,F,D,T)
+    S64 = ops.unpack_fdt_to_dtf(Y)[0].cpu().numpy().astype(np.complex128)       # (D,T,F)
+    if taps:
+        Yw = enh.wpe_block._run(Y)
+        W64 = ops.unpack_fdt_to_dtf(Yw)[0].cpu().numpy().astype(np.complex128)
+        assert rel_err(W64, oracle.wpe_dtf(S64, taps, delay, its, ctx)) < 1e-4
+    else:
+        Yw, W64 = Y, S64
+    act = torch.from_numpy(loc['acitivity_freq'].astype(np.uint8))[None].cuda()
+    post = enh.gss_block._run(Yw, act)
+    m_dev = ops.unpack_fkt_to_ktf(post)[0].cpu().numpy()
+    assert np.abs(m_dev - oracle.gss_posteriors(W64, loc['acitivity_freq'], 10)).max() < 1e-4
+    assert np.abs(np.where(loc['masks'] > 0, loc['masks'] - m_dev, 0)).max() < 1e-6   # same masks inside enhance_observation
+    refX = oracle.beamform(W64, loc['target_mask'], loc['distortion_mask'])
+    assert rel_err(loc['X_hat'], refX) < 1e-4
+    assert rel_err(x_hat, oracle.istft(loc['X_hat'].astype(np.complex128))) < 1e-5
+    # (2) loose: against the float64 reference fixture.  This toy segment (T=82 frames,
+    # WPE with 16 unknowns per channel) amplifies the float32 rounding of the STFT itself
+    # to 5e-4 in the masks even in pure float64 arithmetic (checked with the oracle), so the
+    # bound here documents the storage format, not the kernels.
+    assert np.abs(loc['masks'] - g['masks']).max() < 5e-3
+    assert rel_err(loc['X_hat'], g['X_hat']) < 5e-3
+    assert x_hat.shape == g['x_hat'].shape and rel_err(x_hat, g['x_hat']) < 5e-3
     # stft / istft methods in the reference layout
     S = enh.stft(g['obs'].astype(np.float64))
     assert S.shape == (4, loc['masks'].shape[1], 513)
