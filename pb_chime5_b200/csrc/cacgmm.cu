@@ -52,7 +52,7 @@ struct CacgmmCfg {
     static constexpr int G = NB * (NB + 1) / 2;           // lanes per M-phase group
     static constexpr int NG = NT / G;                     // M-phase groups
     static constexpr int YLD = DP + 1;                    // padded smem row (elements)
-    static constexpr int KP = K;                          // row of the weight tile (unpadded: 2 CTAs/SM need every KB)
+    static constexpr int KP = (K + 1) & ~1;               // padded class count (16 B rows)
     static constexpr int NW = NT / 32;
     static constexpr int JLD = DP + 1;                    // leading dim of Jacobi matrices
     static constexpr int TE = NT;                         // frames per E step = super tile (complex64 tile)
@@ -63,14 +63,14 @@ struct CacgmmCfg {
     static constexpr size_t E_BYTES = size_t(TE) * YLD * sizeof(float2);
     static constexpr size_t MT_BYTES = size_t(TM) * YLD * sizeof(cd);       // complex128 M tile
     static constexpr size_t MS_BYTES = size_t(TM) * YLD * sizeof(float2);   // complex64 staging (cp.async)
-    static constexpr size_t SWEEP_BYTES = size_t(K) * NP * sizeof(cd);
+    static constexpr size_t SWEEP_BYTES = size_t(K) * NP * sizeof(cd) + size_t(2) * K * DP * sizeof(cd) + 2 * K * 8 + 64;
     static constexpr size_t JAC_BYTES = size_t(2) * DP * JLD * sizeof(cd);
     static constexpr size_t YS_BYTES = cmax(cmax(E_BYTES, MT_BYTES + MS_BYTES), cmax(SWEEP_BYTES, JAC_BYTES));
     static constexpr size_t W_BYTES = size_t(TE) * KP * sizeof(double);
     static constexpr size_t B_BYTES = size_t(NP) * K * sizeof(cd);
     static constexpr size_t ACC_BYTES = size_t(K) * NP * sizeof(cd);
     // misc: logdet[32] pi[32] tr[32] | gred[NW*K] | jred[64] | col[K*DP] cd | piv[K*DP] | rot[16] | flags[32] | table[NP] u16
-    static constexpr size_t MISC_BYTES = (96 + NW * K + 64) * 8 + size_t(K) * DP * 16 + size_t(K) * DP * 8
+    static constexpr size_t MISC_BYTES = (96 + NW * K + 64) * 8 + size_t(K) * DP * 8
                                          + 16 * sizeof(JacobiRot) + 32 * 4 + ((NP * 2 + 15) / 16) * 16;
     static constexpr size_t SMEM = YS_BYTES + W_BYTES + B_BYTES + ACC_BYTES + MISC_BYTES;
     static_assert(DP % 2 == 0 && DP <= 32, "padded channel count must be even and <= 32");
@@ -148,8 +148,7 @@ __global__ void __launch_bounds__(NT, MINB) cacgmm_em_kernel(const CacgmmParams 
     double* tr_s = logdet_s + 64;                                        // [32]
     double* gred = logdet_s + 96;                                        // [NW][K]
     double* jred = gred + C::NW * K;                                     // [64]
-    cd* colbuf = reinterpret_cast<cd*>(jred + 64);                       // [K][DP] sweep column
-    double* pivbuf = reinterpret_cast<double*>(colbuf + K * DP);         // [K][DP] sweep pivots
+    double* pivbuf = jred + 64;                                          // [K][DP] sweep pivots
     JacobiRot* jrot = reinterpret_cast<JacobiRot*>(pivbuf + K * DP);     // [16]
     int* flags_s = reinterpret_cast<int*>(jrot + 16);                    // [K] slow-path flags, [31] exact flag
     unsigned short* tri_tab = reinterpret_cast<unsigned short*>(flags_s + 32);   // [NP] (i << 8 | c)
@@ -369,45 +368,66 @@ __global__ void __launch_bounds__(NT, MINB) cacgmm_em_kernel(const CacgmmParams 
         __syncthreads();
 
         // ---- fast path: B_k = (Phi_k / tr)^-1 for all classes at once with the symmetric sweep
-        //      operator (in place, packed lower; pivots = Cholesky pivots^2, logdet = sum log pivots)
-        cd* S = reinterpret_cast<cd*>(ys_raw);            // [K][NPD]
+        //      operator (in place, packed lower; pivots = Cholesky pivots^2, logdet = sum log pivots).
+        //      Thread-private entry metadata is decoded once per pass; one barrier per sweep step
+        //      (the column of the next pivot is forwarded while the current step is applied).
+        cd* S = reinterpret_cast<cd*>(ys_raw);                                  // [K][NP]
+        cd* colb = S + K * C::NP;                                               // [2][K][DP] column of the pivot
+        double* pivb = reinterpret_cast<double*>(colb + 2 * K * DP);            // [2][K]
         const bool need_exact = flags_s[31] != 0;
         if (!need_exact) {
-            for (int e = tid; e < K * NPD; e += NT) {
-                const int k = e / NPD, r = e - k * NPD;
-                const double tr = tr_s[k];
-                const double itr = (tr > 0.0 && isfinite(tr)) ? 1.0 / tr : 0.0;
-                cd v = cscale(acc_sm[k * C::NP + r], itr);
-                const unsigned ic = tri_tab[r];
-                if ((ic >> 8) == (ic & 255)) v.y = 0.0;       // force_hermitian (utils.py:323-334)
-                S[e] = v;
+            constexpr int EPT = (K * C::NP + NT - 1) / NT;                      // entries per thread
+            int ent_meta[EPT];                                                  // k << 16 | i << 8 | c ; -1 = none
+#pragma unroll
+            for (int n = 0; n < EPT; ++n) {
+                const int e = tid + n * NT;
+                int meta = -1;
+                if (e < K * C::NP) {
+                    const int k = e / C::NP, r = e - k * C::NP;
+                    if (r < NPD) {
+                        const unsigned ic = tri_tab[r];
+                        const int i = ic >> 8, c = ic & 255;
+                        meta = (k << 16) | (i << 8) | c;
+                        const double tr = tr_s[k];
+                        const double itr = (tr > 0.0 && isfinite(tr)) ? 1.0 / tr : 0.0;
+                        cd v = cscale(acc_sm[e], itr);
+                        if (i == c) v.y = 0.0;                                  // force_hermitian (utils.py:323-334)
+                        S[e] = v;
+                        if (c == 0) {                                           // column of the first pivot
+                            colb[k * DP + i] = v;
+                            if (i == 0) pivb[k] = v.x;
+                        }
+                    }
+                }
+                ent_meta[n] = meta;
             }
             __syncthreads();
             for (int j = 0; j < D; ++j) {
-                for (int e = tid; e < K * D; e += NT) {
-                    const int k = e / D, i = e - k * D;
-                    const cd* Sk = S + k * NPD;
-                    const cd u = (i >= j) ? Sk[tri(i, j)] : cconj(Sk[tri(j, i)]);
-                    colbuf[k * DP + i] = u;
-                    if (i == j) pivbuf[k * DP + j] = u.x;
-                }
-                __syncthreads();
-                for (int e = tid; e < K * NPD; e += NT) {
-                    const int k = e / NPD, r = e - k * NPD;
-                    const unsigned ic = tri_tab[r];
-                    const int i = ic >> 8, c = ic & 255;
-                    const double piv = pivbuf[k * DP + j];
-                    const double d = (piv > 0.0 && isfinite(piv)) ? 1.0 / piv : 0.0;
+                const cd* col = colb + (j & 1) * K * DP;
+                cd* coln = colb + ((j + 1) & 1) * K * DP;
+                const double* piv = pivb + (j & 1) * K;
+                double* pivn = pivb + ((j + 1) & 1) * K;
+#pragma unroll
+                for (int n = 0; n < EPT; ++n) {
+                    const int meta = ent_meta[n];
+                    if (meta < 0) continue;
+                    const int k = meta >> 16, i = (meta >> 8) & 255, c = meta & 255;
+                    const int e = tid + n * NT;
+                    const double pv = piv[k];
+                    const double d = (pv > 0.0 && isfinite(pv)) ? 1.0 / pv : 0.0;
                     cd v;
-                    if (i == j && c == j) v = cmake(-d, 0.0);
-                    else if (c == j) v = cscale(colbuf[k * DP + i], d);
-                    else if (i == j) v = cscale(cconj(colbuf[k * DP + c]), d);
+                    if (i == j && c == j) { v = cmake(-d, 0.0); pivbuf[k * DP + j] = pv; }
+                    else if (c == j) v = cscale(col[k * DP + i], d);
+                    else if (i == j) v = cscale(cconj(col[k * DP + c]), d);
                     else {
                         v = S[e];
-                        cd ud = cscale(colbuf[k * DP + i], d);
-                        cfmsc(v, ud, colbuf[k * DP + c]);
+                        const cd ud = cscale(col[k * DP + i], d);
+                        cfmsc(v, ud, col[k * DP + c]);
                     }
                     S[e] = v;
+                    // forward the column of the next pivot
+                    if (c == j + 1) { coln[k * DP + i] = v; if (i == j + 1) pivn[k] = v.x; }
+                    else if (i == j + 1) coln[k * DP + c] = cconj(v);
                 }
                 __syncthreads();
             }
@@ -416,10 +436,10 @@ __global__ void __launch_bounds__(NT, MINB) cacgmm_em_kernel(const CacgmmParams 
                 double ld = 0.0, trb = 0.0;
                 bool bad = false;
                 if (lane < D) {
-                    const double piv = pivbuf[k * DP + lane];
-                    bad = !(piv > 0.0) || !isfinite(piv);
-                    ld = bad ? 0.0 : log(piv);
-                    trb = -S[k * NPD + tri(lane, lane)].x;
+                    const double pv = pivbuf[k * DP + lane];
+                    bad = !(pv > 0.0) || !isfinite(pv);
+                    ld = bad ? 0.0 : log(pv);
+                    trb = -S[k * C::NP + tri(lane, lane)].x;
                 }
                 ld = warp_sum(ld); trb = warp_sum(trb);
                 bad = __any_sync(0xffffffffu, bad);
@@ -429,12 +449,13 @@ __global__ void __launch_bounds__(NT, MINB) cacgmm_em_kernel(const CacgmmParams 
                 else if (lane == 0) logdet_s[k] = ld;
             }
             __syncthreads();
-            for (int e = tid; e < K * NPD; e += NT) {
-                const int k = e / NPD, r = e - k * NPD;
+#pragma unroll
+            for (int n = 0; n < EPT; ++n) {
+                const int meta = ent_meta[n];
+                if (meta < 0) continue;
+                const int k = meta >> 16, i = (meta >> 8) & 255, c = meta & 255;
                 if (flags_s[k]) continue;
-                const unsigned ic = tri_tab[r];
-                const int i = ic >> 8, c = ic & 255;
-                const cd v = S[e];
+                const cd v = S[tid + n * NT];
                 Bsm[tri(i, c) * K + k] = (i == c) ? cmake(-v.x, 0.0) : cmake(-2.0 * v.x, -2.0 * v.y);
             }
             __syncthreads();
