@@ -24,6 +24,7 @@ if len(sys.argv) > 2:
     hdr = rows[1]; data = rows[2:]
     si = hdr.index('# Samples'); so = hdr.index('Source'); ie = hdr.index('Instructions Executed')
     s0 = hdr.index('stall_barrier'); names = hdr[s0:s0 + 17]
+    data = [r for r in data if len(r) > si and not r[0].startswith('Kernel Name') and r[0] != 'Address']
     tot = sum(int(r[si] or 0) for r in data)
     seg_start = 0; segs = []
     for i, r in enumerate(data):
