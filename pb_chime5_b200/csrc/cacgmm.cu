@@ -44,7 +44,6 @@ constexpr size_t cmax(size_t a, size_t b) { return a > b ? a : b; }
 __host__ __device__ constexpr int sub_block(int DP) {
     return DP < 12 ? DP : (DP % 6 == 0 ? 6 : 4);
 }
-
 template <int DP, int K, int NT>
 struct CacgmmCfg {
     static constexpr int NP = DP * (DP + 1) / 2;          // packed Hermitian pairs
@@ -207,10 +206,10 @@ __global__ void __launch_bounds__(NT, MINB) cacgmm_em_kernel(const CacgmmParams 
             }
             __syncthreads();
             {
-                const float2* yrow = yf + tid * C::YLD;
                 double qa[K], qb[K];
 #pragma unroll
                 for (int k = 0; k < K; ++k) { qa[k] = 0.0; qb[k] = 0.0; }
+                const float2* yrow = yf + tid * C::YLD;
                 if (pass > 0) QuadAll<DP, K, 0, C::NSB>::run(yrow, Bsm, qa, qb);
                 const int t = s0 + tid;
                 if (t < s1) {
@@ -287,7 +286,9 @@ __global__ void __launch_bounds__(NT, MINB) cacgmm_em_kernel(const CacgmmParams 
                 for (int i = tid; i < DP * TM; i += NT) {
                     const int t = i / DP, d = i - t * DP;
                     const float2 v = ystage[t * C::YLD + d];
-                    yd[t * C::YLD + d] = cmake((double)v.x, (double)v.y);
+                    // planar rows: even channels first, then odd ones, so that the 2x2 blocks of
+                    // consecutive lanes read consecutive 16 B chunks (conflict-free LDS.128)
+                    yd[t * C::YLD + (d & 1) * (DP / 2) + (d >> 1)] = cmake((double)v.x, (double)v.y);
                 }
                 __syncthreads();
                 if (t0 + TM < s1) {           // stage the next tile while this one is consumed
@@ -301,7 +302,7 @@ __global__ void __launch_bounds__(NT, MINB) cacgmm_em_kernel(const CacgmmParams 
                     const int tn = min(TM, s1 - t0);
                     for (int t = m_g; t < tn; t += C::NG) {
                         const cd* yrow = yd + t * C::YLD;
-                        const cd a0 = yrow[r0], a1 = yrow[r0 + 1], b0 = yrow[c0], b1 = yrow[c0 + 1];
+                        const cd a0 = yrow[bi], a1 = yrow[DP / 2 + bi], b0 = yrow[bj], b1 = yrow[DP / 2 + bj];
                         cd P[4];
                         P[0] = cmulc(a0, b0); P[1] = cmulc(a0, b1);
                         P[2] = cmulc(a1, b0); P[3] = cmulc(a1, b1);
