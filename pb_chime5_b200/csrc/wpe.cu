@@ -134,12 +134,15 @@ __global__ void __launch_bounds__(CT_NT) wpe_corr_kernel(const float2* __restric
     for (int a = 0; a < 3; ++a)
 #pragma unroll
         for (int b = 0; b < 3; ++b) { cre[a][b][0] = cre[a][b][1] = 0.0; cim[a][b][0] = cim[a][b][1] = 0.0; }
+    // a warp whose 24 x 24 sub-tile is entirely above the diagonal or below the last row has no work
+    const bool warp_live = !(rt == ct && wn > wm) && (i0 + 24 * wm < m.LD + m.D) && (j0 + 24 * wn < m.LD);
     stage(0, 0);
     int buf = 0;
     for (int t0 = 0; t0 < m.T; t0 += CT_BK, buf ^= 1) {
         asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;\n" ::: "memory");
         __syncthreads();                                   // chunk `buf` landed; everybody left chunk buf^1
         if (t0 + CT_BK < m.T) stage(buf ^ 1, t0 + CT_BK);  // prefetch behind the MMAs
+        if (!warp_live) continue;
 #pragma unroll
         for (int ks = 0; ks < CT_BK / 4; ++ks) {
             const int kk = ks * 4 + tg;
@@ -213,16 +216,18 @@ __device__ inline void warp_tri_inverse_deflated(cd* Dg, int nb, int lane) {
     }
 }
 
-template <int NT>
-__global__ void __launch_bounds__(NT) wpe_panel_kernel(cd* __restrict__ Raug, int* __restrict__ info, WpeDims m, int j0) {
-    __shared__ __align__(16) cd Dg[WS_NB * (WS_NB + 1) / 2];   // packed diagonal block -> its inverse
-    __shared__ int bad[WS_NB];
+// One warp per bin: Cholesky of the diagonal block (zero-pivot deflation), L11 written back,
+// its inverse (packed lower) to `Minv` for the panel rows and the back substitution.
+__global__ void __launch_bounds__(32) wpe_diag_kernel(cd* __restrict__ Raug, cd* __restrict__ Minv,
+                                                      int* __restrict__ info, WpeDims m, int j0, int jb) {
+    __shared__ __align__(16) cd Dg[WS_NB * (WS_NB + 1) / 2];
     const size_t bf = blockIdx.x;
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int lane = threadIdx.x;
     const int n = m.LD, nrows = m.LD + m.D;
     const int nb = min(WS_NB, n - j0);
+    const int nblk = (n + WS_NB - 1) / WS_NB;
     cd* A = Raug + bf * (size_t)nrows * n;
-    for (int e = tid; e < nb * (nb + 1) / 2; e += NT) {
+    for (int e = lane; e < nb * (nb + 1) / 2; e += 32) {
         int r = 0;
         while ((r + 1) * (r + 2) / 2 <= e) ++r;
         const int c = e - r * (r + 1) / 2;
@@ -230,59 +235,73 @@ __global__ void __launch_bounds__(NT) wpe_panel_kernel(cd* __restrict__ Raug, in
         if (r == c) v.y = 0.0;
         Dg[e] = v;
     }
-    __syncthreads();
-    if (warp == 0) {
-        for (int j = 0; j < nb; ++j) {          // Cholesky with zero-pivot deflation
-            cd s = cmake(0.0, 0.0);
-            if (lane >= j && lane < nb) {
-                s = Dg[tri(lane, j)];
-                for (int pp = 0; pp < j; ++pp) cfmsc(s, Dg[tri(lane, pp)], Dg[tri(j, pp)]);
-            }
-            const double djj = __shfl_sync(0xffffffffu, s.x, j);
-            const bool okp = djj > 0.0 && isfinite(djj);
-            const double rr = okp ? sqrt(djj) : 0.0;
-            const double ri = okp ? 1.0 / rr : 0.0;
-            if (lane == j) { Dg[tri(j, j)] = cmake(rr, 0.0); bad[j] = okp ? 0 : 1; }
-            else if (lane > j && lane < nb) Dg[tri(lane, j)] = cscale(s, ri);
-            __syncwarp();
+    __syncwarp();
+    bool any_bad = false;
+    for (int j = 0; j < nb; ++j) {
+        cd s = cmake(0.0, 0.0), s2 = cmake(0.0, 0.0);
+        if (lane >= j && lane < nb) {
+            s = Dg[tri(lane, j)];
+            int pp = 0;
+            for (; pp + 1 < j; pp += 2) { cfmsc(s, Dg[tri(lane, pp)], Dg[tri(j, pp)]); cfmsc(s2, Dg[tri(lane, pp + 1)], Dg[tri(j, pp + 1)]); }
+            if (pp < j) cfmsc(s, Dg[tri(lane, pp)], Dg[tri(j, pp)]);
+            s = cadd(s, s2);
         }
+        const double djj = __shfl_sync(0xffffffffu, s.x, j);
+        const bool okp = djj > 0.0 && isfinite(djj);
+        any_bad |= !okp;
+        const double rr = okp ? sqrt(djj) : 0.0;
+        const double ri = okp ? 1.0 / rr : 0.0;
+        if (lane == j) Dg[tri(j, j)] = cmake(rr, 0.0);
+        else if (lane > j && lane < nb) Dg[tri(lane, j)] = cscale(s, ri);
+        __syncwarp();
     }
-    __syncthreads();
-    for (int e = tid; e < nb * (nb + 1) / 2; e += NT) {
+    for (int e = lane; e < nb * (nb + 1) / 2; e += 32) {
         int r = 0;
         while ((r + 1) * (r + 2) / 2 <= e) ++r;
         const int c = e - r * (r + 1) / 2;
         A[(size_t)(j0 + r) * n + j0 + c] = Dg[e];
     }
+    __syncwarp();
+    warp_tri_inverse_deflated(Dg, nb, lane);
+    cd* out = Minv + (bf * nblk + jb) * (size_t)(WS_NB * (WS_NB + 1) / 2);
+    for (int e = lane; e < nb * (nb + 1) / 2; e += 32) out[e] = Dg[e];
+    if (lane == 0 && any_bad && info) atomicMax(&info[bf / m.F], GSS_INFO_SINGULAR | ((int)(bf % m.F) << 8));
+}
+
+// panel rows below the diagonal block:  L[r, jblock] = A[r, jblock] * L11^{-H}; one thread per row
+constexpr int PR_NT = 128;
+__global__ void __launch_bounds__(PR_NT) wpe_panel_rows_kernel(cd* __restrict__ Raug, const cd* __restrict__ Minv,
+                                                               WpeDims m, int j0, int jb) {
+    __shared__ __align__(16) cd Dg[WS_NB * (WS_NB + 1) / 2];
+    const size_t bf = blockIdx.x;
+    const int tid = threadIdx.x;
+    const int n = m.LD, nrows = m.LD + m.D;
+    const int nb = min(WS_NB, n - j0);
+    const int nblk = (n + WS_NB - 1) / WS_NB;
+    const int r = j0 + nb + blockIdx.y * PR_NT + tid;
+    if (j0 + nb + blockIdx.y * PR_NT >= nrows) return;
+    const cd* mi = Minv + (bf * nblk + jb) * (size_t)(WS_NB * (WS_NB + 1) / 2);
+    for (int e = tid; e < nb * (nb + 1) / 2; e += PR_NT) Dg[e] = mi[e];
     __syncthreads();
-    if (warp == 0) warp_tri_inverse_deflated(Dg, nb, lane);
-    if (tid == 0 && info) {
-        int any = 0;
-        for (int j = 0; j < nb; ++j) any |= bad[j];
-        if (any) atomicMax(&info[bf / m.F], GSS_INFO_SINGULAR | ((int)(bf % m.F) << 8));
-    }
-    __syncthreads();
-    // panel rows below the diagonal block:  L[r, jblock] = A[r, jblock] * L11^{-H}
-    for (int r = j0 + nb + tid; r < nrows; r += NT) {
-        cd acc[WS_NB];
-        cd* row = A + (size_t)r * n + j0;
+    if (r >= nrows) return;
+    cd* row = Raug + bf * (size_t)nrows * n + (size_t)r * n + j0;
+    cd acc[WS_NB];
 #pragma unroll
-        for (int c = 0; c < WS_NB; ++c) acc[c] = c < nb ? row[c] : cmake(0.0, 0.0);
-        // in place, last column first: acc[c] <- sum_{q <= c} acc[q] conj(Minv[c][q])
+    for (int c = 0; c < WS_NB; ++c) acc[c] = c < nb ? row[c] : cmake(0.0, 0.0);
+    // in place, last column first: acc[c] <- sum_{q <= c} acc[q] conj(Minv[c][q])
 #pragma unroll
-        for (int c = WS_NB - 1; c >= 0; --c) {
-            if (c < nb) {
-                cd o = cmake(0.0, 0.0);
+    for (int c = WS_NB - 1; c >= 0; --c) {
+        if (c < nb) {
+            cd o = cmake(0.0, 0.0);
 #pragma unroll
-                for (int q = 0; q < WS_NB; ++q)
-                    if (q <= c) cfmac(o, acc[q], Dg[tri(c, q)]);
-                acc[c] = o;
-            }
+            for (int q = 0; q < WS_NB; ++q)
+                if (q <= c) cfmac(o, acc[q], Dg[tri(c, q)]);
+            acc[c] = o;
         }
-#pragma unroll
-        for (int c = 0; c < WS_NB; ++c)
-            if (c < nb) row[c] = acc[c];
     }
+#pragma unroll
+    for (int c = 0; c < WS_NB; ++c)
+        if (c < nb) row[c] = acc[c];
 }
 
 // A22 -= L21 L21^H on the trailing matrix (origin j1 = j0 + nb).  Same tiling / MMA
@@ -363,100 +382,172 @@ __global__ void __launch_bounds__(CT_NT) wpe_trail_kernel(cd* __restrict__ Raug,
     }
 }
 
-// blocked back substitution  L^H G = Z ,  Z^H sits in rows [n, n + D) of Raug
-template <int NT>
-__global__ void __launch_bounds__(NT) wpe_backsub_kernel(const cd* __restrict__ Raug, cd* __restrict__ G, WpeDims m) {
-    __shared__ __align__(16) cd Dg[WS_NB * (WS_NB + 1) / 2];
-    __shared__ __align__(16) cd Sm[WS_NB][33];               // [i][d], d < 32
-    const size_t bf = blockIdx.x;
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int n = m.LD, nrows = m.LD + m.D;
-    const cd* A = Raug + bf * (size_t)nrows * n;
-    cd* Gb = G + bf * (size_t)n * m.D;
-    const int nblk = (n + WS_NB - 1) / WS_NB;
-    for (int jb = nblk - 1; jb >= 0; --jb) {
-        const int j0 = jb * WS_NB, nb = min(WS_NB, n - j0);
-        // S[i][d] = Z[j0+i][d] - sum_{r >= j0+nb} conj(L[r][j0+i]) G[r][d]
-        for (int e = tid; e < nb * m.D; e += NT) {
-            const int d = e / nb, i = e - d * nb;
-            cd s = cconj(A[(size_t)(n + d) * n + j0 + i]);
-            cd s2 = cmake(0.0, 0.0);
-            int r = j0 + nb;
-            for (; r + 1 < n; r += 2) {
-                cfms(s, cconj(A[(size_t)r * n + j0 + i]), Gb[(size_t)r * m.D + d]);
-                cfms(s2, cconj(A[(size_t)(r + 1) * n + j0 + i]), Gb[(size_t)(r + 1) * m.D + d]);
-            }
-            if (r < n) cfms(s, cconj(A[(size_t)r * n + j0 + i]), Gb[(size_t)r * m.D + d]);
-            Sm[i][d] = cadd(s, s2);
-        }
-        for (int e = tid; e < nb * (nb + 1) / 2; e += NT) {
-            int rr = 0;
-            while ((rr + 1) * (rr + 2) / 2 <= e) ++rr;
-            const int c = e - rr * (rr + 1) / 2;
-            Dg[e] = A[(size_t)(j0 + rr) * n + j0 + c];
-        }
-        __syncthreads();
-        if (warp == 0) warp_tri_inverse_deflated(Dg, nb, lane);
-        __syncthreads();
-        // G[j0+i][d] = sum_{q >= i} conj(Minv[q][i]) S[q][d]
-        for (int e = tid; e < nb * m.D; e += NT) {
-            const int d = e / nb, i = e - d * nb;
-            cd s = cmake(0.0, 0.0);
-            for (int q = i; q < nb; ++q) cfma(s, cconj(Dg[tri(q, i)]), Sm[q][d]);
-            Gb[(size_t)(j0 + i) * m.D + d] = s;
-        }
-        __syncthreads();
-    }
-}
-
-// ---------------------------------------------------------------------------
-// X = Y - G^H Yt ; one thread per frame, all D outputs in registers.
-// ---------------------------------------------------------------------------
-template <int DMAX, int NT>
-__global__ void __launch_bounds__(NT) wpe_apply_kernel(const float2* __restrict__ Y, const cd* __restrict__ G,
-                                                       float2* __restrict__ X, double* __restrict__ power, WpeDims m) {
+// Blocked right-looking back substitution  L^H G = Z  (Z^H sits in rows [n, n + D) of Raug).
+// The right-hand sides S (n x D) stay in shared memory; per block row, last to first:
+//   G_j = L_jj^{-H} S_j ;   S_i -= sum_q conj(L[j0+q][i]) G_j[q]   for all rows i above the block
+// (coalesced, independent loads of L; no dependent global round trips).
+template <int NT, int DMAX>
+__global__ void __launch_bounds__(NT) wpe_backsub_kernel(const cd* __restrict__ Raug, const cd* __restrict__ Minv,
+                                                         cd* __restrict__ G, WpeDims m) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    cd* Gs = reinterpret_cast<cd*>(smem_raw);                         // [LD][D]
+    cd* S = reinterpret_cast<cd*>(smem_raw);                       // [n][D]
+    cd* Gj = S + (size_t)m.LD * m.D;                               // [WS_NB][D]
+    cd* Dg = Gj + WS_NB * m.D;                                     // packed inverse of the diagonal block
     const size_t bf = blockIdx.x;
     const int tid = threadIdx.x;
-    const float2* __restrict__ Yg = Y + bf * m.D * m.T;
-    const cd* Gb = G + bf * (size_t)m.LD * m.D;
-    for (int i = tid; i < m.LD * m.D; i += NT) Gs[i] = Gb[i];
-    __syncthreads();
-    const int t = blockIdx.y * NT + tid;
-    if (t >= m.T) return;
-    cd acc[DMAX];
-#pragma unroll
-    for (int d = 0; d < DMAX; ++d) {
-        acc[d] = cmake(0.0, 0.0);
-        if (d < m.D) { const float2 v = Yg[(size_t)d * m.T + t]; acc[d] = cmake((double)v.x, (double)v.y); }
+    const int n = m.LD, nrows = m.LD + m.D, D = m.D;
+    const cd* A = Raug + bf * (size_t)nrows * n;
+    cd* Gb = G + bf * (size_t)n * D;
+    const int nblk = (n + WS_NB - 1) / WS_NB;
+    for (int e = tid; e < n * D; e += NT) {
+        const int d = e / n, i = e - d * n;                        // coalesced along i
+        S[i * D + d] = cconj(A[(size_t)(n + d) * n + i]);
     }
-    for (int k = 0; k < m.L; ++k) {
-        const int ts = t - m.delay - k;
-        if (ts < 0) break;
-        for (int dp = 0; dp < m.D; ++dp) {
-            const float2 v = __ldg(&Yg[(size_t)dp * m.T + ts]);
-            const cd y = cmake((double)v.x, (double)v.y);
-            const cd* g = Gs + (size_t)(k * m.D + dp) * m.D;
+    for (int jb = nblk - 1; jb >= 0; --jb) {
+        const int j0 = jb * WS_NB, nb = min(WS_NB, n - j0);
+        const cd* mi = Minv + (bf * nblk + jb) * (size_t)(WS_NB * (WS_NB + 1) / 2);
+        for (int e = tid; e < nb * (nb + 1) / 2; e += NT) Dg[e] = mi[e];
+        __syncthreads();
+        // G[j0+i][d] = sum_{q >= i} conj(Minv[q][i]) S[j0+q][d]
+        for (int e = tid; e < nb * D; e += NT) {
+            const int i = e / D, d = e - i * D;
+            cd s = cmake(0.0, 0.0);
+            for (int q = i; q < nb; ++q) cfma(s, cconj(Dg[tri(q, i)]), S[(j0 + q) * D + d]);
+            Gj[i * D + d] = s;
+            Gb[(size_t)(j0 + i) * D + d] = s;
+        }
+        __syncthreads();
+        // rows above the block: one thread per row, all right-hand sides in registers
+        for (int i = tid; i < j0; i += NT) {
+            cd acc[DMAX];
+#pragma unroll
+            for (int d = 0; d < DMAX; ++d) acc[d] = d < D ? S[i * D + d] : cmake(0.0, 0.0);
+            for (int q = 0; q < nb; ++q) {
+                const cd l = cconj(A[(size_t)(j0 + q) * n + i]);
+#pragma unroll
+                for (int d = 0; d < DMAX; ++d)
+                    if (d < D) cfms(acc[d], l, Gj[q * D + d]);
+            }
 #pragma unroll
             for (int d = 0; d < DMAX; ++d)
-                if (d < m.D) cfms(acc[d], cconj(g[d]), y);
+                if (d < D) S[i * D + d] = acc[d];
         }
+        __syncthreads();
     }
-    double pw = 0.0;
-#pragma unroll
-    for (int d = 0; d < DMAX; ++d) {
-        if (d < m.D) {
-            const float2 o = make_float2((float)acc[d].x, (float)acc[d].y);
-            X[bf * m.D * m.T + (size_t)d * m.T + t] = o;
-            // the reference iterates on the float64 X; use the unrounded value for the power
-            pw += cabs2(acc[d]);
-        }
-    }
-    power[bf * m.T + t] = pw / m.D;
 }
 
-struct WpeWs { double* power; double* inv; cd* Raug; cd* G; size_t bytes; };
+// ---------------------------------------------------------------------------
+// X = Y - G^H Yt  (+ mean_d |X|^2 for the next iteration) as a complex GEMM on the FP64
+// tensor-core MMA: M = channels (MT tiles of 8), N = 64 frames per CTA (4 warps x 16),
+// K = taps x channels, streamed one tap (a DP4 x D block of G) at a time with cp.async.
+// ---------------------------------------------------------------------------
+constexpr int AP_NT = 128, AP_TN = 64;
+__host__ __device__ constexpr int ap_gld(int MT) { return MT <= 3 ? 26 : 34; }   // = 2 mod 8: conflict-free LDS.128 fragments
+
+template <int MT>
+__global__ void __launch_bounds__(AP_NT) wpe_apply_kernel(const float2* __restrict__ Y, const cd* __restrict__ G,
+                                                          float2* __restrict__ X, double* __restrict__ power, WpeDims m) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int D = m.D, DP4 = (D + 3) & ~3, hist = m.delay + m.L - 1;
+    const int YW = AP_TN + hist, YLD = YW | 1;                         // odd row stride (float2)
+    constexpr int AP_GLD = ap_gld(MT);
+    cd* Gs = reinterpret_cast<cd*>(smem_raw);                          // [2][DP4][AP_GLD]
+    float2* Ys = reinterpret_cast<float2*>(Gs + 2 * DP4 * AP_GLD);     // [DP4][YLD]
+    const size_t bf = blockIdx.x;
+    const int t0 = blockIdx.y * AP_TN;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int g = lane >> 2, tg = lane & 3;
+    const float2* __restrict__ Yg = Y + bf * (size_t)D * m.T;
+    const cd* __restrict__ Gb = G + bf * (size_t)m.LD * D;
+    auto stage_g = [&](int buf, int k) {
+        cd* dst = Gs + buf * DP4 * AP_GLD;
+        for (int e = tid; e < DP4 * 8 * MT; e += AP_NT) {
+            const int dp = e / (8 * MT), d = e - dp * (8 * MT);
+            if (dp < D && d < D) {
+                const unsigned sa = (unsigned)__cvta_generic_to_shared(&dst[dp * AP_GLD + d]);
+                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(sa), "l"(&Gb[(size_t)(k * D + dp) * D + d]) : "memory");
+            } else dst[dp * AP_GLD + d] = cmake(0.0, 0.0);
+        }
+    };
+    stage_g(0, 0);
+    for (int e = tid; e < DP4 * YW; e += AP_NT) {
+        const int d = e / YW, c = e - d * YW;
+        const int t = t0 - hist + c;
+        float2 v = make_float2(0.f, 0.f);
+        if (d < D && t >= 0 && t < m.T) v = __ldg(&Yg[(size_t)d * m.T + t]);
+        Ys[d * YLD + c] = v;
+    }
+    double cre[MT][2][2], cim[MT][2][2];
+#pragma unroll
+    for (int a = 0; a < MT; ++a)
+#pragma unroll
+        for (int b = 0; b < 2; ++b) { cre[a][b][0] = cre[a][b][1] = 0.0; cim[a][b][0] = cim[a][b][1] = 0.0; }
+    for (int k = 0; k < m.L; ++k) {
+        const int buf = k & 1;
+        asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;\n" ::: "memory");
+        __syncthreads();
+        if (k + 1 < m.L) stage_g(buf ^ 1, k + 1);
+        const cd* gs = Gs + buf * DP4 * AP_GLD;
+        const int coff = hist - (m.delay + k) + 16 * warp + g;       // column of frame (t0 + 16 warp + g) shifted by delay + k
+        for (int ks = 0; ks < DP4 / 4; ++ks) {
+            const int dp = ks * 4 + tg;
+            double gre[MT], gim[MT], ngim[MT], bre[2], bim[2];
+#pragma unroll
+            for (int q = 0; q < MT; ++q) {
+                const cd v = gs[dp * AP_GLD + 8 * q + g];
+                gre[q] = v.x; gim[q] = v.y; ngim[q] = -v.y;
+            }
+#pragma unroll
+            for (int q = 0; q < 2; ++q) {
+                const float2 v = Ys[dp * YLD + coff + 8 * q];
+                bre[q] = (double)v.x; bim[q] = (double)v.y;
+            }
+#pragma unroll
+            for (int mi = 0; mi < MT; ++mi)
+#pragma unroll
+                for (int ni = 0; ni < 2; ++ni) {
+                    // C = conj(G)^T Yt :  re += Gre Bre + Gim Bim ;  im += Gre Bim - Gim Bre
+                    dmma884(cre[mi][ni][0], cre[mi][ni][1], gre[mi], bre[ni]);
+                    dmma884(cre[mi][ni][0], cre[mi][ni][1], gim[mi], bim[ni]);
+                    dmma884(cim[mi][ni][0], cim[mi][ni][1], gre[mi], bim[ni]);
+                    dmma884(cim[mi][ni][0], cim[mi][ni][1], ngim[mi], bre[ni]);
+                }
+        }
+    }
+    // X = Y - C ; power of the unrounded X (the reference iterates on float64)
+    double pw[2][2] = {{0.0, 0.0}, {0.0, 0.0}};
+#pragma unroll
+    for (int mi = 0; mi < MT; ++mi) {
+        const int d = 8 * mi + g;
+#pragma unroll
+        for (int ni = 0; ni < 2; ++ni) {
+            const int tl = 16 * warp + 8 * ni + 2 * tg;
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const int t = t0 + tl + h;
+                if (d < D && t < m.T) {
+                    const float2 y = Ys[d * YLD + hist + tl + h];
+                    const double xr = (double)y.x - cre[mi][ni][h], xi = (double)y.y - cim[mi][ni][h];
+                    X[bf * (size_t)D * m.T + (size_t)d * m.T + t] = make_float2((float)xr, (float)xi);
+                    pw[ni][h] += xr * xr + xi * xi;
+                }
+            }
+        }
+    }
+#pragma unroll
+    for (int ni = 0; ni < 2; ++ni)
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            double v = pw[ni][h];
+            v += __shfl_xor_sync(0xffffffffu, v, 4);
+            v += __shfl_xor_sync(0xffffffffu, v, 8);
+            v += __shfl_xor_sync(0xffffffffu, v, 16);
+            const int t = t0 + 16 * warp + 8 * ni + 2 * tg + h;
+            if (g == 0 && t < m.T) power[bf * m.T + t] = v / D;
+        }
+}
+
+struct WpeWs { double* power; double* inv; cd* Raug; cd* G; cd* Minv; size_t bytes; };
 
 static WpeWs wpe_ws_layout(void* ws, int Bc, int F, int D, int T, int LD) {
     Arena a(ws, ~size_t(0));
@@ -465,6 +556,7 @@ static WpeWs wpe_ws_layout(void* ws, int Bc, int F, int D, int T, int LD) {
     w.inv = a.take<double>((size_t)Bc * F * T);
     w.Raug = a.take<cd>((size_t)Bc * F * (LD + D) * LD);
     w.G = a.take<cd>((size_t)Bc * F * LD * D);
+    w.Minv = a.take<cd>((size_t)Bc * F * ((LD + WS_NB - 1) / WS_NB) * (WS_NB * (WS_NB + 1) / 2));
     w.bytes = a.off;
     return w;
 }
@@ -472,13 +564,22 @@ static WpeWs wpe_ws_layout(void* ws, int Bc, int F, int D, int T, int LD) {
 size_t wpe_ws_bytes(int Bc, int F, int D, int T, int L) { return wpe_ws_layout(nullptr, Bc, F, D, T, L * D).bytes; }
 
 template <int DMAX>
-static int launch_apply(const float2* Y, const cd* G, float2* X, double* power, const WpeDims& m, int BF, cudaStream_t st) {
-    constexpr int NT = 128;
-    const size_t smem = (size_t)m.LD * m.D * sizeof(cd);
-    auto kern = wpe_apply_kernel<DMAX, NT>;
+static int launch_backsub(const cd* Raug, const cd* Minv, cd* G, const WpeDims& m, int BF, size_t smem, cudaStream_t st) {
+    auto kern = wpe_backsub_kernel<256, DMAX>;
     GSS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    dim3 grid(BF, (m.T + NT - 1) / NT);
-    kern<<<grid, NT, smem, st>>>(Y, G, X, power, m);
+    kern<<<BF, 256, smem, st>>>(Raug, Minv, G, m);
+    GSS_LAUNCH_CHECK("wpe_backsub_kernel");
+    return GSS_OK;
+}
+
+template <int MT>
+static int launch_apply(const float2* Y, const cd* G, float2* X, double* power, const WpeDims& m, int BF, cudaStream_t st) {
+    const int DP4 = (m.D + 3) & ~3, hist = m.delay + m.L - 1, YLD = (AP_TN + hist) | 1;
+    const size_t smem = (size_t)2 * DP4 * ap_gld(MT) * sizeof(cd) + (size_t)DP4 * YLD * sizeof(float2);
+    auto kern = wpe_apply_kernel<MT>;
+    GSS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    dim3 grid(BF, (m.T + AP_TN - 1) / AP_TN);
+    kern<<<grid, AP_NT, smem, st>>>(Y, G, X, power, m);
     GSS_LAUNCH_CHECK("wpe_apply_kernel");
     return GSS_OK;
 }
@@ -494,8 +595,8 @@ extern "C" int gss_wpe_c64(const gss_c64* Y, gss_c64* X, int taps, int delay, in
                 "gss_wpe_c64: taps=%d delay=%d iterations=%d psd_context=%d", taps, delay, iterations, psd_context);
     GSS_REQUIRE(D <= 32, GSS_ERR_UNSUPPORTED, "gss_wpe_c64: D=%d > 32 not built", D);
     const int LD = taps * D;
-    GSS_REQUIRE((size_t)LD * D * sizeof(cd) <= 200 * 1024, GSS_ERR_UNSUPPORTED,
-                "gss_wpe_c64: taps*D*D=%d too large for the filter tile", LD * D);
+    GSS_REQUIRE(((size_t)LD * D + 24 * D + 300) * sizeof(cd) <= 220 * 1024, GSS_ERR_UNSUPPORTED,
+                "gss_wpe_c64: taps*D*D=%d too large for the back-substitution tile", LD * D);
     cudaStream_t st = (cudaStream_t)stream;
     if (B == 0 || F == 0) return GSS_OK;
     if (iterations == 0) {
@@ -522,24 +623,33 @@ extern "C" int gss_wpe_c64(const gss_c64* Y, gss_c64* X, int taps, int delay, in
             dim3 grid(BF, (LD + D + CT_BM - 1) / CT_BM, (LD + CT_BM - 1) / CT_BM);
             wpe_corr_kernel<<<grid, CT_NT, 0, st>>>(Yc, w.inv, w.Raug, m);
             GSS_LAUNCH_CHECK("wpe_corr_kernel");
-            for (int j0 = 0; j0 < LD; j0 += WS_NB) {
-                wpe_panel_kernel<256><<<BF, 256, 0, st>>>(w.Raug, infoc, m, j0);
-                GSS_LAUNCH_CHECK("wpe_panel_kernel");
+            for (int j0 = 0, jb = 0; j0 < LD; j0 += WS_NB, ++jb) {
+                wpe_diag_kernel<<<BF, 32, 0, st>>>(w.Raug, w.Minv, infoc, m, j0, jb);
+                GSS_LAUNCH_CHECK("wpe_diag_kernel");
                 const int j1 = std::min(j0 + WS_NB, LD);
-                if (j1 < LD + D && j1 < LD) {
+                dim3 pg(BF, (LD + D - j1 + PR_NT - 1) / PR_NT);
+                wpe_panel_rows_kernel<<<pg, PR_NT, 0, st>>>(w.Raug, w.Minv, m, j0, jb);
+                GSS_LAUNCH_CHECK("wpe_panel_rows_kernel");
+                if (j1 < LD) {
                     dim3 tg(BF, (LD + D - j1 + CT_BM - 1) / CT_BM, (LD - j1 + CT_BM - 1) / CT_BM);
                     wpe_trail_kernel<<<tg, CT_NT, 0, st>>>(w.Raug, m, j0);
                     GSS_LAUNCH_CHECK("wpe_trail_kernel");
                 }
             }
-            wpe_backsub_kernel<256><<<BF, 256, 0, st>>>(w.Raug, w.G, m);
-            GSS_LAUNCH_CHECK("wpe_backsub_kernel");
+            {
+                const size_t bs_smem = ((size_t)LD * D + WS_NB * D + WS_NB * (WS_NB + 1) / 2) * sizeof(cd);
+                int rc2;
+                if (D <= 8) rc2 = launch_backsub<8>(w.Raug, w.Minv, w.G, m, BF, bs_smem, st);
+                else if (D <= 16) rc2 = launch_backsub<16>(w.Raug, w.Minv, w.G, m, BF, bs_smem, st);
+                else if (D <= 24) rc2 = launch_backsub<24>(w.Raug, w.Minv, w.G, m, BF, bs_smem, st);
+                else rc2 = launch_backsub<32>(w.Raug, w.Minv, w.G, m, BF, bs_smem, st);
+                if (rc2) return rc2;
+            }
             int rc;
-            if (D <= 4) rc = launch_apply<4>(Yc, w.G, Xc, w.power, m, BF, st);
-            else if (D <= 8) rc = launch_apply<8>(Yc, w.G, Xc, w.power, m, BF, st);
-            else if (D <= 16) rc = launch_apply<16>(Yc, w.G, Xc, w.power, m, BF, st);
-            else if (D <= 24) rc = launch_apply<24>(Yc, w.G, Xc, w.power, m, BF, st);
-            else rc = launch_apply<32>(Yc, w.G, Xc, w.power, m, BF, st);
+            if (D <= 8) rc = launch_apply<1>(Yc, w.G, Xc, w.power, m, BF, st);
+            else if (D <= 16) rc = launch_apply<2>(Yc, w.G, Xc, w.power, m, BF, st);
+            else if (D <= 24) rc = launch_apply<3>(Yc, w.G, Xc, w.power, m, BF, st);
+            else rc = launch_apply<4>(Yc, w.G, Xc, w.power, m, BF, st);
             if (rc) return rc;
         }
     }

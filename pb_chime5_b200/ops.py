@@ -141,7 +141,7 @@ def cacgmm(Y, activity, iterations, iterations_post=1, affiliation_eps=1e-10,
         weight = torch.empty((B, F, K), dtype=torch.float64, device=Y.device)
         logdet = torch.empty((B, F, K), dtype=torch.float64, device=Y.device)
         cov = torch.empty((B, F, K, D, D), dtype=torch.complex128, device=Y.device)
-    ws = workspace(256, Y.device)
+    ws = workspace(_lib.workspace_bytes(_lib.OP_CACGMM, B, F, D, T, K, 0), Y.device)
     _lib.check(_lib.lib().gss_cacgmm_c64(
         _ptr(Y), _ptr(activity), _ptr(post), int(iterations), int(iterations_post),
         float(affiliation_eps), float(eigenvalue_floor), B, F, D, T, K, T_act,
