@@ -75,7 +75,7 @@ def run_reference(args):
         return
     import multiprocessing as mp
     procs = os.cpu_count() or 1
-    bins = args.cpu_bins
+    bins = args.cpu_bins or 4
     ctx = mp.get_context('fork')
     with ctx.Pool(procs) as pool:
         for i in range(args.warmup):
@@ -260,7 +260,7 @@ def run_gpu(args):
     tfile = ROOT / 'profiles' / 'em_kernel_traffic.json'
     if tfile.exists():
         try:
-            traffic = json.loads(tfile.read_text()).get('dram_bytes_per_launch')
+            traffic = json.loads(tfile.read_text()).get('dram_bytes_per_utterance') * B
         except Exception:
             traffic = None
 
@@ -293,10 +293,11 @@ def run_gpu(args):
         import multiprocessing as mp
         procs = os.cpu_count() or 1
         with mp.get_context('fork').Pool(procs) as pool:
-            v, wall = cpu_sample(pool, procs, args.cpu_bins, 30_000)
+            cbins = args.cpu_bins or 8
+            v, wall = cpu_sample(pool, procs, cbins, 30_000)
         line['cpu_baseline'] = {
             'value': v, 'unit': 'utterances/s', 'cores': procs, 'kind': 'port',
-            'sample': f'{procs} processes x {args.cpu_bins} of 513 bins, all iterations, scaled by 513/{args.cpu_bins}; '
+            'sample': f'{procs} processes x {cbins} of 513 bins, all iterations, scaled by 513/{cbins}; '
                       f'{wall:.1f} s wall'}
     print(json.dumps(line), flush=True)
 
@@ -308,7 +309,7 @@ def main():
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
     ap.add_argument('--batch', type=int, default=4, help='utterances per GPU per step')
-    ap.add_argument('--cpu-bins', type=int, default=1, help='frequency bins per process in a CPU sample')
+    ap.add_argument('--cpu-bins', type=int, default=0, help='frequency bins per process in a CPU sample (0 = 8 for the cpu_baseline of the GPU arm, 4 per step for --impl reference)')
     ap.add_argument('--no-cpu', action='store_true')
     args = ap.parse_args()
     if args.impl == 'reference':
