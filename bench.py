@@ -265,6 +265,8 @@ def run_gpu(args):
             traffic = None
 
     if rank != 0:
+        sharding.barrier()
+        sharding.shutdown()
         return
     line = {
         'metric': METRIC, 'value': value, 'unit': 'utterances/s', 'n_gpus': world,
@@ -300,6 +302,8 @@ def run_gpu(args):
             'sample': f'{procs} processes x {cbins} of 513 bins, all iterations, scaled by 513/{cbins}; '
                       f'{wall:.1f} s wall'}
     print(json.dumps(line), flush=True)
+    sharding.barrier()
+    sharding.shutdown()
 
 
 def main():

@@ -41,6 +41,11 @@ def barrier():
         dist.barrier()
 
 
+def shutdown():
+    if dist.is_available() and dist.is_initialized():
+        dist.destroy_process_group()
+
+
 def broadcast_work_list(items, src=0):
     """Rank `src` decides the work list; everybody gets the same copy."""
     if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
