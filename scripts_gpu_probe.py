@@ -30,3 +30,13 @@ print(f'beamform B={B}: {ms:.2f} ms')
 ms, Xh = timeit(lambda: ops.beamform_from_posterior(Y, post, ti, None, None, bf='gev_ban'), 3)
 print(f'beamform gev B={B}: {ms:.2f} ms')
 print('post sum', float(post.sum()), 'finite', bool(torch.isfinite(post).all()), bool(torch.isfinite(torch.view_as_real(X)).all()))
+
+# cfg5 stress shape, one utterance: 60 s, T=3753, K=6, WPE taps=20, 200 EM iterations
+del Y, post, X, Xh
+torch.cuda.empty_cache()
+obs, act = synth.make_batch(5000, 1, D=24, T=3753, F=513, K=6)
+Y = ops.pack_dtf_to_fdt(torch.from_numpy(obs).to(dev)); A = torch.from_numpy(act).to(dev)
+ms, X = timeit(lambda: ops.wpe(Y, 20, 2, 3), 1)
+print(f'cfg5 wpe taps=20: {ms:.1f} ms/utt')
+ms, post = timeit(lambda: ops.cacgmm(X, A, 200), 1)
+print(f'cfg5 cacgmm 200 it: {ms:.1f} ms/utt, finite {bool(torch.isfinite(post).all())}')

@@ -236,3 +236,18 @@ def test_full_size_properties_and_spot_parity():
     Yw = ops.wpe(Y[:, :2].contiguous(), 10, 2, 3)
     refw = oracle.wpe_dtf(Obs[:, :, :2].astype(np.complex128), 10, 2, 3)
     assert rel_err(ops.unpack_fdt_to_dtf(Yw)[0].cpu().numpy(), refw) < 1e-4
+
+
+def test_stress_shape_cfg5_spot_parity():
+    """BASELINE cfg5 shape (60 s: T=3753, D=24, K=6 = 5 speakers + noise, WPE taps=20):
+    a few bins against the oracle (fewer EM iterations to bound the CPU time)."""
+    Obs, act = synth.make_utterance(555, D=24, T=3753, F=4, K=6)
+    Obs[:, 4:, :] += 0.4 * Obs[:, :-4, :]
+    dev = torch.device('cuda')
+    Y = ops.pack_dtf_to_fdt(torch.from_numpy(Obs).to(dev)[None])
+    Xw = ops.wpe(Y[:, :2].contiguous(), 20, 2, 2)
+    refw = oracle.wpe_dtf(Obs[:, :, :2].astype(np.complex128), 20, 2, 2)
+    assert rel_err(ops.unpack_fdt_to_dtf(Xw)[0].cpu().numpy(), refw) < 1e-4
+    post = ops.cacgmm(Y, torch.from_numpy(act)[None].to(dev), 12)
+    ref = oracle.gss_posteriors(Obs.astype(np.complex128), act, 12)
+    assert np.abs(ops.unpack_fkt_to_ktf(post)[0].cpu().numpy() - ref).max() < 1e-4
