@@ -55,13 +55,16 @@ struct CacgmmCfg {
     static constexpr int NW = NT / 32;
     static constexpr int JLD = DP + 1;                    // leading dim of Jacobi matrices
     static constexpr int TE = NT;                         // frames per E step = super tile (complex64 tile)
-    static constexpr int TM = 64;                         // frames per M step (complex128 tile + complex64 staging)
+#ifndef GSS_TM
+#define GSS_TM 128
+#endif
+    static constexpr int TM = GSS_TM;                     // frames per M tile (complex64, double buffered)
     static constexpr int SB = sub_block(DP);
     static constexpr int NS = DP / SB;
     static constexpr int NSB = NS * (NS + 1) / 2;
     static constexpr size_t E_BYTES = size_t(TE) * YLD * sizeof(float2);
-    static constexpr size_t MT_BYTES = size_t(TM) * YLD * sizeof(cd);       // complex128 M tile
-    static constexpr size_t MS_BYTES = size_t(TM) * YLD * sizeof(float2);   // complex64 staging (cp.async)
+    static constexpr size_t MT_BYTES = size_t(2) * TM * YLD * sizeof(float2);   // double-buffered complex64 M tiles
+    static constexpr size_t MS_BYTES = 0;
     static constexpr size_t SWEEP_BYTES = size_t(K) * NP * sizeof(cd) + size_t(2) * K * DP * sizeof(cd) + 2 * K * 8 + 64;
     static constexpr size_t JAC_BYTES = size_t(2) * DP * JLD * sizeof(cd);
     static constexpr size_t YS_BYTES = cmax(cmax(E_BYTES, MT_BYTES + MS_BYTES), cmax(SWEEP_BYTES, JAC_BYTES));
@@ -93,17 +96,23 @@ __device__ __forceinline__ void quad_subblock(const float2* __restrict__ yrow, c
     }
 #pragma unroll
     for (int a = 0; a < SB; ++a) {
+        // all products of this row first (independent -> hides the FP64 latency), then the FMAs
+        double pre[SB], pim[SB];
 #pragma unroll
         for (int c = 0; c < SB; ++c) {
             if (I == J && c > a) continue;
-            const double pre = fma(rr[a], cr[c], ri[a] * ci[c]);
-            const double pim = fma(ri[a], cr[c], -(rr[a] * ci[c]));
+            pre[c] = fma(rr[a], cr[c], ri[a] * ci[c]);
+            pim[c] = fma(ri[a], cr[c], -(rr[a] * ci[c]));
+        }
+#pragma unroll
+        for (int c = 0; c < SB; ++c) {
+            if (I == J && c > a) continue;
             const cd* b = Bsm + tri(I * SB + a, J * SB + c) * K;
 #pragma unroll
             for (int k = 0; k < K; ++k) {
                 const cd bk = b[k];
-                qa[k] = fma(pre, bk.x, qa[k]);
-                qb[k] = fma(pim, bk.y, qb[k]);
+                qa[k] = fma(pre[c], bk.x, qa[k]);
+                qb[k] = fma(pim[c], bk.y, qb[k]);
             }
         }
     }
@@ -152,8 +161,7 @@ __global__ void __launch_bounds__(NT, MINB) cacgmm_em_kernel(const CacgmmParams 
     int* flags_s = reinterpret_cast<int*>(jrot + 16);                    // [K] slow-path flags, [31] exact flag
     unsigned short* tri_tab = reinterpret_cast<unsigned short*>(flags_s + 32);   // [NP] (i << 8 | c)
     float2* yf = reinterpret_cast<float2*>(ys_raw);                      // E tile [TE][YLD] complex64
-    cd* yd = reinterpret_cast<cd*>(ys_raw);                              // M tile [TM][YLD] complex128
-    float2* ystage = reinterpret_cast<float2*>(ys_raw + C::MT_BYTES);    // M staging [TM][YLD] complex64
+    float2* ym = reinterpret_cast<float2*>(ys_raw);                      // M tiles [2][TM][YLD] complex64
 
     const int tid = threadIdx.x;
     const int lane = tid & 31, warp = tid >> 5;
@@ -273,49 +281,64 @@ __global__ void __launch_bounds__(NT, MINB) cacgmm_em_kernel(const CacgmmParams 
             for (int a = 0; a < 4; ++a)
 #pragma unroll
                 for (int k = 0; k < K; ++k) macc[a][k] = cmake(0.0, 0.0);
-            // stage tile 0
-            for (int i = tid; i < DP * TM; i += NT) {
-                const int d = i / TM, t = i - d * TM;
-                if (d < D && s0 + t < T) cp_async8(&ystage[t * C::YLD + d], &Yg[(size_t)d * T + s0 + t]);
-                else ystage[t * C::YLD + d] = make_float2(0.f, 0.f);
-            }
-            for (int t0 = s0; t0 < s1; t0 += TM) {
-                cp_async_commit_wait_all();
-                __syncthreads();
-                // convert the staged complex64 tile once
+            // M tiles: raw complex64, double buffered, cp.async straight into planar rows (even channels
+            // first, then odd ones: the 2x2 blocks of consecutive lanes read consecutive 8 B chunks);
+            // float32 -> float64 happens on read (XU pipe) -- the tile traffic on the shared-memory
+            // pipe, which bounds this kernel together with the FP64 pipe, is halved.
+            auto stage_m = [&](int buf, int tbase) {
+                float2* dst = ym + buf * (TM * C::YLD);
                 for (int i = tid; i < DP * TM; i += NT) {
-                    const int t = i / DP, d = i - t * DP;
-                    const float2 v = ystage[t * C::YLD + d];
-                    // planar rows: even channels first, then odd ones, so that the 2x2 blocks of
-                    // consecutive lanes read consecutive 16 B chunks (conflict-free LDS.128)
-                    yd[t * C::YLD + (d & 1) * (DP / 2) + (d >> 1)] = cmake((double)v.x, (double)v.y);
+                    const int d = i / TM, t = i - d * TM;
+                    float2* q = &dst[t * C::YLD + (d & 1) * (DP / 2) + (d >> 1)];
+                    if (d < D && tbase + t < T) cp_async8(q, &Yg[(size_t)d * T + tbase + t]);
+                    else *q = make_float2(0.f, 0.f);
                 }
-                __syncthreads();
-                if (t0 + TM < s1) {           // stage the next tile while this one is consumed
-                    for (int i = tid; i < DP * TM; i += NT) {
-                        const int d = i / TM, t = i - d * TM;
-                        if (d < D && t0 + TM + t < T) cp_async8(&ystage[t * C::YLD + d], &Yg[(size_t)d * T + t0 + TM + t]);
-                        else ystage[t * C::YLD + d] = make_float2(0.f, 0.f);
-                    }
-                }
+            };
+            stage_m(0, s0);
+            int mbuf = 0;
+            for (int t0 = s0; t0 < s1; t0 += TM, mbuf ^= 1) {
+                cp_async_commit_wait_all();
+                __syncthreads();                              // tile mbuf landed; everybody left tile mbuf^1
+                if (t0 + TM < s1) stage_m(mbuf ^ 1, t0 + TM); // next tile behind the FMAs
                 if (m_active) {
+                    const float2* ytile = ym + mbuf * (TM * C::YLD);
                     const int tn = min(TM, s1 - t0);
-                    for (int t = m_g; t < tn; t += C::NG) {
-                        const cd* yrow = yd + t * C::YLD;
-                        const cd a0 = yrow[bi], a1 = yrow[DP / 2 + bi], b0 = yrow[bj], b1 = yrow[DP / 2 + bj];
+                    int t = m_g;
+                    float2 fa0, fa1, fb0, fb1;
+                    double wk[K];
+                    if (t < tn) {
+                        const float2* yrow = ytile + t * C::YLD;
+                        fa0 = yrow[bi]; fa1 = yrow[DP / 2 + bi]; fb0 = yrow[bj]; fb1 = yrow[DP / 2 + bj];
+                        const double* wr = wsm + (t0 - s0 + t) * C::KP;
+#pragma unroll
+                        for (int k = 0; k < K; ++k) wk[k] = wr[k];
+                    }
+                    while (t < tn) {
+                        const cd a0 = cmake((double)fa0.x, (double)fa0.y), a1 = cmake((double)fa1.x, (double)fa1.y);
+                        const cd b0 = cmake((double)fb0.x, (double)fb0.y), b1 = cmake((double)fb1.x, (double)fb1.y);
+                        double wc[K];
+#pragma unroll
+                        for (int k = 0; k < K; ++k) wc[k] = wk[k];
+                        const int tnext = t + C::NG;
+                        if (tnext < tn) {                     // operands of the next frame, ahead of the FMAs
+                            const float2* yrow = ytile + tnext * C::YLD;
+                            fa0 = yrow[bi]; fa1 = yrow[DP / 2 + bi]; fb0 = yrow[bj]; fb1 = yrow[DP / 2 + bj];
+                            const double* wr = wsm + (t0 - s0 + tnext) * C::KP;
+#pragma unroll
+                            for (int k = 0; k < K; ++k) wk[k] = wr[k];
+                        }
                         cd P[4];
                         P[0] = cmulc(a0, b0); P[1] = cmulc(a0, b1);
                         P[2] = cmulc(a1, b0); P[3] = cmulc(a1, b1);
-                        const double* wr = wsm + (t0 - s0 + t) * C::KP;
 #pragma unroll
                         for (int k = 0; k < K; ++k) {
-                            const double wk = wr[k];
 #pragma unroll
                             for (int a = 0; a < 4; ++a) {
-                                macc[a][k].x = fma(wk, P[a].x, macc[a][k].x);
-                                macc[a][k].y = fma(wk, P[a].y, macc[a][k].y);
+                                macc[a][k].x = fma(wc[k], P[a].x, macc[a][k].x);
+                                macc[a][k].y = fma(wc[k], P[a].y, macc[a][k].y);
                             }
                         }
+                        t = tnext;
                     }
                 }
             }
@@ -538,9 +561,15 @@ __global__ void __launch_bounds__(NT, MINB) cacgmm_em_kernel(const CacgmmParams 
 // ---------------------------------------------------------------------------
 template <int DP, int K>
 static int launch_cacgmm_dk(const CacgmmParams& p, cudaStream_t st) {
-    constexpr int NT = 256;
+#ifndef GSS_EM_NT
+#define GSS_EM_NT 256
+#endif
+#ifndef GSS_EM_MINB
+#define GSS_EM_MINB 2
+#endif
+    constexpr int NT = GSS_EM_NT;
     using C = CacgmmCfg<DP, K, NT>;
-    auto kern = cacgmm_em_kernel<DP, K, NT, 2>;
+    auto kern = cacgmm_em_kernel<DP, K, NT, GSS_EM_MINB>;
     GSS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM));
     kern<<<p.B * p.F, NT, C::SMEM, st>>>(p);
     GSS_LAUNCH_CHECK("cacgmm_em_kernel");

@@ -1,6 +1,7 @@
 """Run single kernels at cfg2 shape for ncu (B=1)."""
 import sys
 import torch
+import sys, pathlib; sys.path.insert(0, str(pathlib.Path(__file__).resolve().parent.parent))
 from pb_chime5_b200 import ops, synth
 which = sys.argv[1] if len(sys.argv) > 1 else 'em'
 dev = torch.device('cuda:0')
