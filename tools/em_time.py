@@ -1,4 +1,5 @@
 import torch
+import sys, pathlib; sys.path.insert(0, str(pathlib.Path(__file__).resolve().parent.parent))
 from pb_chime5_b200 import ops, synth
 dev = torch.device("cuda:0")
 B = 4
