@@ -151,6 +151,90 @@ __global__ void __launch_bounds__(NT) weighted_cov_kernel(const float2* __restri
     }
 }
 
+// ---------------------------------------------------------------------------
+// Small channel counts (D <= 8): the covariance is HBM bound, not FP64 bound.  One warp per
+// bin, lanes stride the frames (every load is a coalesced 256 B / 128 B row segment), each
+// lane keeps the whole packed Hermitian accumulator of KC classes in registers, one
+// shuffle-tree reduction per bin.  Grid = ceil(bins / 4) CTAs of 4 warps.
+// ---------------------------------------------------------------------------
+template <int D, int KC>
+__global__ void __launch_bounds__(128) weighted_cov_small_kernel(const float2* __restrict__ Y, WeightSrc src,
+                                                                 cd* __restrict__ Phi, int nbins, int F, int T,
+                                                                 int Kout, int normalize) {
+    constexpr int NPAIR = D * (D + 1) / 2;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const size_t bf = (size_t)blockIdx.x * 4 + warp;
+    if (bf >= (size_t)nbins) return;
+    const int b = (int)(bf / F);
+    const int c0 = blockIdx.y * KC;
+    const float2* __restrict__ Yg = Y + bf * D * T;
+    double are[KC][NPAIR], aim[KC][NPAIR], wsum[KC];
+#pragma unroll
+    for (int k = 0; k < KC; ++k) {
+        wsum[k] = 0.0;
+#pragma unroll
+        for (int p = 0; p < NPAIR; ++p) { are[k][p] = 0.0; aim[k][p] = 0.0; }
+    }
+    for (int t = lane; t < T; t += 32) {
+        double yr[D], yi[D], w[KC];
+#pragma unroll
+        for (int d = 0; d < D; ++d) { const float2 v = __ldg(&Yg[(size_t)d * T + t]); yr[d] = (double)v.x; yi[d] = (double)v.y; }
+        if (KC == 2 && src.mode != 0) frame_weights(src, b, bf, T, t, c0, w[0], w[KC - 1]);
+        else {
+#pragma unroll
+            for (int k = 0; k < KC; ++k)
+                w[k] = (c0 + k < src.K) ? (double)src.w[(bf * src.K + c0 + k) * T + t] : 0.0;
+        }
+#pragma unroll
+        for (int k = 0; k < KC; ++k) wsum[k] += w[k];
+#pragma unroll
+        for (int d = 0; d < D; ++d)
+#pragma unroll
+            for (int e = 0; e <= d; ++e) {
+                const double pre = fma(yr[d], yr[e], yi[d] * yi[e]);
+                const double pim = fma(yi[d], yr[e], -(yr[d] * yi[e]));
+#pragma unroll
+                for (int k = 0; k < KC; ++k) {
+                    are[k][tri(d, e)] = fma(w[k], pre, are[k][tri(d, e)]);
+                    aim[k][tri(d, e)] = fma(w[k], pim, aim[k][tri(d, e)]);
+                }
+            }
+    }
+#pragma unroll
+    for (int k = 0; k < KC; ++k) {
+        wsum[k] = warp_sum(wsum[k]);
+#pragma unroll
+        for (int p = 0; p < NPAIR; ++p) { are[k][p] = warp_sum(are[k][p]); aim[k][p] = warp_sum(aim[k][p]); }
+    }
+    // lane p writes row/column entries of pair p (all lanes hold the full sums after the xor tree)
+#pragma unroll
+    for (int k = 0; k < KC; ++k) {
+        if (c0 + k >= Kout) break;
+        const double sc = normalize ? 1.0 / fmax(wsum[k], 1e-10) : 1.0;
+        cd* out = Phi + (bf * Kout + c0 + k) * D * D;
+#pragma unroll
+        for (int d = 0; d < D; ++d)
+#pragma unroll
+            for (int e = 0; e <= d; ++e) {
+                if (lane == (tri(d, e) & 31)) {
+                    const double re = are[k][tri(d, e)] * sc, im = (d == e) ? 0.0 : aim[k][tri(d, e)] * sc;
+                    out[d * D + e] = cmake(re, im);
+                    if (d != e) out[e * D + d] = cmake(re, -im);
+                }
+            }
+    }
+}
+
+template <int D, int KC>
+static int launch_weighted_cov_small(const float2* Y, const WeightSrc& src, cd* Phi, int B, int F, int T, int Kout,
+                                     int normalize, cudaStream_t st) {
+    const int nbins = B * F;
+    dim3 grid((nbins + 3) / 4, (Kout + KC - 1) / KC);
+    weighted_cov_small_kernel<D, KC><<<grid, 128, 0, st>>>(Y, src, Phi, nbins, F, T, Kout, normalize);
+    GSS_LAUNCH_CHECK("weighted_cov_small_kernel");
+    return GSS_OK;
+}
+
 template <int DP>
 static int launch_weighted_cov(const float2* Y, const WeightSrc& src, cd* Phi, double* wsum,
                                int B, int F, int D, int T, int Kout, int normalize, cudaStream_t st) {
@@ -163,6 +247,20 @@ static int launch_weighted_cov(const float2* Y, const WeightSrc& src, cd* Phi, d
 
 int weighted_cov_dispatch(const float2* Y, const WeightSrc& src, cd* Phi, double* wsum,
                           int B, int F, int D, int T, int Kout, int normalize, cudaStream_t st) {
+    if (wsum == nullptr && (D <= 6 || (D <= 8 && src.mode == 0))) {
+        // HBM-bound regime: classes per pass limited by the register budget (2 * KC * D(D+1)/2 doubles)
+        const bool two = src.mode != 0;          // mask pair (target, distortion)
+        switch (D) {
+            case 1: return two ? launch_weighted_cov_small<1, 2>(Y, src, Phi, B, F, T, Kout, normalize, st) : launch_weighted_cov_small<1, 4>(Y, src, Phi, B, F, T, Kout, normalize, st);
+            case 2: return two ? launch_weighted_cov_small<2, 2>(Y, src, Phi, B, F, T, Kout, normalize, st) : launch_weighted_cov_small<2, 4>(Y, src, Phi, B, F, T, Kout, normalize, st);
+            case 3: return two ? launch_weighted_cov_small<3, 2>(Y, src, Phi, B, F, T, Kout, normalize, st) : launch_weighted_cov_small<3, 3>(Y, src, Phi, B, F, T, Kout, normalize, st);
+            case 4: return two ? launch_weighted_cov_small<4, 2>(Y, src, Phi, B, F, T, Kout, normalize, st) : launch_weighted_cov_small<4, 3>(Y, src, Phi, B, F, T, Kout, normalize, st);
+            case 5: return launch_weighted_cov_small<5, 2>(Y, src, Phi, B, F, T, Kout, normalize, st);
+            case 6: return launch_weighted_cov_small<6, 2>(Y, src, Phi, B, F, T, Kout, normalize, st);
+            case 7: return launch_weighted_cov_small<7, 1>(Y, src, Phi, B, F, T, Kout, normalize, st);
+            case 8: return launch_weighted_cov_small<8, 1>(Y, src, Phi, B, F, T, Kout, normalize, st);
+        }
+    }
     const int DP = (D + 1) & ~1;
     switch (DP) {
 #define GSS_CASE(dp) case dp: return launch_weighted_cov<dp>(Y, src, Phi, wsum, B, F, D, T, Kout, normalize, st);
