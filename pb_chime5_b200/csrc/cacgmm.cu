@@ -439,15 +439,20 @@ __global__ void __launch_bounds__(NT, MINB) cacgmm_em_kernel(const CacgmmParams 
                     const int e = tid + n * NT;
                     const double pv = piv[k];
                     const double d = (pv > 0.0 && isfinite(pv)) ? 1.0 / pv : 0.0;
-                    cd v;
-                    if (i == j && c == j) { v = cmake(-d, 0.0); pivbuf[k * DP + j] = pv; }
-                    else if (c == j) v = cscale(col[k * DP + i], d);
-                    else if (i == j) v = cscale(cconj(col[k * DP + c]), d);
-                    else {
-                        v = S[e];
-                        const cd ud = cscale(col[k * DP + i], d);
-                        cfmsc(v, ud, col[k * DP + c]);
-                    }
+                    // branch-free: entries of row/column j are S*d (the stored value IS the column
+                    // entry or its conjugate), the pivot becomes -d, everything else gets the
+                    // rank-1 update  S - (u_i d) conj(u_c)
+                    const cd sv = S[e];
+                    const cd ui = col[k * DP + i], uc = col[k * DP + c];
+                    const bool on_i = (i == j), on_c = (c == j);
+                    cd v = sv;
+                    cfmsc(v, cscale(ui, d), uc);
+                    const cd vs = cscale(sv, d);
+                    v.x = (on_i | on_c) ? vs.x : v.x;
+                    v.y = (on_i | on_c) ? vs.y : v.y;
+                    v.x = (on_i & on_c) ? -d : v.x;
+                    v.y = (on_i & on_c) ? 0.0 : v.y;
+                    if (on_i & on_c) pivbuf[k * DP + j] = pv;
                     S[e] = v;
                     // forward the column of the next pivot
                     if (c == j + 1) { coln[k * DP + i] = v; if (i == j + 1) pivn[k] = v.x; }
