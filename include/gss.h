@@ -26,6 +26,9 @@
  *    optional `info` array (one int32 per utterance, device memory, may be
  *    NULL): 0 ok, otherwise GSS_INFO_* | (first failing bin << 8).
  *  - `ws` is caller-provided device scratch of at least gss_workspace_bytes().
+ *  - Ragged batches: `T` is the frame stride of the batch; `T_per_utt` (device, one int32 per
+ *    utterance, may be NULL = all T) gives the valid frames of each utterance.  Frames beyond
+ *    are ignored on input and zero on output; results are identical to running the utterance alone.
  */
 #ifndef GSS_H_
 #define GSS_H_
@@ -98,7 +101,7 @@ int gss_unpack_ft_to_tf_c64(const gss_c64* src, gss_c64* dst, int B, int T, int 
  * normalize_mode 0: w' = w;  1: w' = w / max(sum_t w, 1e-10) (beamformer.py:124) */
 int gss_weighted_cov_c64(const gss_c64* Y, const float* w, gss_c64* Phi,
                          int normalize_mode, int B, int F, int D, int T, int K,
-                         void* ws, size_t ws_bytes, void* stream);
+                         const int* T_per_utt, void* ws, size_t ws_bytes, void* stream);
 
 /* ---- guided CACGMM EM (GSS.__call__, core.py:154-214; CACGMMTrainer.fit,
  * pb_bss/distribution/cacgmm.py:141-278; CACGMM.predict :63-94) --------------
@@ -112,7 +115,7 @@ int gss_weighted_cov_c64(const gss_c64* Y, const float* w, gss_c64* Phi,
 int gss_cacgmm_c64(const gss_c64* Y, const uint8_t* activity, float* posterior,
                    int iterations, int iterations_post,
                    double affiliation_eps, double eigenvalue_floor,
-                   int B, int F, int D, int T, int K, int T_act,
+                   int B, int F, int D, int T, int K, int T_act, const int* T_per_utt,
                    double* weight_out, double* logdet_out, double* covariance_out,
                    int* info, void* ws, size_t ws_bytes, void* stream);
 
@@ -124,7 +127,7 @@ int gss_cacgmm_c64(const gss_c64* Y, const uint8_t* activity, float* posterior,
 int gss_beamform_c64(const gss_c64* Y, const float* target_mask,
                      const float* distortion_mask, gss_c64* X_hat,
                      int bf_type, int bf_arg, int postfilter,
-                     int B, int F, int D, int T,
+                     int B, int F, int D, int T, const int* T_per_utt,
                      int* ref_channel_out, double* weights_out,
                      int* info, void* ws, size_t ws_bytes, void* stream);
 
@@ -134,7 +137,7 @@ int gss_beamform_c64(const gss_c64* Y, const float* target_mask,
 int gss_beamform_from_posterior_c64(const gss_c64* Y, const float* posterior,
                      const int* target_index, const int* start_ctx, const int* end_ctx,
                      gss_c64* X_hat, int bf_type, int bf_arg, int postfilter,
-                     int B, int F, int D, int T, int K,
+                     int B, int F, int D, int T, int K, const int* T_per_utt,
                      int* ref_channel_out, double* weights_out,
                      int* info, void* ws, size_t ws_bytes, void* stream);
 
@@ -142,7 +145,7 @@ int gss_beamform_from_posterior_c64(const gss_c64* Y, const float* posterior,
  * third party) ---------------------------------------------------------------
  * Y, X (B,F,D,T) c64 (X may not alias Y). */
 int gss_wpe_c64(const gss_c64* Y, gss_c64* X, int taps, int delay, int iterations,
-                int psd_context, int B, int F, int D, int T,
+                int psd_context, int B, int F, int D, int T, const int* T_per_utt,
                 int* info, void* ws, size_t ws_bytes, void* stream);
 
 /* ---- STFT / iSTFT (Enhancer.stft / .istft, core.py:305-321 -> nara_wpe.utils)

@@ -42,14 +42,14 @@ _SIGNATURES = {
     'gss_unpack_fkt_to_ktf_f32': (_i, [_p, _p, _i, _i, _i, _i, _p]),
     'gss_pack_ktf_to_fkt_f32': (_i, [_p, _p, _i, _i, _i, _i, _p]),
     'gss_unpack_ft_to_tf_c64': (_i, [_p, _p, _i, _i, _i, _p]),
-    'gss_weighted_cov_c64': (_i, [_p, _p, _p, _i, _i, _i, _i, _i, _i, _p, _sz, _p]),
-    'gss_cacgmm_c64': (_i, [_p, _p, _p, _i, _i, _d, _d, _i, _i, _i, _i, _i, _i,
+    'gss_weighted_cov_c64': (_i, [_p, _p, _p, _i, _i, _i, _i, _i, _i, _p, _p, _sz, _p]),
+    'gss_cacgmm_c64': (_i, [_p, _p, _p, _i, _i, _d, _d, _i, _i, _i, _i, _i, _i, _p,
                             _p, _p, _p, _p, _p, _sz, _p]),
-    'gss_beamform_c64': (_i, [_p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _i,
+    'gss_beamform_c64': (_i, [_p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _p,
                               _p, _p, _p, _p, _sz, _p]),
     'gss_beamform_from_posterior_c64': (_i, [_p, _p, _p, _p, _p, _p, _i, _i, _i,
-                                             _i, _i, _i, _i, _i, _p, _p, _p, _p, _sz, _p]),
-    'gss_wpe_c64': (_i, [_p, _p, _i, _i, _i, _i, _i, _i, _i, _i, _p, _p, _sz, _p]),
+                                             _i, _i, _i, _i, _i, _p, _p, _p, _p, _p, _sz, _p]),
+    'gss_wpe_c64': (_i, [_p, _p, _i, _i, _i, _i, _i, _i, _i, _i, _p, _p, _p, _sz, _p]),
     'gss_stft_f32': (_i, [_p, _p, _i, _i, _i, _i, _i, _i, _p, _sz, _p]),
     'gss_istft_f32': (_i, [_p, _p, _i, _i, _i, _i, _i, _p, _sz, _p]),
 }

@@ -98,9 +98,9 @@ class WPE:
     iterations: int
     psd_context: int
 
-    def _run(self, Y):
-        """Y (B,F,D,T) complex64 on the device -> same shape."""
-        return ops.wpe(Y, self.taps, self.delay, self.iterations, self.psd_context)
+    def _run(self, Y, frames=None):
+        """Y (B,F,D,T) complex64 on the device -> same shape.  frames: valid frames per utterance."""
+        return ops.wpe(Y, self.taps, self.delay, self.iterations, self.psd_context, frames=frames)
 
     def __call__(self, Obs, stack=None, debug=False):
         ndim = Obs.ndim
@@ -180,9 +180,9 @@ class GSS:
     iterations_post: int
     verbose: bool = True
 
-    def _run(self, Y, activity):
+    def _run(self, Y, activity, frames=None):
         """Y (B,F,D,T) c64, activity (B,K,T_act) uint8/bool -> posterior (B,F,K,T) f32."""
-        return ops.cacgmm(Y, activity, self.iterations, self.iterations_post)
+        return ops.cacgmm(Y, activity, self.iterations, self.iterations_post, frames=frames)
 
     def __call__(self, Obs, acitivity_freq, debug=False):
         x, was_np = _to_device(Obs, torch.complex64)                     # (D,T,F)
@@ -240,11 +240,11 @@ class Beamformer:
         self._check_postfilter()
         return ops.beamform(Y, target_mask, distortion_mask, bf=bf, postfilter=self.postfilter, bf_arg=arg)
 
-    def _run_from_posterior(self, Y, posterior, target_index, start_ctx, end_ctx):
+    def _run_from_posterior(self, Y, posterior, target_index, start_ctx, end_ctx, frames=None):
         bf, arg = self._bf_args()
         self._check_postfilter()
         return ops.beamform_from_posterior(Y, posterior, target_index, start_ctx, end_ctx, bf=bf,
-                                           postfilter=self.postfilter, bf_arg=arg)
+                                           postfilter=self.postfilter, bf_arg=arg, frames=frames)
 
     def __call__(self, Obs, target_mask, distortion_mask, debug=False):
         self._bf_args()
@@ -316,16 +316,19 @@ class Enhancer:
         return _from_device(out.reshape(*lead, out.shape[-1]), was_np, np.float64)
 
     # ---- the device-resident hot path ---------------------------------------
-    def enhance_stft_batch(self, Y, activity_freq, target_index, start_ctx, end_ctx, return_masks=False):
+    def enhance_stft_batch(self, Y, activity_freq, target_index, start_ctx, end_ctx, return_masks=False,
+                           frames=None):
         """Y (B,F,D,T) complex64 CUDA (bin-major), activity_freq (B,K,T_act) uint8,
         target_index / start_ctx / end_ctx (B) int32 -> X_hat (B,F,T) complex64
-        [, posterior (B,F,K,T) float32].  core.py:524-564 without host round trips."""
+        [, posterior (B,F,K,T) float32].  core.py:524-564 without host round trips.
+        frames: optional (B) valid frame counts for a ragged batch padded to T (each utterance
+        gives exactly the result it would give alone; padded frames come back as zeros)."""
         if self.wpe_block is not None:
-            Y = self.wpe_block._run(Y)
-        post = self.gss_block._run(Y, activity_freq)
+            Y = self.wpe_block._run(Y, frames)
+        post = self.gss_block._run(Y, activity_freq, frames)
         if not self.bf_drop_context:
             start_ctx = end_ctx = None
-        X = self.bf_block._run_from_posterior(Y, post, target_index, start_ctx, end_ctx)
+        X = self.bf_block._run_from_posterior(Y, post, target_index, start_ctx, end_ctx, frames)
         return (X, post) if return_masks else X
 
     def enhance_stft_host(self, Obs, acitivity_freq, target_index, start_ctx=None, end_ctx=None,

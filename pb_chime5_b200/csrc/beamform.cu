@@ -27,11 +27,17 @@ struct WeightSrc {
     const int* start_ctx;      // mode 2 (B) frames, may be null
     const int* end_ctx;        // mode 2 (B) frames, may be null
     int K;                     // classes in w / posterior
+    const int* Tper;           // (B) valid frames per utterance or null
 };
+
+__device__ __forceinline__ int valid_frames(const WeightSrc& s, int b, int T) {
+    return s.Tper ? min(max(s.Tper[b], 0), T) : T;
+}
 
 // weights of class pair (c0, c0+1) for frame t of bin (b,f); mode 1/2 always give (target, distortion)
 __device__ __forceinline__ void frame_weights(const WeightSrc& s, int b, size_t bf, int T, int t, int c0,
-                                              double& w0, double& w1) {
+                                              double& w0, double& w1, int Tv = -1) {
+    if (Tv < 0) Tv = T;
     if (s.mode == 0) {
         const float* base = s.w + (bf * s.K) * T;
         w0 = (double)base[(size_t)c0 * T + t];
@@ -43,7 +49,7 @@ __device__ __forceinline__ void frame_weights(const WeightSrc& s, int b, size_t 
         const int sc = s.start_ctx ? s.start_ctx[b] : 0;
         const int ec = s.end_ctx ? s.end_ctx[b] : 0;
         w0 = 0.0; w1 = 0.0;
-        if (t >= sc && t < T - ec) {            // masks[:, :sc] = 0 ; masks[:, -ec:] = 0 (core.py:545-547)
+        if (t >= sc && t < Tv - ec) {           // masks[:, :sc] = 0 ; masks[:, -ec:] = 0 (core.py:545-547)
             const float* base = s.w + (bf * s.K) * T;
             const int ti = s.target_index[b];
             for (int k = 0; k < s.K; ++k) {
@@ -70,6 +76,7 @@ __global__ void __launch_bounds__(NT) weighted_cov_kernel(const float2* __restri
     const int b = (int)(bf / F);
     const int c0 = blockIdx.y * 2;
     const float2* __restrict__ Yg = Y + bf * D * T;
+    const int Tv = valid_frames(src, b, T);
     const int m_g = tid / G, m_l = tid - m_g * G;
     const bool m_active = m_g < NG;
     int bi = 0;
@@ -80,22 +87,22 @@ __global__ void __launch_bounds__(NT) weighted_cov_kernel(const float2* __restri
 #pragma unroll
     for (int a = 0; a < 4; ++a) { macc[a][0] = cmake(0.0, 0.0); macc[a][1] = cmake(0.0, 0.0); }
     double ws0 = 0.0, ws1 = 0.0;
-    for (int t0 = 0; t0 < T; t0 += TM) {
+    for (int t0 = 0; t0 < Tv; t0 += TM) {
         for (int i = tid; i < DP * TM; i += NT) {
             const int d = i / TM, t = i - d * TM;
             float2 v = make_float2(0.f, 0.f);
-            if (d < D && t0 + t < T) v = __ldg(&Yg[(size_t)d * T + t0 + t]);
+            if (d < D && t0 + t < Tv) v = __ldg(&Yg[(size_t)d * T + t0 + t]);
             ysm[t * YLD + d] = cmake((double)v.x, (double)v.y);
         }
         for (int t = tid; t < TM; t += NT) {
             double w0 = 0.0, w1 = 0.0;
-            if (t0 + t < T) frame_weights(src, b, bf, T, t0 + t, c0, w0, w1);
+            if (t0 + t < Tv) frame_weights(src, b, bf, T, t0 + t, c0, w0, w1, Tv);
             wsm[2 * t] = w0; wsm[2 * t + 1] = w1;
             ws0 += w0; ws1 += w1;
         }
         __syncthreads();
         if (m_active) {
-            const int tn = min(TM, T - t0);
+            const int tn = min(TM, Tv - t0);
             for (int t = m_g; t < tn; t += NG) {
                 const cd* yrow = ysm + t * YLD;
                 const cd a0 = yrow[r0], a1 = yrow[r0 + 1], b0 = yrow[cc0], b1 = yrow[cc0 + 1];
@@ -168,6 +175,7 @@ __global__ void __launch_bounds__(128) weighted_cov_small_kernel(const float2* _
     const int b = (int)(bf / F);
     const int c0 = blockIdx.y * KC;
     const float2* __restrict__ Yg = Y + bf * D * T;
+    const int Tv = valid_frames(src, b, T);
     double are[KC][NPAIR], aim[KC][NPAIR], wsum[KC];
 #pragma unroll
     for (int k = 0; k < KC; ++k) {
@@ -175,11 +183,11 @@ __global__ void __launch_bounds__(128) weighted_cov_small_kernel(const float2* _
 #pragma unroll
         for (int p = 0; p < NPAIR; ++p) { are[k][p] = 0.0; aim[k][p] = 0.0; }
     }
-    for (int t = lane; t < T; t += 32) {
+    for (int t = lane; t < Tv; t += 32) {
         double yr[D], yi[D], w[KC];
 #pragma unroll
         for (int d = 0; d < D; ++d) { const float2 v = __ldg(&Yg[(size_t)d * T + t]); yr[d] = (double)v.x; yi[d] = (double)v.y; }
-        if (KC == 2 && src.mode != 0) frame_weights(src, b, bf, T, t, c0, w[0], w[KC - 1]);
+        if (KC == 2 && src.mode != 0) frame_weights(src, b, bf, T, t, c0, w[0], w[KC - 1], Tv);
         else {
 #pragma unroll
             for (int k = 0; k < KC; ++k)
@@ -538,7 +546,9 @@ __global__ void __launch_bounds__(256) bf_apply_kernel(const float2* __restrict_
     }
     if (weights_out && tid < D) weights_out[bf * D + tid] = w[tid];
     const float2* __restrict__ Yg = Y + bf * D * T;
+    const int Tv = valid_frames(src, b, T);
     for (int t = tid; t < T; t += blockDim.x) {
+        if (t >= Tv) { Xhat[bf * T + t] = make_float2(0.f, 0.f); continue; }
         cd s = cmake(0.0, 0.0);
         for (int d = 0; d < D; ++d) {
             const float2 v = __ldg(&Yg[(size_t)d * T + t]);
@@ -546,7 +556,7 @@ __global__ void __launch_bounds__(256) bf_apply_kernel(const float2* __restrict_
         }
         if (postfilter == GSS_POSTFILTER_MASK_MUL) {
             double w0, w1;
-            frame_weights(src, b, bf, T, t, 0, w0, w1);
+            frame_weights(src, b, bf, T, t, 0, w0, w1, Tv);
             s = cscale(s, w0);
         }
         Xhat[bf * T + t] = make_float2((float)s.x, (float)s.y);
@@ -559,13 +569,15 @@ __global__ void bf_simple_kernel(const float2* __restrict__ Y, WeightSrc src, fl
     const size_t bf = blockIdx.x;
     const int b = (int)(bf / F);
     const float2* __restrict__ Yg = Y + bf * D * T;
+    const int Tv = valid_frames(src, b, T);
     for (int t = threadIdx.x; t < T; t += blockDim.x) {
+        if (t >= Tv) { Xhat[bf * T + t] = make_float2(0.f, 0.f); continue; }
         double re = 0.0, im = 0.0;
         if (ch >= 0) { const float2 v = Yg[(size_t)ch * T + t]; re = v.x; im = v.y; }
         else for (int d = 0; d < D; ++d) { const float2 v = Yg[(size_t)d * T + t]; re += v.x; im += v.y; }
         if (postfilter == GSS_POSTFILTER_MASK_MUL) {
             double w0, w1;
-            frame_weights(src, b, bf, T, t, 0, w0, w1);
+            frame_weights(src, b, bf, T, t, 0, w0, w1, Tv);
             re *= w0; im *= w0;
         }
         Xhat[bf * T + t] = make_float2((float)re, (float)im);
@@ -629,7 +641,7 @@ static int beamform_impl(const float2* Y, const WeightSrc& src, float2* Xhat, in
 extern "C" {
 
 int gss_weighted_cov_c64(const gss_c64* Y, const float* w, gss_c64* Phi, int normalize_mode,
-                         int B, int F, int D, int T, int K, void* ws, size_t ws_bytes, void* stream) {
+                         int B, int F, int D, int T, int K, const int* T_per_utt, void* ws, size_t ws_bytes, void* stream) {
     using namespace gss;
     GSS_REQUIRE(Y && w && Phi, GSS_ERR_ARG, "gss_weighted_cov_c64: null pointer");
     GSS_REQUIRE(B >= 0 && F >= 0 && D > 0 && T > 0 && K > 0, GSS_ERR_ARG, "gss_weighted_cov_c64: bad dims");
@@ -638,7 +650,7 @@ int gss_weighted_cov_c64(const gss_c64* Y, const float* w, gss_c64* Phi, int nor
     if (B == 0 || F == 0) return GSS_OK;
     const size_t need = weighted_cov_ws_bytes(B, F, D, K);
     GSS_REQUIRE(ws && ws_bytes >= need, GSS_ERR_WORKSPACE, "gss_weighted_cov_c64: workspace %zu < %zu", ws_bytes, need);
-    WeightSrc src{}; src.mode = 0; src.w = w; src.K = K;
+    WeightSrc src{}; src.mode = 0; src.w = w; src.K = K; src.Tper = T_per_utt;
     cudaStream_t st = (cudaStream_t)stream;
     int rc = weighted_cov_dispatch((const float2*)Y, src, (cd*)ws, nullptr, B, F, D, T, K, normalize_mode, st);
     if (rc) return rc;
@@ -649,11 +661,11 @@ int gss_weighted_cov_c64(const gss_c64* Y, const float* w, gss_c64* Phi, int nor
 }
 
 int gss_beamform_c64(const gss_c64* Y, const float* target_mask, const float* distortion_mask, gss_c64* X_hat,
-                     int bf_type, int bf_arg, int postfilter, int B, int F, int D, int T,
+                     int bf_type, int bf_arg, int postfilter, int B, int F, int D, int T, const int* T_per_utt,
                      int* ref_channel_out, double* weights_out, int* info, void* ws, size_t ws_bytes, void* stream) {
     using namespace gss;
     GSS_REQUIRE(target_mask && distortion_mask, GSS_ERR_ARG, "gss_beamform_c64: null mask");
-    WeightSrc src{}; src.mode = 1; src.m0 = target_mask; src.m1 = distortion_mask; src.K = 2;
+    WeightSrc src{}; src.mode = 1; src.m0 = target_mask; src.m1 = distortion_mask; src.K = 2; src.Tper = T_per_utt;
     return beamform_impl((const float2*)Y, src, (float2*)X_hat, bf_type, bf_arg, postfilter, B, F, D, T,
                          ref_channel_out, weights_out, info, ws, ws_bytes, (cudaStream_t)stream);
 }
@@ -661,13 +673,13 @@ int gss_beamform_c64(const gss_c64* Y, const float* target_mask, const float* di
 int gss_beamform_from_posterior_c64(const gss_c64* Y, const float* posterior, const int* target_index,
                                     const int* start_ctx, const int* end_ctx, gss_c64* X_hat,
                                     int bf_type, int bf_arg, int postfilter, int B, int F, int D, int T, int K,
-                                    int* ref_channel_out, double* weights_out, int* info,
+                                    const int* T_per_utt, int* ref_channel_out, double* weights_out, int* info,
                                     void* ws, size_t ws_bytes, void* stream) {
     using namespace gss;
     GSS_REQUIRE(posterior && target_index, GSS_ERR_ARG, "gss_beamform_from_posterior_c64: null pointer");
     GSS_REQUIRE(K > 1 && K < 20, GSS_ERR_ARG, "K=%d", K);
     WeightSrc src{}; src.mode = 2; src.w = posterior; src.target_index = target_index;
-    src.start_ctx = start_ctx; src.end_ctx = end_ctx; src.K = K;
+    src.start_ctx = start_ctx; src.end_ctx = end_ctx; src.K = K; src.Tper = T_per_utt;
     return beamform_impl((const float2*)Y, src, (float2*)X_hat, bf_type, bf_arg, postfilter, B, F, D, T,
                          ref_channel_out, weights_out, info, ws, ws_bytes, (cudaStream_t)stream);
 }

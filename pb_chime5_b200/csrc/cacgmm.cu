@@ -26,6 +26,7 @@ namespace gss {
 struct CacgmmParams {
     const float2* Y;          // (B,F,D,T)
     const uint8_t* activity;  // (B,K,T_act)
+    const int* Tper;          // (B) valid frames per utterance (<= T) or null
     float* posterior;         // (B,F,K,T)
     double* weight_out;       // (B,F,K) or null
     double* logdet_out;       // (B,F,K) or null
@@ -167,8 +168,13 @@ __global__ void __launch_bounds__(NT, MINB) cacgmm_em_kernel(const CacgmmParams 
     const int lane = tid & 31, warp = tid >> 5;
     const int bf = blockIdx.x;
     const int b = bf / p.F, f = bf - b * p.F;
-    const int D = p.D, T = p.T;
-    const float2* __restrict__ Yg = p.Y + (size_t)bf * D * T;
+    const int D = p.D, Ts = p.T;                               // Ts: frame stride of the batch
+    const int T = p.Tper ? min(max(p.Tper[b], 0), Ts) : Ts;    // valid frames of this utterance
+    const float2* __restrict__ Yg = p.Y + (size_t)bf * D * Ts;
+    if (T <= 0) {
+        for (int i = tid; i < K * Ts; i += NT) p.posterior[(size_t)bf * K * Ts + i] = 0.f;
+        return;
+    }
     const uint8_t* __restrict__ act = p.activity + (size_t)b * K * p.T_act;
 
     // M-phase role: group m_g, lane m_l -> 2x2 block (bi >= bj)
@@ -209,7 +215,7 @@ __global__ void __launch_bounds__(NT, MINB) cacgmm_em_kernel(const CacgmmParams 
             for (int i = tid; i < DP * TE; i += NT) {
                 const int d = i / TE, t = i - d * TE;
                 float2 v = make_float2(0.f, 0.f);
-                if (d < D && s0 + t < T) v = __ldg(&Yg[(size_t)d * T + s0 + t]);
+                if (d < D && s0 + t < T) v = __ldg(&Yg[(size_t)d * Ts + s0 + t]);
                 yf[t * C::YLD + d] = v;
             }
             __syncthreads();
@@ -266,7 +272,7 @@ __global__ void __launch_bounds__(NT, MINB) cacgmm_em_kernel(const CacgmmParams 
                     if (is_final) {
 #pragma unroll
                         for (int k = 0; k < K; ++k)
-                            p.posterior[((size_t)bf * K + k) * T + t] = (float)g[k];
+                            p.posterior[((size_t)bf * K + k) * Ts + t] = (float)g[k];
                     }
 #pragma unroll
                     for (int k = 0; k < K; ++k) { gsum[k] += g[k]; wsm[tid * C::KP + k] = w[k]; }
@@ -290,7 +296,7 @@ __global__ void __launch_bounds__(NT, MINB) cacgmm_em_kernel(const CacgmmParams 
                 for (int i = tid; i < DP * TM; i += NT) {
                     const int d = i / TM, t = i - d * TM;
                     float2* q = &dst[t * C::YLD + (d & 1) * (DP / 2) + (d >> 1)];
-                    if (d < D && tbase + t < T) cp_async8(q, &Yg[(size_t)d * T + tbase + t]);
+                    if (d < D && tbase + t < T) cp_async8(q, &Yg[(size_t)d * Ts + tbase + t]);
                     else *q = make_float2(0.f, 0.f);
                 }
             };
@@ -362,7 +368,13 @@ __global__ void __launch_bounds__(NT, MINB) cacgmm_em_kernel(const CacgmmParams 
                 __syncthreads();
             }
         }
-        if (is_final) break;
+        if (is_final) {
+            for (int i = tid; i < K * (Ts - T); i += NT) {
+                const int k = i / (Ts - T), t = T + i - k * (Ts - T);
+                p.posterior[((size_t)bf * K + k) * Ts + t] = 0.f;
+            }
+            break;
+        }
         if (pass == 0) {
             // all-zero frames make q = tiny, where the eigenvalue normalisation of the reference
             // does not cancel any more -> this bin needs the exact (eigh) class matrices.
@@ -608,7 +620,7 @@ int cacgmm_dispatch(const CacgmmParams& p, int K, cudaStream_t st) {
 extern "C" int gss_cacgmm_c64(const gss_c64* Y, const uint8_t* activity, float* posterior,
                               int iterations, int iterations_post,
                               double affiliation_eps, double eigenvalue_floor,
-                              int B, int F, int D, int T, int K, int T_act,
+                              int B, int F, int D, int T, int K, int T_act, const int* T_per_utt,
                               double* weight_out, double* logdet_out, double* covariance_out,
                               int* info, void* ws, size_t ws_bytes, void* stream) {
     using namespace gss;
@@ -626,7 +638,7 @@ extern "C" int gss_cacgmm_c64(const gss_c64* Y, const uint8_t* activity, float* 
     GSS_REQUIRE(D <= 32, GSS_ERR_UNSUPPORTED, "gss_cacgmm_c64: D=%d > 32 not built", D);
     if (B == 0 || F == 0) return GSS_OK;
     CacgmmParams p;
-    p.Y = (const float2*)Y; p.activity = activity; p.posterior = posterior;
+    p.Y = (const float2*)Y; p.activity = activity; p.posterior = posterior; p.Tper = T_per_utt;
     p.weight_out = weight_out; p.logdet_out = logdet_out; p.cov_out = covariance_out;
     p.info = info; p.slow_count = nullptr;
     p.B = B; p.F = F; p.D = D; p.T = T; p.T_act = T_act;

@@ -18,11 +18,15 @@
 
 namespace gss {
 
-struct WpeDims { int F, D, T, L, delay, LD; };
+struct WpeDims { int F, D, T, L, delay, LD; const int* Tper; };   // T: frame stride; Tper: valid frames per utterance or null
 
-__device__ __forceinline__ cd wpe_row_value(const float2* __restrict__ Yg, const WpeDims& m, int idx, int t) {
+__device__ __forceinline__ int wpe_valid_frames(const WpeDims& m, size_t bf) {
+    return m.Tper ? min(max(m.Tper[bf / m.F], 0), m.T) : m.T;
+}
+
+__device__ __forceinline__ cd wpe_row_value(const float2* __restrict__ Yg, const WpeDims& m, int idx, int t, int Tv) {
     // idx < LD : tap row (k, d) ; LD <= idx < LD + D : the unshifted observation
-    if (t >= m.T) return cmake(0.0, 0.0);
+    if (t >= Tv) return cmake(0.0, 0.0);
     int d, ts;
     if (idx < m.LD) { const int k = idx / m.D; d = idx - k * m.D; ts = t - m.delay - k; }
     else if (idx < m.LD + m.D) { d = idx - m.LD; ts = t; }
@@ -33,10 +37,11 @@ __device__ __forceinline__ cd wpe_row_value(const float2* __restrict__ Yg, const
 }
 
 // raw power[t] = mean_d |Y[d,t]|^2   (first iteration: X = Y)
-__global__ void wpe_power_kernel(const float2* __restrict__ Y, double* __restrict__ power, int D, int T) {
+__global__ void wpe_power_kernel(const float2* __restrict__ Y, double* __restrict__ power, WpeDims m) {
     const size_t bf = blockIdx.x;
+    const int D = m.D, T = m.T, Tv = wpe_valid_frames(m, bf);
     const float2* Yg = Y + bf * D * T;
-    for (int t = threadIdx.x; t < T; t += blockDim.x) {
+    for (int t = threadIdx.x; t < Tv; t += blockDim.x) {
         double s = 0.0;
         for (int d = 0; d < D; ++d) { const float2 v = Yg[(size_t)d * T + t]; s = fma((double)v.x, (double)v.x, fma((double)v.y, (double)v.y, s)); }
         power[bf * T + t] = s / D;
@@ -44,11 +49,12 @@ __global__ void wpe_power_kernel(const float2* __restrict__ Y, double* __restric
 }
 
 // inv[t] = 1 / max(smooth(power)[t], 1e-10 * max_t smooth(power))
-__global__ void wpe_invpower_kernel(const double* __restrict__ power, double* __restrict__ inv, int T, int ctx) {
+__global__ void wpe_invpower_kernel(const double* __restrict__ power, double* __restrict__ inv, WpeDims m, int ctx) {
     __shared__ double red[32];
     const size_t bf = blockIdx.x;
-    const double* p = power + bf * T;
-    double* o = inv + bf * T;
+    const int T = wpe_valid_frames(m, bf);          // statistics over the valid frames only
+    const double* p = power + bf * m.T;
+    double* o = inv + bf * m.T;
     double mx = 0.0;
     for (int t = threadIdx.x; t < T; t += blockDim.x) {
         double v;
@@ -106,6 +112,7 @@ __global__ void __launch_bounds__(CT_NT) wpe_corr_kernel(const float2* __restric
     const int g = lane >> 2, tg = lane & 3;
     const int wm = warp >> 1, wn = warp & 1;
     const int i0 = rt * CT_BM, j0 = ct * CT_BM;
+    const int Tv = wpe_valid_frames(m, bf);
     // staging role: thread < 96 owns one row of A (tid < 48) or B; its source row and shift are fixed
     const int s_which = tid / CT_BM, s_r = tid - s_which * CT_BM;
     const float2* s_src = nullptr;
@@ -121,12 +128,12 @@ __global__ void __launch_bounds__(CT_NT) wpe_corr_kernel(const float2* __restric
 #pragma unroll
             for (int tt = 0; tt < CT_BK; ++tt) {
                 const int t = t0 + tt, ts = t - s_shift;
-                if (s_src != nullptr && t < m.T && ts >= 0) cp_async8(&dst[tt], &s_src[ts]);
+                if (s_src != nullptr && t < Tv && ts >= 0) cp_async8(&dst[tt], &s_src[ts]);
                 else dst[tt] = make_float2(0.f, 0.f);
             }
         } else if (tid < 2 * CT_BM + CT_BK) {
             const int tt = tid - 2 * CT_BM, t = t0 + tt;
-            wsm[buf][tt] = t < m.T ? iv[t] : 0.0;
+            wsm[buf][tt] = t < Tv ? iv[t] : 0.0;
         }
     };
     double cre[3][3][2], cim[3][3][2];
@@ -138,10 +145,10 @@ __global__ void __launch_bounds__(CT_NT) wpe_corr_kernel(const float2* __restric
     const bool warp_live = !(rt == ct && wn > wm) && (i0 + 24 * wm < m.LD + m.D) && (j0 + 24 * wn < m.LD);
     stage(0, 0);
     int buf = 0;
-    for (int t0 = 0; t0 < m.T; t0 += CT_BK, buf ^= 1) {
+    for (int t0 = 0; t0 < Tv; t0 += CT_BK, buf ^= 1) {
         asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;\n" ::: "memory");
         __syncthreads();                                   // chunk `buf` landed; everybody left chunk buf^1
-        if (t0 + CT_BK < m.T) stage(buf ^ 1, t0 + CT_BK);  // prefetch behind the MMAs
+        if (t0 + CT_BK < Tv) stage(buf ^ 1, t0 + CT_BK);   // prefetch behind the MMAs
         if (!warp_live) continue;
 #pragma unroll
         for (int ks = 0; ks < CT_BK / 4; ++ks) {
@@ -458,6 +465,7 @@ __global__ void __launch_bounds__(AP_NT) wpe_apply_kernel(const float2* __restri
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int g = lane >> 2, tg = lane & 3;
     const float2* __restrict__ Yg = Y + bf * (size_t)D * m.T;
+    const int Tv = wpe_valid_frames(m, bf);
     const cd* __restrict__ Gb = G + bf * (size_t)m.LD * D;
     auto stage_g = [&](int buf, int k) {
         cd* dst = Gs + buf * DP4 * AP_GLD;
@@ -474,7 +482,7 @@ __global__ void __launch_bounds__(AP_NT) wpe_apply_kernel(const float2* __restri
         const int d = e / YW, c = e - d * YW;
         const int t = t0 - hist + c;
         float2 v = make_float2(0.f, 0.f);
-        if (d < D && t >= 0 && t < m.T) v = __ldg(&Yg[(size_t)d * m.T + t]);
+        if (d < D && t >= 0 && t < Tv) v = __ldg(&Yg[(size_t)d * m.T + t]);
         Ys[d * YLD + c] = v;
     }
     double cre[MT][2][2], cim[MT][2][2];
@@ -525,7 +533,8 @@ __global__ void __launch_bounds__(AP_NT) wpe_apply_kernel(const float2* __restri
 #pragma unroll
             for (int h = 0; h < 2; ++h) {
                 const int t = t0 + tl + h;
-                if (d < D && t < m.T) {
+                if (d < D && t < m.T && t >= Tv) X[bf * (size_t)D * m.T + (size_t)d * m.T + t] = make_float2(0.f, 0.f);
+                if (d < D && t < Tv) {
                     const float2 y = Ys[d * YLD + hist + tl + h];
                     const double xr = (double)y.x - cre[mi][ni][h], xi = (double)y.y - cim[mi][ni][h];
                     X[bf * (size_t)D * m.T + (size_t)d * m.T + t] = make_float2((float)xr, (float)xi);
@@ -543,7 +552,7 @@ __global__ void __launch_bounds__(AP_NT) wpe_apply_kernel(const float2* __restri
             v += __shfl_xor_sync(0xffffffffu, v, 8);
             v += __shfl_xor_sync(0xffffffffu, v, 16);
             const int t = t0 + 16 * warp + 8 * ni + 2 * tg + h;
-            if (g == 0 && t < m.T) power[bf * m.T + t] = v / D;
+            if (g == 0 && t < Tv) power[bf * m.T + t] = v / D;
         }
 }
 
@@ -587,7 +596,7 @@ static int launch_apply(const float2* Y, const cd* G, float2* X, double* power, 
 }  // namespace gss
 
 extern "C" int gss_wpe_c64(const gss_c64* Y, gss_c64* X, int taps, int delay, int iterations, int psd_context,
-                           int B, int F, int D, int T, int* info, void* ws, size_t ws_bytes, void* stream) {
+                           int B, int F, int D, int T, const int* T_per_utt, int* info, void* ws, size_t ws_bytes, void* stream) {
     using namespace gss;
     GSS_REQUIRE(Y && X && Y != X, GSS_ERR_ARG, "gss_wpe_c64: null or aliased pointers");
     GSS_REQUIRE(B >= 0 && F >= 0 && D > 0 && T > 0, GSS_ERR_ARG, "gss_wpe_c64: bad dims");
@@ -607,18 +616,18 @@ extern "C" int gss_wpe_c64(const gss_c64* Y, gss_c64* X, int taps, int delay, in
     GSS_REQUIRE(ws && ws_bytes >= per_utt, GSS_ERR_WORKSPACE, "gss_wpe_c64: workspace %zu < %zu (one utterance)", ws_bytes, per_utt);
     int Bc = (int)std::min<size_t>((size_t)B, ws_bytes / per_utt);
     while (Bc > 1 && wpe_ws_bytes(Bc, F, D, T, taps) > ws_bytes) --Bc;
-    WpeDims m{F, D, T, taps, delay, LD};
     for (int b0 = 0; b0 < B; b0 += Bc) {
+        WpeDims m{F, D, T, taps, delay, LD, T_per_utt ? T_per_utt + b0 : nullptr};
         const int bn = std::min(Bc, B - b0);
         const int BF = bn * F;
         const float2* Yc = (const float2*)Y + (size_t)b0 * F * D * T;
         float2* Xc = (float2*)X + (size_t)b0 * F * D * T;
         int* infoc = info ? info + b0 : nullptr;
         WpeWs w = wpe_ws_layout(ws, bn, F, D, T, LD);
-        wpe_power_kernel<<<BF, 256, 0, st>>>(Yc, w.power, D, T);
+        wpe_power_kernel<<<BF, 256, 0, st>>>(Yc, w.power, m);
         GSS_LAUNCH_CHECK("wpe_power_kernel");
         for (int it = 0; it < iterations; ++it) {
-            wpe_invpower_kernel<<<BF, 256, 0, st>>>(w.power, w.inv, T, psd_context);
+            wpe_invpower_kernel<<<BF, 256, 0, st>>>(w.power, w.inv, m, psd_context);
             GSS_LAUNCH_CHECK("wpe_invpower_kernel");
             dim3 grid(BF, (LD + D + CT_BM - 1) / CT_BM, (LD + CT_BM - 1) / CT_BM);
             wpe_corr_kernel<<<grid, CT_NT, 0, st>>>(Yc, w.inv, w.Raug, m);

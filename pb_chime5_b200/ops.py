@@ -108,7 +108,16 @@ def unpack_ft_to_tf(x):
 
 # ---- numeric blocks ---------------------------------------------------------
 
-def weighted_cov(Y, w, normalize=True):
+def _tper(frames, B, device):
+    """Optional valid-frame counts per utterance -> int32 device tensor (or None)."""
+    if frames is None:
+        return None
+    t = torch.as_tensor(frames, dtype=torch.int32).reshape(-1).to(device)
+    assert t.numel() == B, (t.numel(), B)
+    return t.contiguous()
+
+
+def weighted_cov(Y, w, normalize=True, frames=None):
     """Phi[b,f,k] = sum_t w'[b,f,k,t] y y^H.  Y (B,F,D,T) c64, w (B,F,K,T) f32."""
     Y = _need(Y, torch.complex64, 4, 'Y')
     w = _need(w, torch.float32, 4, 'w')
@@ -119,12 +128,13 @@ def weighted_cov(Y, w, normalize=True):
     n = _lib.workspace_bytes(_lib.OP_WEIGHTED_COV, B, F, D, T, K, 0)
     ws = workspace(n, Y.device)
     _lib.check(_lib.lib().gss_weighted_cov_c64(_ptr(Y), _ptr(w), _ptr(out), 1 if normalize else 0,
-                                               B, F, D, T, K, _ptr(ws), ws.numel(), _stream()))
+                                               B, F, D, T, K, _ptr(_tper(frames, B, Y.device)),
+                                               _ptr(ws), ws.numel(), _stream()))
     return out
 
 
 def cacgmm(Y, activity, iterations, iterations_post=1, affiliation_eps=1e-10,
-           eigenvalue_floor=1e-10, return_model=False):
+           eigenvalue_floor=1e-10, return_model=False, frames=None):
     """Guided CACGMM EM.  Y (B,F,D,T) c64, activity (B,K,T_act) bool/uint8 ->
     posterior (B,F,K,T) f32 [, model dict]."""
     Y = _need(Y, torch.complex64, 4, 'Y')
@@ -144,7 +154,7 @@ def cacgmm(Y, activity, iterations, iterations_post=1, affiliation_eps=1e-10,
     ws = workspace(_lib.workspace_bytes(_lib.OP_CACGMM, B, F, D, T, K, 0), Y.device)
     _lib.check(_lib.lib().gss_cacgmm_c64(
         _ptr(Y), _ptr(activity), _ptr(post), int(iterations), int(iterations_post),
-        float(affiliation_eps), float(eigenvalue_floor), B, F, D, T, K, T_act,
+        float(affiliation_eps), float(eigenvalue_floor), B, F, D, T, K, T_act, _ptr(_tper(frames, B, Y.device)),
         _ptr(weight), _ptr(logdet), _ptr(cov), _ptr(info), _ptr(ws), ws.numel(), _stream()))
     check_info(info, 'cacgmm')
     if return_model:
@@ -152,7 +162,7 @@ def cacgmm(Y, activity, iterations, iterations_post=1, affiliation_eps=1e-10,
     return post
 
 
-def _bf_call(Y, fn, lead_args, bf, bf_arg, postfilter, K=None, return_aux=False):
+def _bf_call(Y, fn, lead_args, bf, bf_arg, postfilter, K=None, return_aux=False, frames=None):
     B, F, D, T = Y.shape
     if bf not in _lib.BF_TYPES:
         raise NotImplementedError(bf)
@@ -166,7 +176,8 @@ def _bf_call(Y, fn, lead_args, bf, bf_arg, postfilter, K=None, return_aux=False)
     ws = workspace(n, Y.device)
     dims = (B, F, D, T) if K is None else (B, F, D, T, K)
     _lib.check(fn(_ptr(Y), *lead_args, _ptr(X), _lib.BF_TYPES[bf], int(bf_arg), _lib.POSTFILTERS[postfilter],
-                  *dims, _ptr(ref), _ptr(wts), _ptr(info), _ptr(ws), ws.numel(), _stream()))
+                  *dims, _ptr(_tper(frames, B, Y.device)), _ptr(ref), _ptr(wts), _ptr(info), _ptr(ws), ws.numel(),
+                  _stream()))
     check_info(info, 'beamform')
     if return_aux:
         return X, dict(ref_channel=ref, weights=wts)
@@ -174,7 +185,7 @@ def _bf_call(Y, fn, lead_args, bf, bf_arg, postfilter, K=None, return_aux=False)
 
 
 def beamform(Y, target_mask, distortion_mask, bf='mvdrSouden_ban', postfilter=None, bf_arg=0,
-             return_aux=False):
+             return_aux=False, frames=None):
     """Y (B,F,D,T) c64; masks (B,F,T) f32 -> X_hat (B,F,T) c64."""
     Y = _need(Y, torch.complex64, 4, 'Y')
     B, F, D, T = Y.shape
@@ -183,11 +194,11 @@ def beamform(Y, target_mask, distortion_mask, bf='mvdrSouden_ban', postfilter=No
     assert tm.shape == (B, F, T), (tm.shape, B, F, T)
     assert dm.shape == (B, F, T), (dm.shape, B, F, T)
     return _bf_call(Y, _lib.lib().gss_beamform_c64, (_ptr(tm), _ptr(dm)), bf, bf_arg, postfilter,
-                    return_aux=return_aux)
+                    return_aux=return_aux, frames=frames)
 
 
 def beamform_from_posterior(Y, posterior, target_index, start_ctx=None, end_ctx=None,
-                            bf='mvdrSouden_ban', postfilter=None, bf_arg=0, return_aux=False):
+                            bf='mvdrSouden_ban', postfilter=None, bf_arg=0, return_aux=False, frames=None):
     """Fused core.py:537-564.  posterior (B,F,K,T) f32; target_index/start_ctx/end_ctx (B) int32."""
     Y = _need(Y, torch.complex64, 4, 'Y')
     B, F, D, T = Y.shape
@@ -205,10 +216,10 @@ def beamform_from_posterior(Y, posterior, target_index, start_ctx=None, end_ctx=
     ti, sc, ec = ivec(target_index), ivec(start_ctx), ivec(end_ctx)
     return _bf_call(Y, _lib.lib().gss_beamform_from_posterior_c64,
                     (_ptr(post), _ptr(ti), _ptr(sc), _ptr(ec)), bf, bf_arg, postfilter, K=K,
-                    return_aux=return_aux)
+                    return_aux=return_aux, frames=frames)
 
 
-def wpe(Y, taps=10, delay=3, iterations=3, psd_context=0):
+def wpe(Y, taps=10, delay=3, iterations=3, psd_context=0, frames=None):
     """Y (B,F,D,T) c64 -> dereverberated (B,F,D,T) c64."""
     Y = _need(Y, torch.complex64, 4, 'Y')
     B, F, D, T = Y.shape
@@ -217,8 +228,8 @@ def wpe(Y, taps=10, delay=3, iterations=3, psd_context=0):
     n = _lib.workspace_bytes(_lib.OP_WPE, B, F, D, T, 0, int(taps))
     ws = workspace(n, Y.device)
     _lib.check(_lib.lib().gss_wpe_c64(_ptr(Y), _ptr(X), int(taps), int(delay), int(iterations),
-                                      int(psd_context), B, F, D, T, _ptr(info), _ptr(ws), ws.numel(),
-                                      _stream()))
+                                      int(psd_context), B, F, D, T, _ptr(_tper(frames, B, Y.device)), _ptr(info),
+                                      _ptr(ws), ws.numel(), _stream()))
     return X
 
 

@@ -251,3 +251,33 @@ def test_stress_shape_cfg5_spot_parity():
     post = ops.cacgmm(Y, torch.from_numpy(act)[None].to(dev), 12)
     ref = oracle.gss_posteriors(Obs.astype(np.complex128), act, 12)
     assert np.abs(ops.unpack_fkt_to_ktf(post)[0].cpu().numpy() - ref).max() < 1e-4
+
+
+def test_ragged_batch_equals_single_utterances():
+    """T_per_utt: a padded batch of utterances of different lengths gives, for each utterance,
+    exactly what the utterance gives alone (WPE + EM + MVDR), and zeros in the padding."""
+    dev = torch.device('cuda')
+    lens = [150, 97, 128]
+    Tmax, D, F, K = 160, 8, 5, 3
+    enh = core.get_enhancer(wpe_tabs=3, wpe_iterations=2, bss_iterations=6)
+    Ypad = torch.zeros((len(lens), F, D, Tmax), dtype=torch.complex64, device=dev)
+    Apad = torch.zeros((len(lens), K, Tmax), dtype=torch.uint8, device=dev)
+    singles = []
+    for b, T in enumerate(lens):
+        obs, act = synth.make_utterance(700 + b, D=D, T=T, F=F, K=K)
+        Y = ops.pack_dtf_to_fdt(torch.from_numpy(obs).to(dev)[None])
+        A = torch.from_numpy(act.astype(np.uint8))[None].to(dev)
+        Ypad[b, :, :, :T] = Y[0]
+        Ypad[b, :, :, T:] = 7.0          # garbage in the padding must be ignored
+        Apad[b, :, :T] = A[0]
+        Apad[b, :, T:] = 1
+        iv = lambda v: torch.tensor([v], dtype=torch.int32, device=dev)
+        singles.append(enh.enhance_stft_batch(Y, A, iv(b % K), iv(3), iv(3), return_masks=True))
+    ti = torch.tensor([b % K for b in range(len(lens))], dtype=torch.int32, device=dev)
+    c3 = torch.full((len(lens),), 3, dtype=torch.int32, device=dev)
+    X, post = enh.enhance_stft_batch(Ypad, Apad, ti, c3, c3, return_masks=True, frames=lens)
+    for b, T in enumerate(lens):
+        Xs, ps = singles[b]
+        assert torch.equal(post[b, :, :, :T], ps[0])
+        assert torch.equal(X[b, :, :T], Xs[0])
+        assert float(post[b, :, :, T:].abs().max()) == 0 and float(X[b, :, T:].abs().max()) == 0

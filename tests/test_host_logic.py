@@ -35,24 +35,24 @@ def test_abi_argument_errors_map_to_reference_exceptions():
     assert n.value > 513 * 240 * 240 * 16
     # null pointers / limits never reach a launch
     with pytest.raises(AssertionError):
-        _lib.check(L.gss_cacgmm_c64(None, None, None, 1, 1, 1e-10, 1e-10, 1, 1, 4, 10, 3, 10,
+        _lib.check(L.gss_cacgmm_c64(None, None, None, 1, 1, 1e-10, 1e-10, 1, 1, 4, 10, 3, 10, None,
                                     None, None, None, None, None, 0, None))
     one = ctypes.c_void_p(16)            # dummy non-null, never dereferenced on the host
     with pytest.raises(AssertionError, match='sure'):      # cacgmm.py:248  D < 35
-        _lib.check(L.gss_cacgmm_c64(one, one, one, 1, 1, 1e-10, 1e-10, 1, 1, 35, 10, 3, 10,
+        _lib.check(L.gss_cacgmm_c64(one, one, one, 1, 1, 1e-10, 1e-10, 1, 1, 35, 10, 3, 10, None,
                                     None, None, None, None, None, 0, None))
     with pytest.raises(AssertionError, match='sure'):      # cacgmm.py:247  K < 20
-        _lib.check(L.gss_cacgmm_c64(one, one, one, 1, 1, 1e-10, 1e-10, 1, 1, 4, 10, 20, 10,
+        _lib.check(L.gss_cacgmm_c64(one, one, one, 1, 1, 1e-10, 1e-10, 1, 1, 4, 10, 20, 10, None,
                                     None, None, None, None, None, 0, None))
     with pytest.raises(NotImplementedError):               # iterations_post == 0 (core.py:198-202)
-        _lib.check(L.gss_cacgmm_c64(one, one, one, 1, 0, 1e-10, 1e-10, 1, 1, 4, 10, 3, 10,
+        _lib.check(L.gss_cacgmm_c64(one, one, one, 1, 0, 1e-10, 1e-10, 1, 1, 4, 10, 3, 10, None,
                                     None, None, None, None, None, 0, None))
     with pytest.raises(AssertionError):                    # beamforming_wrapper.py:44  D < 30
-        _lib.check(L.gss_beamform_c64(one, one, one, one, 0, 0, 0, 1, 1, 30, 10, None, None, None, one, 1 << 30, None))
+        _lib.check(L.gss_beamform_c64(one, one, one, one, 0, 0, 0, 1, 1, 30, 10, None, None, None, None, one, 1 << 30, None))
     with pytest.raises(NotImplementedError):               # unknown beamformer type
-        _lib.check(L.gss_beamform_c64(one, one, one, one, 17, 0, 0, 1, 1, 4, 10, None, None, None, one, 1 << 30, None))
+        _lib.check(L.gss_beamform_c64(one, one, one, one, 17, 0, 0, 1, 1, 4, 10, None, None, None, None, one, 1 << 30, None))
     with pytest.raises(RuntimeError, match='workspace'):
-        _lib.check(L.gss_beamform_c64(one, one, one, one, 0, 0, 0, 1, 1, 4, 10, None, None, None, one, 8, None))
+        _lib.check(L.gss_beamform_c64(one, one, one, one, 0, 0, 0, 1, 1, 4, 10, None, None, None, None, one, 8, None))
 
 
 def test_get_enhancer_signature_matches_reference():
