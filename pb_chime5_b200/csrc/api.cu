@@ -55,7 +55,8 @@ int gss_workspace_bytes(int op, int B, int F, int D, int T, int K, int L, size_t
     size_t n = 256;
     switch (op) {
         case GSS_OP_WEIGHTED_COV: n = weighted_cov_ws_bytes(B, F, D, K); break;
-        case GSS_OP_CACGMM: n = 1024; break;
+        case GSS_OP_CACGMM:   // warm-start eigenvectors of the exact path + flags
+            n = align_up(((size_t)B * F * K + 2) * sizeof(int)) + align_up((size_t)B * F * K * D * (D + 2) * 16); break;
         case GSS_OP_BEAMFORM: n = beamform_ws_bytes(B, F, D); break;
         case GSS_OP_WPE: n = wpe_ws_bytes(B < 4 ? B : 4, F, D, T, L); break;   // utterances are processed in chunks
         case GSS_OP_STFT: n = 256; break;

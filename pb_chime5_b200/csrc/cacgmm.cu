@@ -32,7 +32,9 @@ struct CacgmmParams {
     double* logdet_out;       // (B,F,K) or null
     double* cov_out;          // (B,F,K,D,D) complex128 or null
     int* info;                // (B) or null
-    int* slow_count;          // (1) or null : number of slow-path (Jacobi) class updates
+    int* slow_count;          // (2) or null : [0] slow-path (Jacobi) class updates, [1] Jacobi sweeps
+    double* jac_v;            // (B*F*K, D, D+1) complex128 or null: eigenvectors of the previous pass (warm start)
+    int* jac_has_v;           // (B*F*K) zeroed per launch
     int B, F, D, T, T_act;
     int iterations, iterations_post;
     double eps, floor_;
@@ -67,7 +69,7 @@ struct CacgmmCfg {
     static constexpr size_t MT_BYTES = size_t(2) * TM * YLD * sizeof(float2);   // double-buffered complex64 M tiles
     static constexpr size_t MS_BYTES = 0;
     static constexpr size_t SWEEP_BYTES = size_t(K) * NP * sizeof(cd) + size_t(2) * K * DP * sizeof(cd) + 2 * K * 8 + 64;
-    static constexpr size_t JAC_BYTES = size_t(2) * DP * JLD * sizeof(cd);
+    static constexpr size_t JAC_BYTES = size_t(3) * DP * JLD * sizeof(cd);
     static constexpr size_t YS_BYTES = cmax(cmax(E_BYTES, MT_BYTES + MS_BYTES), cmax(SWEEP_BYTES, JAC_BYTES));
     static constexpr size_t W_BYTES = size_t(TE) * KP * sizeof(double);
     static constexpr size_t B_BYTES = size_t(NP) * K * sizeof(cd);
@@ -519,9 +521,43 @@ __global__ void __launch_bounds__(NT, MINB) cacgmm_em_kernel(const CacgmmParams 
                 A[r * C::JLD + c] = v;
             }
             __syncthreads();
-            const int sweeps = block_jacobi_eigh(A, V, D, C::JLD, jrot, jred, tid, NT);
+            // Warm start: EM changes the covariance slowly, so the eigenvectors of the previous pass
+            // almost diagonalise it: A' = V^H A V needs 1-2 sweeps instead of ~8.
+            bool warm = false;
+            cd* Vg = nullptr;
+            if (p.jac_v != nullptr) {
+                Vg = reinterpret_cast<cd*>(p.jac_v) + ((size_t)bf * K + k) * D * C::JLD;
+                warm = p.jac_has_v[(size_t)bf * K + k] != 0;
+            }
+            if (warm) {
+                cd* Tm = V + DP * C::JLD;                                  // third scratch matrix
+                for (int i = tid; i < D * C::JLD; i += NT) V[i] = Vg[i];
+                __syncthreads();
+                for (int i = tid; i < D * D; i += NT) {                    // T = A V
+                    const int r = i / D, c = i - r * D;
+                    cd acc = cmake(0.0, 0.0);
+                    for (int j = 0; j < D; ++j) cfma(acc, A[r * C::JLD + j], V[j * C::JLD + c]);
+                    Tm[r * C::JLD + c] = acc;
+                }
+                __syncthreads();
+                for (int i = tid; i < D * D; i += NT) {                    // A' = V^H T (lower, then mirrored)
+                    const int r = i / D, c = i - r * D;
+                    if (c > r) continue;
+                    cd acc = cmake(0.0, 0.0);
+                    for (int j = 0; j < D; ++j) cfma(acc, cconj(V[j * C::JLD + r]), Tm[j * C::JLD + c]);
+                    if (r == c) acc.y = 0.0;
+                    A[r * C::JLD + c] = acc;
+                    if (r != c) A[c * C::JLD + r] = cconj(acc);
+                }
+                __syncthreads();
+            }
+            const int sweeps = block_jacobi_eigh(A, V, D, C::JLD, jrot, jred, tid, NT, !warm);
             if (sweeps < 0 && tid == 0 && p.info) atomicMax(&p.info[b], GSS_INFO_NO_CONVERGE | (f << 8));
-            if (tid == 0 && p.slow_count) atomicAdd(p.slow_count, 1);
+            if (tid == 0 && p.slow_count) { atomicAdd(p.slow_count, 1); atomicAdd(p.slow_count + 1, sweeps < 0 ? 40 : sweeps); }
+            if (Vg != nullptr) {
+                for (int i = tid; i < D * C::JLD; i += NT) Vg[i] = V[i];
+                if (tid == 0) p.jac_has_v[(size_t)bf * K + k] = 1;
+            }
             double* lam = jred;                  // [D] inverse floored eigenvalues
             __syncthreads();
             if (tid == 0) {
@@ -624,7 +660,6 @@ extern "C" int gss_cacgmm_c64(const gss_c64* Y, const uint8_t* activity, float* 
                               double* weight_out, double* logdet_out, double* covariance_out,
                               int* info, void* ws, size_t ws_bytes, void* stream) {
     using namespace gss;
-    (void)ws; (void)ws_bytes;
     GSS_REQUIRE(Y && activity && posterior, GSS_ERR_ARG, "gss_cacgmm_c64: null pointer");
     GSS_REQUIRE(B >= 0 && F >= 0 && T > 0, GSS_ERR_ARG, "gss_cacgmm_c64: bad dims B=%d F=%d T=%d", B, F, T);
     GSS_REQUIRE(D > 1, GSS_ERR_ARG, "gss_cacgmm_c64: D=%d, need D > 1 (cacgmm.py:196)", D);
@@ -641,6 +676,16 @@ extern "C" int gss_cacgmm_c64(const gss_c64* Y, const uint8_t* activity, float* 
     p.Y = (const float2*)Y; p.activity = activity; p.posterior = posterior; p.Tper = T_per_utt;
     p.weight_out = weight_out; p.logdet_out = logdet_out; p.cov_out = covariance_out;
     p.info = info; p.slow_count = nullptr;
+    p.jac_v = nullptr; p.jac_has_v = nullptr;
+    {   // optional warm-start store for the exact (Jacobi) path; without workspace the path starts cold
+        Arena a(ws, ws_bytes);
+        int* has = a.take<int>((size_t)B * F * K + 2);
+        double* jv = a.take<double>((size_t)B * F * K * D * (D + 2) * 2);
+        if (ws != nullptr && a.ok()) {
+            GSS_CUDA(cudaMemsetAsync(has, 0, ((size_t)B * F * K + 2) * sizeof(int), (cudaStream_t)stream));
+            p.jac_has_v = has; p.jac_v = jv; p.slow_count = has + (size_t)B * F * K;
+        }
+    }
     p.B = B; p.F = F; p.D = D; p.T = T; p.T_act = T_act;
     p.iterations = iterations; p.iterations_post = iterations_post;
     p.eps = affiliation_eps; p.floor_ = eigenvalue_floor;

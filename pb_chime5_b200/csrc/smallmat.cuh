@@ -130,7 +130,10 @@ __device__ inline int block_jacobi_eigh(cd* A, cd* V, int n, int ld, JacobiRot* 
         }
         off = block_sum(off, red, tid, nthreads);
         dia = block_sum(dia, red, tid, nthreads);
-        if (off <= 1e-30 * dia || off == 0.0) break;
+        // converged when the off-diagonal norm is at the rounding level of the matrix
+        // (n * eps relative): below that the sweeps only shuffle rounding noise
+        const double tol = 4.0 * (double)(n * n) * 4.93e-32;
+        if (off <= tol * dia || off == 0.0) break;
         const double thresh = 1e-36 * dia;
         for (int round = 0; round < m - 1; ++round) {
             if (tid < half) {
