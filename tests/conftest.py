@@ -14,6 +14,17 @@ def pytest_configure(config):
     config.addinivalue_line('markers', 'gpu: needs a CUDA device (run on the B200 box)')
 
 
+@pytest.fixture(scope='session', autouse=True)
+def built_library():
+    """The C-ABI library is a build artefact (git-ignored): build it once if it is missing so
+    that the CPU suite can check the exported surface on a fresh checkout."""
+    lib = ROOT / 'pb_chime5_b200' / 'csrc' / 'libgss.so'
+    if not lib.exists():
+        import subprocess
+        subprocess.run(['bash', str(ROOT / 'pb_chime5_b200' / 'csrc' / 'build.sh')], check=True)
+    return lib
+
+
 @pytest.fixture(scope='session')
 def golden_dir():
     return GOLDEN
