@@ -148,6 +148,22 @@ int gss_wpe_c64(const gss_c64* Y, gss_c64* X, int taps, int delay, int iteration
                 int psd_context, int B, int F, int D, int T, const int* T_per_utt,
                 int* info, void* ws, size_t ws_bytes, void* stream);
 
+/* ---- whole STFT-domain hot path in one call (Enhancer.enhance_observation without the
+ * transforms, core.py:524-564), reference layouts on both sides ---------------------
+ * Obs (B,D,T,F) c64; activity (B,K,T_act) u8; target_index / start_ctx / end_ctx (B) int32
+ * device (context in frames, may be NULL = no context drop); T_per_utt (B) or NULL.
+ * X_hat (B,T,F) c64; posterior (B,K,T,F) f32 or NULL (as GSS returns it: context NOT zeroed).
+ * wpe_taps == 0 or wpe_iterations == 0 skips WPE (wpe_block is None).  Workspace:
+ * gss_workspace_bytes(GSS_OP_ENHANCE, B, F, D, T, K, wpe_taps). */
+int gss_enhance_c64(const gss_c64* Obs, const uint8_t* activity, const int* target_index,
+                    const int* start_ctx, const int* end_ctx, const int* T_per_utt,
+                    gss_c64* X_hat, float* posterior,
+                    int wpe_taps, int wpe_delay, int wpe_iterations, int wpe_psd_context,
+                    int em_iterations, int em_iterations_post,
+                    int bf_type, int bf_arg, int postfilter,
+                    int B, int F, int D, int T, int K, int T_act,
+                    int* info, void* ws, size_t ws_bytes, void* stream);
+
 /* ---- STFT / iSTFT (Enhancer.stft / .istft, core.py:305-321 -> nara_wpe.utils)
  * x (B,D,N) f32 -> Y (B,F,D,T) c64 bin-major, F = size/2+1,
  * T = ceil((N + 2*(size-shift)*fading - size + shift)/shift); Blackman window. */

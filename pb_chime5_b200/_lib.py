@@ -50,6 +50,7 @@ _SIGNATURES = {
     'gss_beamform_from_posterior_c64': (_i, [_p, _p, _p, _p, _p, _p, _i, _i, _i,
                                              _i, _i, _i, _i, _i, _p, _p, _p, _p, _p, _sz, _p]),
     'gss_wpe_c64': (_i, [_p, _p, _i, _i, _i, _i, _i, _i, _i, _i, _p, _p, _p, _sz, _p]),
+    'gss_enhance_c64': (_i, [_p] * 8 + [_i] * 15 + [_p, _p, _sz, _p]),
     'gss_stft_f32': (_i, [_p, _p, _i, _i, _i, _i, _i, _i, _p, _sz, _p]),
     'gss_istft_f32': (_i, [_p, _p, _i, _i, _i, _i, _i, _p, _sz, _p]),
 }

@@ -12,7 +12,7 @@
 #include "smallmat.cuh"
 
 #ifndef GSS_DP_LIST
-#define GSS_DP_LIST GSS_CASE(2) GSS_CASE(4) GSS_CASE(6) GSS_CASE(8) GSS_CASE(12) GSS_CASE(16) GSS_CASE(24)
+#define GSS_DP_LIST GSS_CASE(2) GSS_CASE(4) GSS_CASE(6) GSS_CASE(8) GSS_CASE(10) GSS_CASE(12) GSS_CASE(16) GSS_CASE(20) GSS_CASE(24)
 #endif
 
 namespace gss {

@@ -1,0 +1,73 @@
+// gss_enhance_c64: the whole STFT-domain hot path of Enhancer.enhance_observation
+// (pb_chime5/core.py:524-564) behind one C call, reference layouts in and out:
+//   Obs (B,D,T,F) -> pack -> [WPE] -> guided CACGMM EM -> context drop + target/distortion
+//   split + beamformer (+ postfilter) -> X_hat (B,T,F) [, posterior (B,K,T,F)]
+// Pure orchestration of the other entry points on one stream; no extra kernels.
+#include "common.cuh"
+
+namespace gss {
+size_t beamform_ws_bytes(int B, int F, int D);
+size_t wpe_ws_bytes(int Bc, int F, int D, int T, int L);
+
+struct EnhanceWs { float2* Yf; float2* Yw; float* post; float2* Xf; void* sub; size_t sub_bytes; size_t bytes; };
+
+static size_t cacgmm_ws_bytes(int B, int F, int D, int K) {
+    return align_up(((size_t)B * F * K + 2) * sizeof(int)) + align_up((size_t)B * F * K * D * (D + 2) * 16);
+}
+
+static EnhanceWs enhance_layout(void* ws, int B, int F, int D, int T, int K, int L, bool wpe) {
+    Arena a(ws, ~size_t(0));
+    EnhanceWs w;
+    w.Yf = a.take<float2>((size_t)B * F * D * T);
+    w.Yw = wpe ? a.take<float2>((size_t)B * F * D * T) : nullptr;
+    w.post = a.take<float>((size_t)B * F * K * T);
+    w.Xf = a.take<float2>((size_t)B * F * T);
+    size_t sub = std::max(cacgmm_ws_bytes(B, F, D, K), beamform_ws_bytes(B, F, D));
+    if (wpe) sub = std::max(sub, wpe_ws_bytes(B < 4 ? B : 4, F, D, T, L));
+    w.sub = a.take<char>(sub);
+    w.sub_bytes = sub;
+    w.bytes = a.off;
+    return w;
+}
+
+size_t enhance_ws_bytes(int B, int F, int D, int T, int K, int L) {
+    return enhance_layout(nullptr, B, F, D, T, K, L, L > 0).bytes;
+}
+}  // namespace gss
+
+extern "C" int gss_enhance_c64(const gss_c64* Obs, const uint8_t* activity, const int* target_index,
+                               const int* start_ctx, const int* end_ctx, const int* T_per_utt,
+                               gss_c64* X_hat, float* posterior,
+                               int wpe_taps, int wpe_delay, int wpe_iterations, int wpe_psd_context,
+                               int em_iterations, int em_iterations_post,
+                               int bf_type, int bf_arg, int postfilter,
+                               int B, int F, int D, int T, int K, int T_act,
+                               int* info, void* ws, size_t ws_bytes, void* stream) {
+    using namespace gss;
+    GSS_REQUIRE(Obs && activity && target_index && X_hat, GSS_ERR_ARG, "gss_enhance_c64: null pointer");
+    GSS_REQUIRE(B >= 0 && F > 0 && D > 0 && T > 0 && K > 1, GSS_ERR_ARG, "gss_enhance_c64: bad dims");
+    if (B == 0) return GSS_OK;
+    const bool wpe = wpe_taps > 0 && wpe_iterations > 0;
+    EnhanceWs w = enhance_layout(ws, B, F, D, T, K, wpe ? wpe_taps : 0, wpe);
+    GSS_REQUIRE(ws && ws_bytes >= w.bytes, GSS_ERR_WORKSPACE, "gss_enhance_c64: workspace %zu < %zu", ws_bytes, w.bytes);
+    int rc = gss_pack_dtf_to_fdt_c64(Obs, (gss_c64*)w.Yf, B, D, T, F, stream);
+    if (rc) return rc;
+    const gss_c64* Y = (const gss_c64*)w.Yf;
+    if (wpe) {
+        rc = gss_wpe_c64(Y, (gss_c64*)w.Yw, wpe_taps, wpe_delay, wpe_iterations, wpe_psd_context, B, F, D, T,
+                         T_per_utt, info, w.sub, w.sub_bytes, stream);
+        if (rc) return rc;
+        Y = (const gss_c64*)w.Yw;
+    }
+    rc = gss_cacgmm_c64(Y, activity, w.post, em_iterations, em_iterations_post, 1e-10, 1e-10, B, F, D, T, K, T_act,
+                        T_per_utt, nullptr, nullptr, nullptr, info, w.sub, w.sub_bytes, stream);
+    if (rc) return rc;
+    rc = gss_beamform_from_posterior_c64(Y, w.post, target_index, start_ctx, end_ctx, (gss_c64*)w.Xf, bf_type, bf_arg,
+                                         postfilter, B, F, D, T, K, T_per_utt, nullptr, nullptr, info,
+                                         w.sub, w.sub_bytes, stream);
+    if (rc) return rc;
+    rc = gss_unpack_ft_to_tf_c64((const gss_c64*)w.Xf, X_hat, B, T, F, stream);
+    if (rc) return rc;
+    if (posterior) rc = gss_unpack_fkt_to_ktf_f32(w.post, posterior, B, K, T, F, stream);
+    return rc;
+}

@@ -264,3 +264,36 @@ def istft(X, size=1024, shift=256, fading=True):
     _lib.check(_lib.lib().gss_istft_f32(_ptr(X), _ptr(out), B, T, int(size), int(shift), 1 if fading else 0,
                                         _ptr(ws), ws.numel(), _stream()))
     return out
+
+
+def enhance(Obs, activity, target_index, start_ctx=None, end_ctx=None, frames=None, *, wpe=None,
+            em_iterations=20, em_iterations_post=1, bf='mvdrSouden_ban', postfilter=None, bf_arg=0,
+            return_posterior=True):
+    """Whole STFT-domain hot path in ONE library call (gss_enhance_c64), reference layouts:
+    Obs (B,D,T,F) c64, activity (B,K,T_act) -> X_hat (B,T,F) c64 [, posterior (B,K,T,F) f32].
+    wpe: None or (taps, delay, iterations, psd_context)."""
+    Obs = _need(Obs, torch.complex64, 4, 'Obs')
+    B, D, T, F = Obs.shape
+    if activity.dtype == torch.bool:
+        activity = activity.to(torch.uint8)
+    activity = _need(activity, torch.uint8, 3, 'activity')
+    K, T_act = activity.shape[1], activity.shape[2]
+    if bf not in _lib.BF_TYPES:
+        raise NotImplementedError(bf)
+    if postfilter not in _lib.POSTFILTERS:
+        raise NotImplementedError(postfilter)
+    taps, delay, its, ctx = wpe if wpe is not None else (0, 0, 0, 0)
+    ivec = lambda v: None if v is None else torch.as_tensor(v, dtype=torch.int32).reshape(-1).to(Obs.device).contiguous()
+    ti, sc, ec = ivec(target_index), ivec(start_ctx), ivec(end_ctx)
+    assert ti is not None and ti.numel() == B
+    X = torch.empty((B, T, F), dtype=torch.complex64, device=Obs.device)
+    post = torch.empty((B, K, T, F), dtype=torch.float32, device=Obs.device) if return_posterior else None
+    info = torch.zeros((max(B, 1),), dtype=torch.int32, device=Obs.device)
+    ws = workspace(_lib.workspace_bytes(_lib.OP_ENHANCE, B, F, D, T, K, int(taps)), Obs.device)
+    _lib.check(_lib.lib().gss_enhance_c64(
+        _ptr(Obs), _ptr(activity), _ptr(ti), _ptr(sc), _ptr(ec), _ptr(_tper(frames, B, Obs.device)),
+        _ptr(X), _ptr(post), int(taps), int(delay), int(its), int(ctx), int(em_iterations), int(em_iterations_post),
+        _lib.BF_TYPES[bf], int(bf_arg), _lib.POSTFILTERS[postfilter], B, F, D, T, K, T_act,
+        _ptr(info), _ptr(ws), ws.numel(), _stream()))
+    check_info(info, 'enhance')
+    return (X, post) if return_posterior else X

@@ -109,7 +109,7 @@ def _gss_both(Obs, act, iters, post_iters=1):
     return got, ref
 
 
-@pytest.mark.parametrize('D,K', [(2, 2), (3, 3), (5, 4), (6, 6), (7, 3), (12, 5), (16, 3)])
+@pytest.mark.parametrize('D,K', [(2, 2), (3, 3), (5, 4), (6, 6), (7, 3), (10, 4), (12, 5), (16, 3), (20, 5)])
 def test_gss_channel_and_class_counts(D, K):
     Obs, act = synth.make_utterance(100 + D, D=D, T=140, F=3, K=K)
     got, ref = _gss_both(Obs, act, 6)
@@ -296,3 +296,20 @@ def test_gss_rank_deficient_class():
     err = np.abs(got - ref)
     assert np.quantile(err, 0.99) < 1e-4, np.quantile(err, 0.99)
     assert err.max() < 5e-2, err.max()
+
+
+def test_single_call_enhance_equals_blocks():
+    """gss_enhance_c64 (one C call, reference layouts) == the block-wise device path."""
+    dev = torch.device('cuda')
+    B = 2
+    obs, act = synth.make_batch(900, B, D=4, T=110, F=7, K=3)
+    enh = core.get_enhancer(wpe_tabs=3, wpe_iterations=2, bss_iterations=5)
+    O = torch.from_numpy(obs).to(dev); A = torch.from_numpy(act).to(dev)
+    ti = torch.tensor([0, 1], dtype=torch.int32, device=dev)
+    c3 = torch.full((B,), 3, dtype=torch.int32, device=dev)
+    X1, p1 = enh.enhance_stft_batch(ops.pack_dtf_to_fdt(O), A, ti, c3, c3, return_masks=True)
+    X2, p2 = ops.enhance(O, A, ti, c3, c3, wpe=(3, 2, 2, 0), em_iterations=5)
+    assert torch.equal(ops.unpack_ft_to_tf(X1), X2)
+    assert torch.equal(ops.unpack_fkt_to_ktf(p1), p2)
+    X3 = ops.enhance(O, A, ti, None, None, wpe=None, em_iterations=5, bf='gev_ban', return_posterior=False)
+    assert X3.shape == (B, 110, 7) and torch.isfinite(torch.view_as_real(X3)).all()
