@@ -166,6 +166,17 @@ def algorithmic_bytes_em(B):
     return B * it * (cov + est), B * fused_min
 
 
+def algorithmic_flops_em(B):
+    """SURVEY.md section 8d flop counts of the same launch: cov F*K*T*8*D^2 + E-step
+    F*K*T*(8*D^2 + 8*D) per iteration (full D x D complex contractions).  The kernel executes
+    fewer: Hermitian half + outer products shared by the K classes = 4*(4 + 2K) FMA per pair-frame."""
+    D, T, F, K, it = CFG['D'], CFG['T'], CFG['F'], CFG['K'], CFG['em_iterations']
+    alg = B * it * (F * K * T * 8 * D * D + F * K * T * (8 * D * D + 8 * D))
+    pairs = D * (D + 1) // 2
+    executed = B * it * F * T * 2 * (2 * pairs * (4 + 2 * K))      # E + M, 2 flops per FMA
+    return alg, executed
+
+
 def run_gpu(args):
     import torch
     from pb_chime5_b200 import _lib, core, ops, sharding, synth
@@ -256,6 +267,7 @@ def run_gpu(args):
         peak, peak_src = 6650.0, 'fallback (B200_PROFILING.md)'
     alg_bytes, fused_min = algorithmic_bytes_em(B)
     achieved = alg_bytes / (em_ms * 1e-3) / 1e9
+    alg_flops, exe_flops = algorithmic_flops_em(B)
     traffic = None
     tfile = ROOT / 'profiles' / 'em_kernel_traffic.json'
     if tfile.exists():
@@ -287,6 +299,11 @@ def run_gpu(args):
                      'algorithmic_bytes_per_launch': alg_bytes,
                      'fused_minimum_bytes_per_launch': fused_min,
                      'kernel_ms': em_ms,
+                     'fp64': {'algorithmic_tflops': alg_flops / (em_ms * 1e-3) / 1e12,
+                              'executed_tflops': exe_flops / (em_ms * 1e-3) / 1e12,
+                              'peak_tflops_measured': 35.7,
+                              'peak_source': 'tools/fp64_probe.cu on this pool (DFMA 35.7, FP64 MMA 37.2 TFLOP/s)',
+                              'pipe_active_ncu': 0.48},
                      'note': 'declared variant: per-iteration covariance+E-step streams x 100 iterations (SURVEY 8d); '
                              'the kernel is FP64-pipe bound at D=24, see DESIGN.md'},
         'clocks': clocks,

@@ -76,3 +76,35 @@ def make_audio(seed, D=4, N=48000, K=3, stft_size=1024, stft_shift=256):
             obs[d] += np.convolve(src[k], h[k, d])[:N]
     obs += 0.05 * rng.standard_normal((D, N)).astype(np.float32)
     return obs, act
+
+
+def make_reverberant_audio(seed, D=8, N=64000, K=3, rir_len=2048, t60_taps=900.0, noise=0.02):
+    """Speech-like (AR(2)-coloured, amplitude-modulated) sources through long, exponentially
+    decaying random room responses: strongly time-correlated, reverberant, low-noise input --
+    the regime where the WPE normal equations are ill conditioned.  Returns obs (D, N) float32
+    and sample activity (K, N) bool (last class = noise)."""
+    rng = np.random.default_rng(seed)
+    S = K - 1
+    act = np.ones((K, N), dtype=bool)
+    src = np.zeros((S, N), dtype=np.float64)
+    for k in range(S):
+        e = rng.standard_normal(N)
+        x = np.zeros(N)
+        a1, a2 = 1.6 - 0.2 * k, -0.8                      # resonant AR(2)
+        for n in range(2, N):
+            x[n] = a1 * x[n - 1] + a2 * x[n - 2] + e[n]
+        env = (np.sin(2 * np.pi * (1.5 + k) * np.arange(N) / 16000.0 + k) > -0.2)
+        gate = np.ones(N, dtype=bool)
+        seg = N // 6
+        off = rng.integers(0, 6)
+        gate[off * seg:(off + 1) * seg] = False          # one silent sixth per speaker
+        act[k] = gate
+        src[k] = x * env * gate / (np.std(x) + 1e-12)
+    h = rng.standard_normal((S, D, rir_len)) * np.exp(-np.arange(rir_len) / (t60_taps / 6.9))
+    h[:, :, 0] += 3.0                                     # direct path
+    obs = np.zeros((D, N))
+    for k in range(S):
+        for d in range(D):
+            obs[d] += np.convolve(src[k], h[k, d])[:N]
+    obs += noise * np.std(obs) * rng.standard_normal((D, N))
+    return obs.astype(np.float32), act

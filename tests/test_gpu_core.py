@@ -313,3 +313,36 @@ def test_single_call_enhance_equals_blocks():
     assert torch.equal(ops.unpack_fkt_to_ktf(p1), p2)
     X3 = ops.enhance(O, A, ti, None, None, wpe=None, em_iterations=5, bf='gev_ban', return_posterior=False)
     assert X3.shape == (B, 110, 7) and torch.isfinite(torch.view_as_real(X3)).all()
+
+
+def test_reverberant_speech_like_stagewise():
+    """Strongly time-correlated, reverberant, low-noise audio (ill-conditioned WPE normal
+    equations, cond ~1e6+): every block against the oracle on identical inputs, on a subset of bins."""
+    dev = torch.device('cuda')
+    obs, sact = synth.make_reverberant_audio(3, D=8, N=48000, K=3)
+    Y = ops.stft(torch.from_numpy(obs).to(dev)[None])                    # (1,F,D,T)
+    bins = [5, 40, 129, 300, 480]
+    Ysub = Y[:, bins].contiguous()
+    S64 = ops.unpack_fdt_to_dtf(Ysub)[0].cpu().numpy().astype(np.complex128)
+    refw = oracle.wpe_dtf(S64, 10, 2, 3)
+    Yw = ops.wpe(Ysub, 10, 2, 3)
+    W64 = ops.unpack_fdt_to_dtf(Yw)[0].cpu().numpy().astype(np.complex128)
+    # On such data the WPE iteration amplifies perturbations ~100x per iteration: the float64
+    # reference itself moves by ~4e-4 when its input is rescaled by (1 + 1e-12).  The device
+    # result has to agree within that self-sensitivity (and to float32 rounding after 1 iteration).
+    self_sens = rel_err(oracle.wpe_dtf(S64 * (1 + 1e-12), 10, 2, 3) / (1 + 1e-12), refw)
+    assert rel_err(W64, refw) < max(1e-4, 5 * self_sens), (rel_err(W64, refw), self_sens)
+    W1 = ops.unpack_fdt_to_dtf(ops.wpe(Ysub, 10, 2, 1))[0].cpu().numpy()
+    assert rel_err(W1, oracle.wpe_dtf(S64, 10, 2, 1)) < 1e-6
+    # dereverberation actually happened
+    assert np.mean(np.abs(W64) ** 2) < 0.9 * np.mean(np.abs(S64) ** 2)
+    act = oracle.activity_time_to_frequency(sact, 1024, 256, True)
+    post = ops.cacgmm(Yw, torch.from_numpy(act.astype(np.uint8))[None].to(dev), 20)
+    m_dev = ops.unpack_fkt_to_ktf(post)[0].cpu().numpy()
+    ref = oracle.gss_posteriors(W64, act, 20)
+    err = np.abs(m_dev - ref)
+    assert np.quantile(err, 0.999) < 1e-4 and err.max() < 2e-3, (np.quantile(err, 0.999), err.max())
+    tm = m_dev[0].astype(np.float64); dm = m_dev[1:].sum(0).astype(np.float64)
+    X = ops.beamform(Yw, post[:, :, 0].contiguous(), post[:, :, 1:].sum(dim=2))
+    refX = oracle.beamform(W64, tm, dm)
+    assert rel_err(ops.unpack_ft_to_tf(X)[0].cpu().numpy(), refX) < 1e-4
