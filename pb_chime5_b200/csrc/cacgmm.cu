@@ -352,22 +352,57 @@ __global__ void __launch_bounds__(NT, MINB) cacgmm_em_kernel(const CacgmmParams 
             }
             __syncthreads();
             // ---- flush: reduce over the M-phase groups in fixed order (deterministic) ----
-            for (int g = 0; g < C::NG; ++g) {
-                if (m_active && m_g == g) {
+            if constexpr (C::NG <= 4) {
+                for (int g = 0; g < C::NG; ++g) {
+                    if (m_active && m_g == g) {
 #pragma unroll
-                    for (int a = 0; a < 4; ++a) {
-                        const int d = r0 + (a >> 1), e = c0 + (a & 1);
-                        if (e <= d) {
+                        for (int a = 0; a < 4; ++a) {
+                            const int d = r0 + (a >> 1), e = c0 + (a & 1);
+                            if (e <= d) {
 #pragma unroll
-                            for (int k = 0; k < K; ++k) {
-                                cd* dst = &acc_sm[k * C::NP + tri(d, e)];
-                                if (g == 0 && s0 == 0) *dst = macc[a][k];
-                                else { cd v = *dst; v.x += macc[a][k].x; v.y += macc[a][k].y; *dst = v; }
+                                for (int k = 0; k < K; ++k) {
+                                    cd* dst = &acc_sm[k * C::NP + tri(d, e)];
+                                    if (g == 0 && s0 == 0) *dst = macc[a][k];
+                                    else { cd v = *dst; v.x += macc[a][k].x; v.y += macc[a][k].y; *dst = v; }
+                                }
                             }
                         }
                     }
+                    __syncthreads();
                 }
-                __syncthreads();
+            } else {
+                // many small groups (few channels): dump the partial blocks of a chunk of groups into a
+                // shared slab (the frame tiles are dead here) and let one thread sum each entry.
+                constexpr int ENT = 4 * K;                        // entries per lane
+                constexpr int PER_GROUP = C::G * ENT;             // entries per group
+                constexpr int CHUNK = (int)(C::YS_BYTES / (PER_GROUP * sizeof(cd)));
+                static_assert(CHUNK >= 1, "slab too small");
+                cd* slab = reinterpret_cast<cd*>(ys_raw);
+                for (int g0 = 0; g0 < C::NG; g0 += CHUNK) {
+                    const int cnt = min(CHUNK, C::NG - g0);
+                    if (m_active && m_g >= g0 && m_g < g0 + cnt) {
+                        cd* dst = slab + (size_t)(m_g - g0) * PER_GROUP + m_l * ENT;
+#pragma unroll
+                        for (int a = 0; a < 4; ++a)
+#pragma unroll
+                            for (int k = 0; k < K; ++k) dst[a * K + k] = macc[a][k];
+                    }
+                    __syncthreads();
+                    for (int e = tid; e < PER_GROUP; e += NT) {
+                        const int l = e / ENT, ak = e - l * ENT, a = ak / K, k = ak - a * K;
+                        int lb = 0;
+                        while ((lb + 1) * (lb + 2) / 2 <= l) ++lb;
+                        const int d = 2 * lb + (a >> 1), ee = 2 * (l - lb * (lb + 1) / 2) + (a & 1);
+                        if (ee <= d) {
+                            cd sum = cmake(0.0, 0.0);
+                            for (int g = 0; g < cnt; ++g) { const cd v = slab[(size_t)g * PER_GROUP + e]; sum.x += v.x; sum.y += v.y; }
+                            cd* dst = &acc_sm[k * C::NP + tri(d, ee)];
+                            if (g0 == 0 && s0 == 0) *dst = sum;
+                            else { cd v = *dst; v.x += sum.x; v.y += sum.y; *dst = v; }
+                        }
+                    }
+                    __syncthreads();
+                }
             }
         }
         if (is_final) {
