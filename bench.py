@@ -31,10 +31,24 @@ import numpy as np
 ROOT = Path(__file__).resolve().parent
 sys.path.insert(0, str(ROOT))
 
-CFG = dict(D=24, T=941, F=513, K=5, taps=10, delay=2, wpe_iterations=3, em_iterations=100,
-           bf='mvdrSouden_ban', ctx_frames=3)
-WORKLOAD = ('cfg2: 15 s utterances, 6 arrays x 4 mics (D=24), T=941 frames, F=513 bins, K=5 classes, '
-            'WPE taps=10 delay=2 it=3 + CACGMM 100 EM it + MVDR-Souden+BAN')
+WORKLOADS = {
+    # BASELINE.json configs[1] -- the configuration the metric is quoted on (default)
+    'cfg2': (dict(D=24, T=941, F=513, K=5, taps=10, delay=2, wpe_iterations=3, em_iterations=100,
+                  bf='mvdrSouden_ban', ctx_frames=3),
+             'cfg2: 15 s utterances, 6 arrays x 4 mics (D=24), T=941 frames, F=513 bins, K=5 classes, '
+             'WPE taps=10 delay=2 it=3 + CACGMM 100 EM it + MVDR-Souden+BAN'),
+    # configs[0] -- the reference's own CPU-runnable case (1 array, WPE off, 20 EM iterations)
+    'cfg1': (dict(D=4, T=941, F=513, K=3, taps=0, delay=0, wpe_iterations=0, em_iterations=20,
+                  bf='mvdrSouden_ban', ctx_frames=3),
+             'cfg1: 15 s utterances, 1 array x 4 mics (D=4), T=941, F=513, K=3, WPE off, '
+             'CACGMM 20 EM it + MVDR-Souden+BAN'),
+    # configs[4] -- stress shape
+    'cfg5': (dict(D=24, T=3753, F=513, K=6, taps=20, delay=2, wpe_iterations=3, em_iterations=200,
+                  bf='mvdrSouden_ban', ctx_frames=3),
+             'cfg5: 60 s utterances, D=24, T=3753, F=513, K=6 (5 speakers + noise), WPE taps=20 it=3 + '
+             'CACGMM 200 EM it + MVDR-Souden+BAN'),
+}
+CFG, WORKLOAD = WORKLOADS['cfg2']
 METRIC = 'utterances/sec (15 s, 24-ch, 513-bin STFT)'
 
 
@@ -52,7 +66,8 @@ def _cpu_worker(args):
     Obs = Obs.astype(np.complex128)
     t0 = time.perf_counter()
     oracle.enhance_stft(Obs, act, 0,
-                        wpe=dict(taps=c['taps'], delay=c['delay'], iterations=c['wpe_iterations'], psd_context=0),
+                        wpe=(dict(taps=c['taps'], delay=c['delay'], iterations=c['wpe_iterations'], psd_context=0)
+                             if c['taps'] else None),
                         gss_iterations=c['em_iterations'], bf=c['bf'],
                         start_context_frames=c['ctx_frames'], end_context_frames=c['ctx_frames'],
                         loop_over_bins=True)
@@ -187,7 +202,8 @@ def run_gpu(args):
     dev = torch.device('cuda', local)
     c = CFG
     B = args.batch
-    enh = core.get_enhancer(wpe=True, wpe_tabs=c['taps'], wpe_delay=c['delay'], wpe_iterations=c['wpe_iterations'],
+    enh = core.get_enhancer(wpe=bool(c['taps']), wpe_tabs=max(c['taps'], 1), wpe_delay=c['delay'],
+                            wpe_iterations=c['wpe_iterations'],
                             bss_iterations=c['em_iterations'], bf=c['bf'])
 
     # two distinct host batches (pinned), alternated between steps; each is B*93 MB >> L2
@@ -286,7 +302,7 @@ def run_gpu(args):
         'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f64',
         'data': 'synthetic',
         'config': {'workload': WORKLOAD, 'batch_per_gpu': B,
-                   'l2': f'inputs {B * 93} MB per step per GPU > 126 MB L2, two input sets alternated',
+                   'l2': f"inputs {B * c['D'] * c['T'] * c['F'] * 8 // 1000000} MB per step per GPU vs 126 MB L2, two input sets alternated",
                    'value_region': 'inputs resident in HBM in the reference layout (B,D,T,F); timed: pack, WPE, EM, beamformer, unpack',
                    'arithmetic': 'complex64 storage, float64 arithmetic'},
         'e2e': {'value': e2e_value, 'unit': 'utterances/s', 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h,
@@ -304,7 +320,7 @@ def run_gpu(args):
                               'peak_tflops_measured': 35.7,
                               'peak_source': 'tools/fp64_probe.cu on this pool (DFMA 35.7, FP64 MMA 37.2 TFLOP/s)',
                               'pipe_active_ncu': 0.48},
-                     'note': 'declared variant: per-iteration covariance+E-step streams x 100 iterations (SURVEY 8d); '
+                     'note': 'declared variant: per-iteration covariance+E-step streams x EM iterations (SURVEY 8d); '
                              'the kernel is FP64-pipe bound at D=24, see DESIGN.md'},
         'clocks': clocks,
     }
@@ -329,10 +345,16 @@ def main():
     ap.add_argument('--steps', type=int, default=4)
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
-    ap.add_argument('--batch', type=int, default=4, help='utterances per GPU per step')
+    ap.add_argument('--batch', type=int, default=0, help='utterances per GPU per step (0: 4 for cfg2, 32 for cfg1, 1 for cfg5)')
     ap.add_argument('--cpu-bins', type=int, default=0, help='frequency bins per process in a CPU sample (0 = 8 for the cpu_baseline of the GPU arm, 4 per step for --impl reference)')
     ap.add_argument('--no-cpu', action='store_true')
+    ap.add_argument('--workload', default='cfg2', choices=sorted(WORKLOADS),
+                    help='cfg2 = the metric configuration (default); cfg1 / cfg5 are side measurements')
     args = ap.parse_args()
+    global CFG, WORKLOAD
+    CFG, WORKLOAD = WORKLOADS[args.workload]
+    if args.batch <= 0:
+        args.batch = {'cfg2': 4, 'cfg1': 32, 'cfg5': 1}[args.workload]
     if args.impl == 'reference':
         run_reference(args)
     else:
