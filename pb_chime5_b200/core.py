@@ -194,11 +194,18 @@ class GSS:
             # the reference passes an unsupported keyword to CACGMM.predict here (core.py:198-202)
             raise TypeError("predict() got an unexpected keyword argument 'source_activity_mask'")
         Y = ops.pack_dtf_to_fdt(x[None])
-        post = self._run(Y, act[None])
+        if debug:
+            # the reference keeps the fitted models (`learned`, core.py:204-212); here: mixture
+            # weights (F,K), class covariances scaled to unit trace (F,K,D,D) and the log
+            # determinants the last E-step used (F,K), as host arrays
+            post, model = ops.cacgmm(Y, act[None], self.iterations, self.iterations_post, return_model=True)
+        else:
+            post = self._run(Y, act[None])
         out = ops.unpack_fkt_to_ktf(post)[0]                              # (K,T,F)
         out = _from_device(out, was_np, np.float64)
         if debug:
-            self.locals = dict(Obs=Obs, acitivity_freq=acitivity_freq, posterior=out)
+            learned = {k: v[0].cpu().numpy() for k, v in model.items()}
+            self.locals = dict(Obs=Obs, acitivity_freq=acitivity_freq, posterior=out, learned=learned)
         return out
 
 

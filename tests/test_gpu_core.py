@@ -346,3 +346,22 @@ def test_reverberant_speech_like_stagewise():
     X = ops.beamform(Yw, post[:, :, 0].contiguous(), post[:, :, 1:].sum(dim=2))
     refX = oracle.beamform(W64, tm, dm)
     assert rel_err(ops.unpack_ft_to_tf(X)[0].cpu().numpy(), refX) < 1e-4
+
+
+def test_gss_debug_keeps_the_model(golden_dir):
+    """debug=True stores the fitted model like the reference's `learned` (core.py:204-212):
+    the covariance must reproduce the reference's class covariances up to the scale that the
+    model is invariant to (reference: largest eigenvalue 1; here: unit trace)."""
+    g = np.load(golden_dir / 'gss_d4_k3.npz')
+    Obs = g['Obs'].astype(np.complex128)
+    gss = core.GSS(iterations=int(g['iterations']), iterations_post=1, verbose=False)
+    post = gss(Obs, g['activity'], debug=True)
+    learned = gss.locals['learned']
+    _, models = oracle.gss_posteriors(Obs, g['activity'], int(g['iterations']), return_models=True)
+    weight, eigvec, eigval = models
+    cov_ref = np.einsum('...wx,...x,...zx->...wz', eigvec, eigval, eigvec.conj())
+    cov_ref = cov_ref / np.trace(cov_ref, axis1=-1, axis2=-2).real[..., None, None]
+    assert learned['covariance'].shape == cov_ref.shape
+    assert np.abs(learned['covariance'] - cov_ref).max() < 1e-6
+    assert np.abs(learned['weight'] - weight[..., 0]).max() < 1e-6
+    assert np.abs(post - g['posterior']).max() < 1e-4
