@@ -375,6 +375,75 @@ class Enhancer:
         torch.cuda.current_stream().synchronize()
         return res
 
+    def enhance_stft_host_stream(self, batches, return_masks=True):
+        """Pipelined variant of `enhance_stft_host` for a sequence of batches: yields one result
+        dict per input batch, in order.  `batches` yields tuples
+        (Obs (B,D,T,F) complex64 pinned host tensor, acitivity_freq (B,K,T_act), target_index,
+        start_ctx, end_ctx).  The host->device copy of batch i+1 and the device->host copy of
+        batch i-1 run on side streams while batch i is computed (two input slots in HBM, results
+        land in fresh pinned buffers); every batch is still copied in and out in full."""
+        dev = _device()
+        compute = torch.cuda.current_stream()
+        h2d, d2h = torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev)
+
+        def upload(item):
+            Obs, act, ti, sc, ec = item
+            obs_h = Obs if isinstance(Obs, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(Obs))
+            assert obs_h.dtype == torch.complex64 and obs_h.ndim == 4, (obs_h.dtype, obs_h.shape)
+            ivec = lambda v: None if v is None else torch.as_tensor(v, dtype=torch.int32).to(dev, non_blocking=True)
+            with torch.cuda.stream(h2d):
+                x = obs_h.to(dev, non_blocking=True)
+                a = torch.as_tensor(act).to(torch.uint8).to(dev, non_blocking=True)
+                vecs = (ivec(ti), ivec(sc), ivec(ec))
+                ready = torch.cuda.Event()
+                ready.record(h2d)
+            return x, a, vecs, ready
+
+        def download(X_tf, m_ktf, done):
+            with torch.cuda.stream(d2h):
+                d2h.wait_event(done)
+                res = {'X_hat': torch.empty(X_tf.shape, dtype=X_tf.dtype, pin_memory=True)}
+                res['X_hat'].copy_(X_tf, non_blocking=True)
+                if m_ktf is not None:
+                    res['masks'] = torch.empty(m_ktf.shape, dtype=m_ktf.dtype, pin_memory=True)
+                    res['masks'].copy_(m_ktf, non_blocking=True)
+                fin = torch.cuda.Event()
+                fin.record(d2h)
+            return res, fin, (X_tf, m_ktf)        # keep the device tensors alive until the copy is done
+
+        it = iter(batches)
+        try:
+            nxt = upload(next(it))
+        except StopIteration:
+            return
+        pending = None
+        while nxt is not None:
+            x, a, (ti, sc, ec), ready = nxt
+            try:
+                nxt = upload(next(it))                    # overlaps with the kernels issued below
+            except StopIteration:
+                nxt = None
+            compute.wait_event(ready)
+            for t in (x, a, ti, sc, ec):
+                if t is not None:
+                    t.record_stream(compute)
+            Y = ops.pack_dtf_to_fdt(x)
+            X, post = self.enhance_stft_batch(Y, a, ti, sc, ec, return_masks=True)
+            X_tf = ops.unpack_ft_to_tf(X)
+            m_ktf = ops.unpack_fkt_to_ktf(post) if return_masks else None
+            done = torch.cuda.Event()
+            done.record(compute)
+            X_tf.record_stream(d2h)
+            if m_ktf is not None:
+                m_ktf.record_stream(d2h)
+            cur = download(X_tf, m_ktf, done)
+            if pending is not None:
+                pending[1].synchronize()
+                yield pending[0]
+            pending = cur
+        pending[1].synchronize()
+        yield pending[0]
+
     def enhance_observation(self, obs, ex_array_activity, speaker_id, ex=None, debug=False):
         """obs (D, N) samples, ex_array_activity {speaker: (N,) bool} -> x_hat (N',).
         core.py:514-571."""

@@ -365,3 +365,17 @@ def test_gss_debug_keeps_the_model(golden_dir):
     assert np.abs(learned['covariance'] - cov_ref).max() < 1e-6
     assert np.abs(learned['weight'] - weight[..., 0]).max() < 1e-6
     assert np.abs(post - g['posterior']).max() < 1e-4
+
+
+def test_pipelined_host_stream_equals_synchronous_calls():
+    enh = core.get_enhancer(wpe_tabs=3, wpe_iterations=2, bss_iterations=4)
+    items = []
+    for i in range(3):
+        obs, act = synth.make_batch(1200 + 10 * i, 2, D=4, T=100, F=6, K=3)
+        items.append((torch.from_numpy(obs).pin_memory(), act, [0, 1], [3, 3], [3, 3]))
+    ref = [enh.enhance_stft_host(*it) for it in items]
+    got = list(enh.enhance_stft_host_stream(iter(items)))
+    assert len(got) == 3
+    for r, g in zip(ref, got):
+        assert torch.equal(r['X_hat'], g['X_hat']) and torch.equal(r['masks'], g['masks'])
+    assert list(enh.enhance_stft_host_stream(iter([]))) == []
