@@ -379,3 +379,30 @@ def test_pipelined_host_stream_equals_synchronous_calls():
     for r, g in zip(ref, got):
         assert torch.equal(r['X_hat'], g['X_hat']) and torch.equal(r['masks'], g['masks'])
     assert list(enh.enhance_stft_host_stream(iter([]))) == []
+
+
+@pytest.mark.parametrize('D,K,T,F', [(2, 2, 2, 1), (4, 3, 31, 2), (4, 3, 256, 2), (4, 3, 257, 3), (8, 4, 129, 2),
+                                      (24, 6, 65, 1), (24, 2, 513, 1), (3, 5, 64, 4)])
+def test_shape_boundaries(D, K, T, F):
+    """Tile / super-tile boundaries, tiny and odd shapes, all three blocks against the oracle."""
+    Obs, act = synth.make_utterance(4000 + D + T, D=D, T=T, F=F, K=K)
+    for k in range(K - 1):                    # distinct activity patterns (short T makes everybody active,
+        act[k, k::K] = False                  # which leaves the reference-channel SNRs exactly tied)
+    if T > 8:
+        Obs[:, 2:, :] += 0.4 * Obs[:, :-2, :]
+    O = Obs.astype(np.complex128)
+    got, ref = _gss_both(Obs, act, 5)
+    assert np.isfinite(got).all() and np.abs(got - ref).max() < 1e-4
+    taps = 3
+    refw = oracle.wpe_dtf(O, taps, 1, 2)
+    gotw = core.WPE(taps, 1, 2, 0)(O)
+    assert np.isfinite(gotw).all()
+    if T > 4 * taps * D:                      # otherwise the normal equations are singular / ill posed
+        assert rel_err(gotw, refw) < 1e-4
+    tm = ref[0].astype(np.float32); dm = ref[1:].sum(0).astype(np.float32)
+    X = core.Beamformer('mvdrSouden_ban', None)(O, tm, dm)
+    refX = oracle.beamform(O, tm.astype(np.float64), dm.astype(np.float64))
+    if T > 2 * D:
+        assert rel_err(X, refX) < 1e-4
+    else:
+        assert np.isfinite(X).all()
