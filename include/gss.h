@@ -173,6 +173,20 @@ int gss_stft_f32(const float* x, gss_c64* Y, int B, int D, int N,
 int gss_istft_f32(const gss_c64* X, float* x, int B, int T,
                   int size, int shift, int fading, void* ws, size_t ws_bytes, void* stream);
 
+/* ---- diagnostics (used by tests/ and tools/, not by the product path) -----------
+ * WPE correlation-build selection: gram_mode -1 = default (environment GSS_WPE_GRAM=f64|i8, else
+ * INT8 tensor cores with float64 re-do of ill-conditioned bins), 0 = float64 (DMMA), 1 = INT8
+ * only, 2 = INT8 + re-do; tau < 0 = default threshold of the re-do test. */
+int gss_debug_wpe_config(int gram_mode, double tau);
+/* bins re-done in float64 since the last reset (synchronises the device) */
+int gss_debug_wpe_redo_count(int reset);
+/* one correlation build: Y (B,F,D,T) c64, inv (B,F,T) f64 -> Raug (B,F,taps*D+D,taps*D) c128,
+ * lower trapezoid (rows [0,LD): R, rows [LD,LD+D): P^H); mode 0 = float64, 1 = INT8.
+ * Workspace: gss_workspace_bytes(GSS_OP_WPE, ...). */
+int gss_debug_wpe_gram(const gss_c64* Y, const double* inv, double* Raug, int mode, int variant,
+                       int B, int F, int D, int T, int taps, int delay, const int* T_per_utt,
+                       void* ws, size_t ws_bytes, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

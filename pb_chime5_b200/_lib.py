@@ -53,6 +53,9 @@ _SIGNATURES = {
     'gss_enhance_c64': (_i, [_p] * 8 + [_i] * 15 + [_p, _p, _sz, _p]),
     'gss_stft_f32': (_i, [_p, _p, _i, _i, _i, _i, _i, _i, _p, _sz, _p]),
     'gss_istft_f32': (_i, [_p, _p, _i, _i, _i, _i, _i, _p, _sz, _p]),
+    'gss_debug_wpe_config': (_i, [_i, _d]),
+    'gss_debug_wpe_redo_count': (_i, [_i]),
+    'gss_debug_wpe_gram': (_i, [_p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _i, _p, _p, _sz, _p]),
 }
 
 _lib = None

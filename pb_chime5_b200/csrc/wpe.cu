@@ -15,14 +15,10 @@
 // substitution for free).
 #include "common.cuh"
 #include "smallmat.cuh"
+#include "wpe_i8.cuh"
+#include <cstdlib>
 
 namespace gss {
-
-struct WpeDims { int F, D, T, L, delay, LD; const int* Tper; };   // T: frame stride; Tper: valid frames per utterance or null
-
-__device__ __forceinline__ int wpe_valid_frames(const WpeDims& m, size_t bf) {
-    return m.Tper ? min(max(m.Tper[bf / m.F], 0), m.T) : m.T;
-}
 
 __device__ __forceinline__ cd wpe_row_value(const float2* __restrict__ Yg, const WpeDims& m, int idx, int t, int Tv) {
     // idx < LD : tap row (k, d) ; LD <= idx < LD + D : the unshifted observation
@@ -99,9 +95,10 @@ __device__ __forceinline__ void cp_async8(void* smem_dst, const void* gsrc) {
 constexpr int CT_SLD = 20;     // staging row stride in float2 (40 words = 8 mod 32: conflict-free fragment loads)
 
 __global__ void __launch_bounds__(CT_NT) wpe_corr_kernel(const float2* __restrict__ Y, const double* __restrict__ inv,
-                                                         cd* __restrict__ Raug, WpeDims m) {
+                                                         cd* __restrict__ Raug, WpeDims m, const int* __restrict__ redo) {
     const int rt = blockIdx.y, ct = blockIdx.z;
     if (ct > rt || ct * CT_BM >= m.LD || rt * CT_BM >= m.LD + m.D) return;
+    if (redo != nullptr && redo[blockIdx.x] == 0) return;      // second pass: flagged bins only
     // raw complex64 staging, double buffered: [buf][A|B][row][frame]; weights per frame
     __shared__ __align__(16) float2 st[2][2][CT_BM][CT_SLD];
     __shared__ double wsm[2][CT_BK];
@@ -226,9 +223,11 @@ __device__ inline void warp_tri_inverse_deflated(cd* Dg, int nb, int lane) {
 // One warp per bin: Cholesky of the diagonal block (zero-pivot deflation), L11 written back,
 // its inverse (packed lower) to `Minv` for the panel rows and the back substitution.
 __global__ void __launch_bounds__(32) wpe_diag_kernel(cd* __restrict__ Raug, cd* __restrict__ Minv,
-                                                      int* __restrict__ info, WpeDims m, int j0, int jb) {
+                                                      int* __restrict__ info, WpeDims m, int j0, int jb,
+                                                      const int* __restrict__ redo) {
     __shared__ __align__(16) cd Dg[WS_NB * (WS_NB + 1) / 2];
     const size_t bf = blockIdx.x;
+    if (redo != nullptr && redo[bf] == 0) return;
     const int lane = threadIdx.x;
     const int n = m.LD, nrows = m.LD + m.D;
     const int nb = min(WS_NB, n - j0);
@@ -278,9 +277,10 @@ __global__ void __launch_bounds__(32) wpe_diag_kernel(cd* __restrict__ Raug, cd*
 // panel rows below the diagonal block:  L[r, jblock] = A[r, jblock] * L11^{-H}; one thread per row
 constexpr int PR_NT = 128;
 __global__ void __launch_bounds__(PR_NT) wpe_panel_rows_kernel(cd* __restrict__ Raug, const cd* __restrict__ Minv,
-                                                               WpeDims m, int j0, int jb) {
+                                                               WpeDims m, int j0, int jb, const int* __restrict__ redo) {
     __shared__ __align__(16) cd Dg[WS_NB * (WS_NB + 1) / 2];
     const size_t bf = blockIdx.x;
+    if (redo != nullptr && redo[bf] == 0) return;
     const int tid = threadIdx.x;
     const int n = m.LD, nrows = m.LD + m.D;
     const int nb = min(WS_NB, n - j0);
@@ -313,9 +313,11 @@ __global__ void __launch_bounds__(PR_NT) wpe_panel_rows_kernel(cd* __restrict__ 
 
 // A22 -= L21 L21^H on the trailing matrix (origin j1 = j0 + nb).  Same tiling / MMA
 // mapping as wpe_corr_kernel; the k dimension is the nb <= 24 columns of the panel.
-__global__ void __launch_bounds__(CT_NT) wpe_trail_kernel(cd* __restrict__ Raug, WpeDims m, int j0) {
+__global__ void __launch_bounds__(CT_NT) wpe_trail_kernel(cd* __restrict__ Raug, WpeDims m, int j0,
+                                                          const int* __restrict__ redo) {
     const int rt = blockIdx.y, ct = blockIdx.z;
     if (ct > rt) return;
+    if (redo != nullptr && redo[blockIdx.x] == 0) return;
     const int n = m.LD, nrows = m.LD + m.D;
     const int nb = min(WS_NB, n - j0), j1 = j0 + nb;
     const int i0 = j1 + rt * CT_BM, c0 = j1 + ct * CT_BM;
@@ -387,6 +389,26 @@ __global__ void __launch_bounds__(CT_NT) wpe_trail_kernel(cd* __restrict__ Raug,
                 A[(size_t)i * n + j] = v;
             }
     }
+}
+
+// INT8 Gram path, a-posteriori check.  After the Cholesky factorisation L_jj^2 / R_jj is
+// 1 - (squared multiple correlation of row j with the rows before it), a scale-invariant
+// measure of how much of the pivot survived the elimination.  A bin whose smallest ratio is
+// below `tau` (or not finite: dead channels, failures) is flagged and re-done in float64.
+__device__ int g_wpe_redo_total = 0;
+
+__global__ void __launch_bounds__(32) wpe_flag_kernel(const cd* __restrict__ Raug, const double* __restrict__ rdiag,
+                                                      int* __restrict__ flag, WpeDims m, double tau) {
+    const size_t bf = blockIdx.x;
+    const int n = m.LD, lane = threadIdx.x;
+    const cd* A = Raug + bf * (size_t)(m.LD + m.D) * n;
+    bool bad = false;
+    for (int j = lane; j < n; j += 32) {
+        const double l = A[(size_t)j * n + j].x, r = rdiag[bf * (size_t)n + j];
+        if (!(l * l >= tau * r) || !(r > 0.0) || !isfinite(l)) bad = true;
+    }
+    bad = __any_sync(0xffffffffu, bad);
+    if (lane == 0) { flag[bf] = bad ? 1 : 0; if (bad) atomicAdd(&g_wpe_redo_total, 1); }
 }
 
 // Blocked right-looking back substitution  L^H G = Z  (Z^H sits in rows [n, n + D) of Raug).
@@ -556,9 +578,10 @@ __global__ void __launch_bounds__(AP_NT) wpe_apply_kernel(const float2* __restri
         }
 }
 
-struct WpeWs { double* power; double* inv; cd* Raug; cd* G; cd* Minv; size_t bytes; };
+struct WpeWs { double* power; double* inv; cd* Raug; cd* G; cd* Minv; double* rdiag; int* flag; WpeI8Ws i8; bool has_i8; size_t bytes; };
 
-static WpeWs wpe_ws_layout(void* ws, int Bc, int F, int D, int T, int LD) {
+static WpeWs wpe_ws_layout(void* ws, int Bc, int F, int D, int T, int L) {
+    const int LD = L * D;
     Arena a(ws, ~size_t(0));
     WpeWs w;
     w.power = a.take<double>((size_t)Bc * F * T);
@@ -566,11 +589,65 @@ static WpeWs wpe_ws_layout(void* ws, int Bc, int F, int D, int T, int LD) {
     w.Raug = a.take<cd>((size_t)Bc * F * (LD + D) * LD);
     w.G = a.take<cd>((size_t)Bc * F * LD * D);
     w.Minv = a.take<cd>((size_t)Bc * F * ((LD + WS_NB - 1) / WS_NB) * (WS_NB * (WS_NB + 1) / 2));
+    w.has_i8 = wpe_i8_applicable(D, T, L);
+    w.rdiag = nullptr; w.flag = nullptr;
+    if (w.has_i8) {
+        w.rdiag = a.take<double>((size_t)Bc * F * LD);
+        w.flag = a.take<int>((size_t)Bc * F);
+        const size_t used = wpe_i8_ws_layout(ws ? (char*)ws + a.off : nullptr, F, D, T, L, &w.i8);
+        a.off += align_up(used);
+    }
     w.bytes = a.off;
     return w;
 }
 
-size_t wpe_ws_bytes(int Bc, int F, int D, int T, int L) { return wpe_ws_layout(nullptr, Bc, F, D, T, L * D).bytes; }
+size_t wpe_ws_bytes(int Bc, int F, int D, int T, int L) { return wpe_ws_layout(nullptr, Bc, F, D, T, L).bytes; }
+
+// Gram path selection: GSS_WPE_GRAM=f64 forces the FP64 tensor-core (DMMA) build, =i8 the INT8
+// build without the float64 re-do; default: INT8 where built, flagged bins re-done in float64.
+static int g_gram_mode_override = -1;
+static double g_tau_override = -1.0;
+static int wpe_gram_mode() {
+    if (g_gram_mode_override >= 0) return g_gram_mode_override;
+    static int mode = -1;
+    if (mode < 0) {
+        const char* e = getenv("GSS_WPE_GRAM");
+        mode = (e && e[0] == 'f') ? 0 : (e && e[0] == 'i') ? 1 : 2;
+    }
+    return mode;
+}
+static double wpe_i8_tau() {
+    if (g_tau_override >= 0.0) return g_tau_override;
+    static double tau = -1.0;
+    if (tau < 0.0) { const char* e = getenv("GSS_WPE_I8_TAU"); tau = e ? atof(e) : 1e-3; if (!(tau >= 0.0)) tau = 1e-3; }
+    return tau;
+}
+
+// blocked Cholesky of Raug with the P^H rows riding along (all bins, or the flagged ones)
+static int wpe_factor(const WpeWs& w, const WpeDims& m, int BF, int* infoc, const int* redo, cudaStream_t st) {
+    const int LD = m.LD, D = m.D;
+    for (int j0 = 0, jb = 0; j0 < LD; j0 += WS_NB, ++jb) {
+        wpe_diag_kernel<<<BF, 32, 0, st>>>(w.Raug, w.Minv, infoc, m, j0, jb, redo);
+        GSS_LAUNCH_CHECK("wpe_diag_kernel");
+        const int j1 = std::min(j0 + WS_NB, LD);
+        dim3 pg(BF, (LD + D - j1 + PR_NT - 1) / PR_NT);
+        wpe_panel_rows_kernel<<<pg, PR_NT, 0, st>>>(w.Raug, w.Minv, m, j0, jb, redo);
+        GSS_LAUNCH_CHECK("wpe_panel_rows_kernel");
+        if (j1 < LD) {
+            dim3 tg(BF, (LD + D - j1 + CT_BM - 1) / CT_BM, (LD - j1 + CT_BM - 1) / CT_BM);
+            wpe_trail_kernel<<<tg, CT_NT, 0, st>>>(w.Raug, m, j0, redo);
+            GSS_LAUNCH_CHECK("wpe_trail_kernel");
+        }
+    }
+    return GSS_OK;
+}
+
+static int wpe_corr_f64(const float2* Yc, const WpeWs& w, const WpeDims& m, int BF, const int* redo, cudaStream_t st) {
+    dim3 grid(BF, (m.LD + m.D + CT_BM - 1) / CT_BM, (m.LD + CT_BM - 1) / CT_BM);
+    wpe_corr_kernel<<<grid, CT_NT, 0, st>>>(Yc, w.inv, w.Raug, m, redo);
+    GSS_LAUNCH_CHECK("wpe_corr_kernel");
+    return GSS_OK;
+}
 
 template <int DMAX>
 static int launch_backsub(const cd* Raug, const cd* Minv, cd* G, const WpeDims& m, int BF, size_t smem, cudaStream_t st) {
@@ -623,26 +700,27 @@ extern "C" int gss_wpe_c64(const gss_c64* Y, gss_c64* X, int taps, int delay, in
         const float2* Yc = (const float2*)Y + (size_t)b0 * F * D * T;
         float2* Xc = (float2*)X + (size_t)b0 * F * D * T;
         int* infoc = info ? info + b0 : nullptr;
-        WpeWs w = wpe_ws_layout(ws, bn, F, D, T, LD);
+        WpeWs w = wpe_ws_layout(ws, bn, F, D, T, taps);
+        const int gram_mode = w.has_i8 ? wpe_gram_mode() : 0;
         wpe_power_kernel<<<BF, 256, 0, st>>>(Yc, w.power, m);
         GSS_LAUNCH_CHECK("wpe_power_kernel");
         for (int it = 0; it < iterations; ++it) {
             wpe_invpower_kernel<<<BF, 256, 0, st>>>(w.power, w.inv, m, psd_context);
             GSS_LAUNCH_CHECK("wpe_invpower_kernel");
-            dim3 grid(BF, (LD + D + CT_BM - 1) / CT_BM, (LD + CT_BM - 1) / CT_BM);
-            wpe_corr_kernel<<<grid, CT_NT, 0, st>>>(Yc, w.inv, w.Raug, m);
-            GSS_LAUNCH_CHECK("wpe_corr_kernel");
-            for (int j0 = 0, jb = 0; j0 < LD; j0 += WS_NB, ++jb) {
-                wpe_diag_kernel<<<BF, 32, 0, st>>>(w.Raug, w.Minv, infoc, m, j0, jb);
-                GSS_LAUNCH_CHECK("wpe_diag_kernel");
-                const int j1 = std::min(j0 + WS_NB, LD);
-                dim3 pg(BF, (LD + D - j1 + PR_NT - 1) / PR_NT);
-                wpe_panel_rows_kernel<<<pg, PR_NT, 0, st>>>(w.Raug, w.Minv, m, j0, jb);
-                GSS_LAUNCH_CHECK("wpe_panel_rows_kernel");
-                if (j1 < LD) {
-                    dim3 tg(BF, (LD + D - j1 + CT_BM - 1) / CT_BM, (LD - j1 + CT_BM - 1) / CT_BM);
-                    wpe_trail_kernel<<<tg, CT_NT, 0, st>>>(w.Raug, m, j0);
-                    GSS_LAUNCH_CHECK("wpe_trail_kernel");
+            int rcf;
+            if (gram_mode == 0) {
+                if ((rcf = wpe_corr_f64(Yc, w, m, BF, nullptr, st))) return rcf;
+                if ((rcf = wpe_factor(w, m, BF, infoc, nullptr, st))) return rcf;
+            } else {
+                // INT8 tensor-core Gram matrix; ill-conditioned bins are flagged after the
+                // factorisation and re-done (Gram + factorisation) in float64
+                if ((rcf = wpe_gram_i8_run(Yc, w.inv, w.Raug, w.rdiag, m, BF, w.i8, 0, st))) return rcf;
+                if ((rcf = wpe_factor(w, m, BF, gram_mode == 2 ? nullptr : infoc, nullptr, st))) return rcf;
+                if (gram_mode == 2) {
+                    wpe_flag_kernel<<<BF, 32, 0, st>>>(w.Raug, w.rdiag, w.flag, m, wpe_i8_tau());
+                    GSS_LAUNCH_CHECK("wpe_flag_kernel");
+                    if ((rcf = wpe_corr_f64(Yc, w, m, BF, w.flag, st))) return rcf;
+                    if ((rcf = wpe_factor(w, m, BF, infoc, w.flag, st))) return rcf;
                 }
             }
             {
@@ -663,4 +741,40 @@ extern "C" int gss_wpe_c64(const gss_c64* Y, gss_c64* X, int taps, int delay, in
         }
     }
     return GSS_OK;
+}
+
+// ---- diagnostics (tests, tools/) ---------------------------------------------------------
+extern "C" int gss_debug_wpe_config(int gram_mode, double tau) {
+    gss::g_gram_mode_override = gram_mode;      // -1: environment / default, 0: f64, 1: i8 only, 2: i8 + f64 re-do
+    gss::g_tau_override = tau;                  // < 0: environment / default
+    return GSS_OK;
+}
+
+extern "C" int gss_debug_wpe_redo_count(int reset) {
+    int v = 0;
+    if (cudaMemcpyFromSymbol(&v, gss::g_wpe_redo_total, sizeof(int)) != cudaSuccess) return -1;
+    if (reset) { const int z = 0; cudaMemcpyToSymbol(gss::g_wpe_redo_total, &z, sizeof(int)); }
+    return v;
+}
+
+extern "C" int gss_debug_wpe_gram(const gss_c64* Y, const double* inv, double* Raug, int mode, int variant,
+                                  int B, int F, int D, int T, int taps, int delay, const int* T_per_utt,
+                                  void* ws, size_t ws_bytes, void* stream) {
+    using namespace gss;
+    GSS_REQUIRE(Y && inv && Raug, GSS_ERR_ARG, "gss_debug_wpe_gram: null pointer");
+    GSS_REQUIRE(B > 0 && F > 0 && D > 0 && T > 0 && taps > 0 && delay >= 0, GSS_ERR_ARG, "gss_debug_wpe_gram: bad dims");
+    cudaStream_t st = (cudaStream_t)stream;
+    WpeDims m{F, D, T, taps, delay, taps * D, T_per_utt};
+    const int BF = B * F;
+    if (mode == 0) {
+        WpeWs w{};
+        w.inv = const_cast<double*>(inv);
+        w.Raug = reinterpret_cast<cd*>(Raug);
+        return wpe_corr_f64((const float2*)Y, w, m, BF, nullptr, st);
+    }
+    GSS_REQUIRE(wpe_i8_applicable(D, T, taps), GSS_ERR_UNSUPPORTED, "gss_debug_wpe_gram: INT8 path not built for D=%d taps=%d T=%d", D, taps, T);
+    WpeI8Ws i8;
+    const size_t need = wpe_i8_ws_layout(ws, F, D, T, taps, &i8);
+    GSS_REQUIRE(ws && ws_bytes >= need, GSS_ERR_WORKSPACE, "gss_debug_wpe_gram: workspace %zu < %zu", ws_bytes, need);
+    return wpe_gram_i8_run((const float2*)Y, inv, reinterpret_cast<cd*>(Raug), nullptr, m, BF, i8, variant, st);
 }

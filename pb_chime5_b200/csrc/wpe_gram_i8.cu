@@ -1,0 +1,455 @@
+// WPE correlation build on the Blackwell INT8 tensor cores (tcgen05.mma kind::i8),
+// exact integer arithmetic ("Ozaki" digit splitting), float64 recombination.
+//
+// What it computes (same contract as wpe_corr_kernel in wpe.cu): the lower trapezoid of
+//   C[i][j] = sum_t inv_t a_i(t) conj(a_j(t)),   a = [Yt ; Y]  (nara_wpe.wpe.wpe_v6:
+//   get_correlations / R = Yt Lambda^-1 Yt^H, P = Yt Lambda^-1 Y^H; call site
+//   pb_chime5/core.py:52-58, algorithm per SURVEY.md appendix A).
+//
+// How.  u_r(t) = a_r(t) sqrt(inv_t) (power-whitened rows: bounded dynamic range), every
+// complex row gets a power-of-two scale 2^e_r so that |u 2^e| < 2^38, the scaled value is
+// rounded ONCE to a 40-bit integer x (one FP64 FMA with a magic constant) and split into
+// five balanced base-256 digits d_p in [-128, 127] (x = sum_p d_p 256^(4-p)).  The real
+// Gram matrix of the 2(LD+D) real rows (re/im interleaved) is then
+//   sum_t x_a x_b = sum_{p,q} 256^(8-p-q) sum_t d_p(a,t) d_q(b,t)
+// where every inner sum is an INT8 x INT8 -> INT32 tensor-core GEMM (exact).  Digit pairs
+// with p + q <= 4 are kept (15 MMAs per k-step, five INT32 accumulators per tile in TMEM,
+// one per order p + q); the dropped pairs are below 2^-38 of the row scales.  The epilogue
+// recombines the five accumulators into one int64 per entry (exact), forms
+// Re = rr + ii and Im = ir - ri between the two lanes of a complex row (exact), converts to
+// float64 once and undoes the row scales.  Measured error vs the float64 Gram matrix:
+// <= 6e-10 sqrt(R_ii R_jj) on adversarial envelopes, ~1e-11 typical (tests/test_gpu_wpe_i8.py);
+// bins whose normal equations are too ill-conditioned for that are re-done by the FP64
+// (DMMA) path, see wpe.cu.
+//
+// Kernels: wpe_i8_scale_kernel (row maxima -> exponents, sqrt(inv)), wpe_i8_slice_kernel
+// (digit planes in the canonical no-swizzle K-major UMMA layout, so tiles are plain 1-D bulk
+// copies), wpe_gram_i8_kernel (TMA producer warp / MMA issuer warp / 4 epilogue warps,
+// 5-stage mbarrier pipeline, TMEM accumulators).
+#include "wpe_i8.cuh"
+#include <algorithm>
+
+namespace gss {
+
+constexpr int GI_NS = 5;                                 // int8 digit planes per value
+constexpr int GI_BM = 128;                               // real rows per tile (UMMA M)
+constexpr int GI_NMAX = 96;                              // real columns per tile: 5 accumulators x 96 <= 512 TMEM columns
+constexpr int GI_STAGES = 5;
+constexpr int GI_NT = 192;                               // warp 0 TMA, warp 1 MMA + TMEM alloc, warps 2..5 epilogue
+constexpr int GI_A_SLICE = 2 * GI_BM * 16;               // one digit plane of the A tile, one k-step (32 frames)
+constexpr int GI_A_STAGE = GI_NS * GI_A_SLICE;           // 20480
+constexpr int GI_B_STAGE = GI_NS * 2 * GI_NMAX * 16;     // 15360
+constexpr int GI_STAGE_BYTES = GI_A_STAGE + GI_B_STAGE;  // 35840
+constexpr int GI_SMEM = GI_STAGES * GI_STAGE_BYTES;      // 179200 (forces one CTA per SM: TMEM is allocated whole)
+constexpr int GI_MAX_ITEMS = 96;
+constexpr int GI_HEADROOM = 37;                          // |x| in [2^37, 2^38) at the row maximum
+
+struct GiItem { short r0, c0, n; };                      // first real row of the A tile, first real column, width
+struct GiPlan { int n_items; GiItem items[GI_MAX_ITEMS]; };
+struct GiDims { int NRc, NRp, KB; };                     // complex rows D + LD, padded real rows, 16-frame blocks (even)
+
+static GiDims gi_dims(int D, int T, int LD) {
+    GiDims g;
+    g.NRc = D + LD;
+    g.NRp = 2 * D + (2 * LD + GI_BM - 1) / GI_BM * GI_BM;
+    g.KB = (T + 31) / 32 * 2;
+    return g;
+}
+__host__ __device__ static inline size_t gi_slice_bytes_per_bin(const GiDims& g) { return (size_t)GI_NS * g.KB * g.NRp * 16; }
+
+bool wpe_i8_applicable(int D, int T, int L) {
+    const int LD = L * D;
+    // the digit sums must fit INT32: 2^14 per product, 5 pairs per order
+    if ((long long)(T + 32) * 5 * 16384 >= 2147483647LL) return false;
+    const int tiles = (2 * LD + GI_BM - 1) / GI_BM;
+    int items = 0;
+    for (int i = 0; i < tiles; ++i) {
+        int C = std::min(2 * D + GI_BM * (i + 1), 2 * D + 2 * LD);
+        C = (C + 15) / 16 * 16;
+        items += (C + GI_NMAX - 1) / GI_NMAX;
+    }
+    return LD >= 48 && items <= GI_MAX_ITEMS;
+}
+
+static int gi_chunk_bins(int F, int D, int T, int L) {
+    const GiDims g = gi_dims(D, T, L * D);
+    const size_t per = gi_slice_bytes_per_bin(g);
+    int n = (int)((size_t)96 << 20) / (int)per;          // keep one chunk of digit planes inside L2 (126 MB)
+    return std::max(1, std::min(n, 64));
+}
+
+size_t wpe_i8_ws_layout(void* p, int F, int D, int T, int L, WpeI8Ws* out) {
+    const GiDims g = gi_dims(D, T, L * D);
+    const int cb = gi_chunk_bins(F, D, T, L);
+    Arena a(p, ~size_t(0));
+    out->slices = a.take<int8_t>((size_t)cb * gi_slice_bytes_per_bin(g));
+    out->mu = a.take<double>((size_t)cb * T);
+    out->ex = a.take<int>((size_t)cb * g.NRc);
+    out->chunk_bins = cb;
+    return a.off;
+}
+
+size_t wpe_i8_ws_bytes(int F, int D, int T, int L) {
+    if (!wpe_i8_applicable(D, T, L)) return 0;
+    WpeI8Ws w;
+    return wpe_i8_ws_layout(nullptr, F, D, T, L, &w);
+}
+
+// ---------------------------------------------------------------------------------------------
+// row exponents and sqrt(inv)
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) wpe_i8_scale_kernel(const float2* __restrict__ Y, const double* __restrict__ inv,
+                                                           double* __restrict__ mu, int* __restrict__ ex,
+                                                           WpeDims m, GiDims g, size_t bf0) {
+    extern __shared__ float mus[];                         // [T]
+    const size_t bf = bf0 + blockIdx.x;
+    const int T = m.T, Tv = wpe_valid_frames(m, bf);
+    const float2* __restrict__ Yg = Y + bf * (size_t)m.D * T;
+    const double* __restrict__ iv = inv + bf * (size_t)T;
+    double* muo = mu + (size_t)blockIdx.x * T;
+    for (int t = threadIdx.x; t < T; t += blockDim.x) {
+        const double v = t < Tv ? sqrt(iv[t]) : 0.0;
+        muo[t] = v;
+        mus[t] = (float)v;
+    }
+    __syncthreads();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    for (int rc = warp; rc < g.NRc; rc += nw) {
+        int d, s;
+        if (rc < m.D) { d = rc; s = 0; }
+        else { const int k = (rc - m.D) / m.D; d = rc - m.D - k * m.D; s = m.delay + k; }
+        float mx = 0.f;
+        for (int t = s + lane; t < Tv; t += 32) {
+            const float2 v = __ldg(&Yg[(size_t)d * T + t - s]);
+            mx = fmaxf(mx, fmaxf(fabsf(v.x), fabsf(v.y)) * mus[t]);
+        }
+        for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+        if (lane == 0) {
+            int e = 0;
+            if (mx > 0.f && isfinite(mx)) e = GI_HEADROOM - ilogbf(mx);
+            ex[(size_t)blockIdx.x * g.NRc + rc] = e;
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// digit planes.  Layout per bin: [plane p][kb = t / 16][real row][t % 16] int8, i.e. the
+// canonical K-major no-swizzle UMMA layout: a core matrix (8 rows x 16 B) is 128 contiguous
+// bytes, 8-row groups are 128 B apart (SBO), the two 16-frame halves of a k-step (rows x 16 B)
+// apart (LBO).  Real row 2 rc = Re, 2 rc + 1 = Im of complex row rc; rows [0, D) = Y (unshifted),
+// rows [D, D + LD) = the taps.  Thread = (kb, complex row): 16 frames, both real rows.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ unsigned gi_pack4(unsigned a, unsigned b, unsigned c, unsigned d, int byte) {
+    const unsigned sel = 0x0040u | (unsigned)byte | ((unsigned)byte << 4);     // [a.byte, b.byte, -, -]
+    const unsigned ab = __byte_perm(a, b, sel), cdv = __byte_perm(c, d, sel);
+    return __byte_perm(ab, cdv, 0x5410) ^ 0x80808080u;     // offset-binary digit -> two's complement
+}
+
+__global__ void __launch_bounds__(256) wpe_i8_slice_kernel(const float2* __restrict__ Y, const double* __restrict__ mu,
+                                                           const int* __restrict__ ex, int8_t* __restrict__ slices,
+                                                           WpeDims m, GiDims g, size_t bf0) {
+    const int half = g.NRp >> 1;
+    const int idx = blockIdx.x * 256 + threadIdx.x;
+    if (idx >= half * g.KB) return;
+    const int kb = idx / half, rc = idx - kb * half;
+    const size_t bl = blockIdx.y, bf = bf0 + bl;
+    const int T = m.T, Tv = wpe_valid_frames(m, bf);
+    int8_t* out = slices + bl * gi_slice_bytes_per_bin(g);
+    unsigned lo_re[16], hi_re[16], lo_im[16], hi_im[16];
+    bool live = rc < g.NRc;
+    int d = 0, s = 0;
+    if (live) {
+        if (rc < m.D) { d = rc; s = 0; }
+        else { const int k = (rc - m.D) / m.D; d = rc - m.D - k * m.D; s = m.delay + k; }
+    }
+    if (live) {
+        const float2* __restrict__ Yg = Y + bf * (size_t)m.D * T + (size_t)d * T;
+        const double* __restrict__ mub = mu + bl * (size_t)T;
+        const int e = ex[bl * g.NRc + rc];
+        const double sc = __longlong_as_double((long long)(1023 + e) << 52);
+        // 1.5 * 2^52 + 0x8080808080: the low 40 mantissa bits of fma(y, w, magic) are x + bias
+        const double magic = 6755399441055744.0 + 551911719040.0;
+#pragma unroll
+        for (int tt = 0; tt < 16; ++tt) {
+            const int t = kb * 16 + tt, ts = t - s;
+            float2 v = make_float2(0.f, 0.f);
+            double w = 0.0;
+            if (t < Tv && ts >= 0) { v = __ldg(&Yg[ts]); w = mub[t] * sc; }
+            const double zr = fma((double)v.x, w, magic), zi = fma((double)v.y, w, magic);
+            lo_re[tt] = (unsigned)__double2loint(zr); hi_re[tt] = (unsigned)__double2hiint(zr);
+            lo_im[tt] = (unsigned)__double2loint(zi); hi_im[tt] = (unsigned)__double2hiint(zi);
+        }
+    }
+#pragma unroll
+    for (int p = 0; p < GI_NS; ++p) {
+        // plane p = digit of weight 256^(4-p): byte 4-p of the 40-bit value (byte 4 = low byte of the high word)
+        uint4 re4 = make_uint4(0u, 0u, 0u, 0u), im4 = make_uint4(0u, 0u, 0u, 0u);
+        if (live) {
+            unsigned wr[4], wi[4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                if (p == 0) {
+                    wr[q] = gi_pack4(hi_re[4 * q], hi_re[4 * q + 1], hi_re[4 * q + 2], hi_re[4 * q + 3], 0);
+                    wi[q] = gi_pack4(hi_im[4 * q], hi_im[4 * q + 1], hi_im[4 * q + 2], hi_im[4 * q + 3], 0);
+                } else {
+                    wr[q] = gi_pack4(lo_re[4 * q], lo_re[4 * q + 1], lo_re[4 * q + 2], lo_re[4 * q + 3], 4 - p);
+                    wi[q] = gi_pack4(lo_im[4 * q], lo_im[4 * q + 1], lo_im[4 * q + 2], lo_im[4 * q + 3], 4 - p);
+                }
+            }
+            re4 = make_uint4(wr[0], wr[1], wr[2], wr[3]);
+            im4 = make_uint4(wi[0], wi[1], wi[2], wi[3]);
+        }
+        uint4* dst = reinterpret_cast<uint4*>(out + (((size_t)p * g.KB + kb) * g.NRp + 2 * rc) * 16);
+        dst[0] = re4;
+        dst[1] = im4;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// PTX wrappers (sm_100a)
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    uint32_t done = 0;
+    for (unsigned spin = 0; !done; ++spin) {
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+        if (spin > (1u << 26)) __trap();                  // a lost arrival must not hang the GPU
+    }
+}
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+// D[tmem] (+)= A[smem] B[smem]^T, INT8 x INT8 -> INT32, M = 128, K = 32
+__device__ __forceinline__ void tc_mma_i8(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                 "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n\t}"
+                 ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void tc_ld16(uint32_t taddr, int (&v)[16]) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+                   "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+                 : "r"(taddr) : "memory");
+}
+__device__ __forceinline__ void tc_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// shared-memory matrix descriptor, K-major, no swizzle (cute::UMMA::SmemDescriptor, mma_sm100_desc.hpp):
+// start address, leading byte offset (between the two 16 B k-chunks), stride byte offset (between
+// 8-row groups), all >> 4; version 1 (bits 46..47); layout type 0 (bits 61..63).
+__device__ __forceinline__ uint64_t umma_desc(uint32_t saddr, uint32_t lbo, uint32_t sbo) {
+    return (uint64_t)((saddr >> 4) & 0x3FFFu) | ((uint64_t)((lbo >> 4) & 0x3FFFu) << 16) |
+           ((uint64_t)((sbo >> 4) & 0x3FFFu) << 32) | ((uint64_t)1 << 46);
+}
+// instruction descriptor (cute::UMMA::InstrDescriptor): D = S32 (2 << 4), A = B = signed 8 bit (1 << 7, 1 << 10),
+// both K-major, N >> 3 at bit 17, M >> 4 at bit 24.
+__device__ __forceinline__ uint32_t umma_idesc_i8(int n) {
+    return (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(GI_BM >> 4) << 24);
+}
+
+// ---------------------------------------------------------------------------------------------
+// the GEMM.  grid (items, bins of the chunk); one 128 x n output tile per CTA.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(GI_NT, 1) wpe_gram_i8_kernel(const int8_t* __restrict__ slices, const int* __restrict__ ex,
+                                                               cd* __restrict__ Raug, double* __restrict__ rdiag,
+                                                               WpeDims m, GiDims g, GiPlan plan, size_t bf0, int variant) {
+    extern __shared__ __align__(128) unsigned char smem[];
+    __shared__ __align__(8) unsigned long long bar_full[GI_STAGES], bar_empty[GI_STAGES], bar_acc;
+    __shared__ uint32_t tmem_slot;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const GiItem it = plan.items[blockIdx.x];
+    const int n = it.n;
+    const size_t bl = blockIdx.y, bf = bf0 + bl;
+    const int Tv = wpe_valid_frames(m, bf);
+    const int nk = min(g.KB >> 1, (Tv + 31) >> 5);          // k-steps of 32 frames
+    const int8_t* __restrict__ sl = slices + bl * ((size_t)GI_NS * g.KB * g.NRp * 16);
+    const uint32_t smem_base = smem_u32(smem);
+
+    if (tid == 0) {
+        for (int s = 0; s < GI_STAGES; ++s) { mbar_init(smem_u32(&bar_full[s]), 1); mbar_init(smem_u32(&bar_empty[s]), 1); }
+        mbar_init(smem_u32(&bar_acc), 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_slot)), "n"(512) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = tmem_slot;
+
+    if (nk > 0) {
+        if (warp == 0) {
+            // ===== TMA producer: 2 x 5 x (A 2 KB + B n*16 B) bulk copies per stage =====
+            if (lane == 0) {
+                const uint32_t stage_tx = (uint32_t)(GI_NS * 2 * (GI_BM * 16 + n * 16));
+                for (int ks = 0; ks < nk; ++ks) {
+                    const int st = ks % GI_STAGES;
+                    if (ks >= GI_STAGES) mbar_wait(smem_u32(&bar_empty[st]), ((ks / GI_STAGES) - 1) & 1);
+                    const uint32_t full = smem_u32(&bar_full[st]);
+                    mbar_expect_tx(full, stage_tx);
+                    const uint32_t a_dst = smem_base + st * GI_STAGE_BYTES, b_dst = a_dst + GI_A_STAGE;
+#pragma unroll
+                    for (int p = 0; p < GI_NS; ++p)
+#pragma unroll
+                        for (int h = 0; h < 2; ++h) {
+                            const size_t row0 = ((size_t)p * g.KB + 2 * ks + h) * g.NRp;
+                            bulk_g2s(a_dst + (p * 2 + h) * (GI_BM * 16), sl + (row0 + it.r0) * 16, GI_BM * 16, full);
+                            bulk_g2s(b_dst + (p * 2 + h) * (n * 16), sl + (row0 + it.c0) * 16, n * 16, full);
+                        }
+                }
+            }
+        } else if (warp == 1) {
+            // ===== MMA issuer: 15 digit-pair MMAs per stage, accumulator of order p + q at column (p + q) n =====
+            if (lane == 0) {
+                const uint32_t idesc = umma_idesc_i8(n);
+                const uint32_t a_lbo = (variant & 1) ? 128u : (uint32_t)(GI_BM * 16), a_sbo = (variant & 1) ? (uint32_t)(GI_BM * 16) : 128u;
+                const uint32_t b_lbo = (variant & 1) ? 128u : (uint32_t)(n * 16), b_sbo = (variant & 1) ? (uint32_t)(n * 16) : 128u;
+                for (int ks = 0; ks < nk; ++ks) {
+                    const int st = ks % GI_STAGES;
+                    mbar_wait(smem_u32(&bar_full[st]), (ks / GI_STAGES) & 1);
+                    tc_fence_after();
+                    const uint32_t a_src = smem_base + st * GI_STAGE_BYTES, b_src = a_src + GI_A_STAGE;
+#pragma unroll
+                    for (int p = 0; p < GI_NS; ++p)
+#pragma unroll
+                        for (int q = 0; q + p < GI_NS; ++q) {
+                            const uint64_t ad = umma_desc(a_src + p * GI_A_SLICE, a_lbo, a_sbo);
+                            const uint64_t bd = umma_desc(b_src + q * (2 * n * 16), b_lbo, b_sbo);
+                            tc_mma_i8(tmem + (uint32_t)((p + q) * n), ad, bd, idesc, (ks > 0 || p > 0) ? 1u : 0u);
+                        }
+                    tc_commit(smem_u32(&bar_empty[st]));   // stage free once these MMAs have read it
+                }
+                tc_commit(smem_u32(&bar_acc));             // accumulators complete
+            }
+        } else {
+            // ===== epilogue: TMEM -> int64 recombination -> complex float64 -> Raug =====
+            const int q = warp & 3;                        // TMEM lane quarter this warp may access
+            const int a = it.r0 + 32 * q + lane;           // real row (digit-plane numbering)
+            const int rca = a >> 1, i = rca - m.D;
+            const bool odd = a & 1;
+            const bool row_ok = i >= 0 && i < m.LD;
+            const int* __restrict__ exb = ex + bl * (size_t)g.NRc;
+            const int ea = (rca < g.NRc) ? exb[rca] : 0;
+            cd* __restrict__ Rb = Raug + bf * (size_t)(m.LD + m.D) * m.LD;
+            mbar_wait(smem_u32(&bar_acc), 0);
+            tc_fence_after();
+            for (int cb = 0; cb < n; cb += 16) {
+                int acc[GI_NS][16];
+#pragma unroll
+                for (int o = 0; o < GI_NS; ++o) tc_ld16(tmem + ((uint32_t)(32 * q) << 16) + (uint32_t)(o * n + cb), acc[o]);
+                tc_ld_wait();
+#pragma unroll
+                for (int jj = 0; jj < 8; ++jj) {
+                    long long v0 = 0, v1 = 0;              // entries (a, 2 cc) and (a, 2 cc + 1)
+#pragma unroll
+                    for (int o = 0; o < GI_NS; ++o) {
+                        v0 += (long long)acc[o][2 * jj] << (8 * (GI_NS - 1 - o));
+                        v1 += (long long)acc[o][2 * jj + 1] << (8 * (GI_NS - 1 - o));
+                    }
+                    // even lane holds (rr, ri), odd lane (ir, ii):  Re = rr + ii,  Im = ir - ri
+                    const long long other = __shfl_xor_sync(0xffffffffu, v1, 1);
+                    const long long comb = odd ? v0 - other : v0 + other;
+                    const int cc = (it.c0 + cb) / 2 + jj;  // complex column (digit-plane numbering)
+                    if (!row_ok || cc >= g.NRc) continue;
+                    const int eb = exb[cc];
+                    double val = (double)comb * __longlong_as_double((long long)(1023 + 32 - ea - eb) << 52);
+                    if (cc < m.D) {
+                        // (tap row i, channel cc): conj goes to the P^H rows of Raug
+                        double* dst = reinterpret_cast<double*>(&Rb[(size_t)(m.LD + cc) * m.LD + i]);
+                        if (odd) dst[1] = -val; else dst[0] = val;
+                    } else {
+                        const int j = cc - m.D;
+                        if (j <= i) {
+                            double* dst = reinterpret_cast<double*>(&Rb[(size_t)i * m.LD + j]);
+                            if (odd) dst[1] = (i == j) ? 0.0 : val;
+                            else {
+                                dst[0] = val;
+                                if (i == j && rdiag) rdiag[bf * (size_t)m.LD + i] = val;
+                            }
+                        }
+                    }
+                }
+            }
+        }
+    } else if (warp >= 2) {
+        // no valid frames: the trapezoid is zero
+        const int q = warp & 3, a = it.r0 + 32 * q + lane, i = (a >> 1) - m.D;
+        cd* __restrict__ Rb = Raug + bf * (size_t)(m.LD + m.D) * m.LD;
+        if (i >= 0 && i < m.LD && !(a & 1)) {
+            for (int cc = it.c0 / 2; cc < (it.c0 + n) / 2 && cc < g.NRc; ++cc) {
+                if (cc < m.D) Rb[(size_t)(m.LD + cc) * m.LD + i] = cmake(0.0, 0.0);
+                else if (cc - m.D <= i) { Rb[(size_t)i * m.LD + cc - m.D] = cmake(0.0, 0.0); if (cc - m.D == i && rdiag) rdiag[bf * (size_t)m.LD + i] = 0.0; }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(512) : "memory");
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// host
+// ---------------------------------------------------------------------------------------------
+static GiPlan gi_plan(int D, int LD) {
+    GiPlan pl;
+    pl.n_items = 0;
+    const int tiles = (2 * LD + GI_BM - 1) / GI_BM;
+    // heavy (wide) row tiles first: better tail behaviour
+    for (int i = tiles - 1; i >= 0; --i) {
+        int C = std::min(2 * D + GI_BM * (i + 1), 2 * D + 2 * LD);
+        C = (C + 15) / 16;                                 // 16-column units
+        const int nch = (C * 16 + GI_NMAX - 1) / GI_NMAX;
+        int c0 = 0;
+        for (int c = 0; c < nch; ++c) {
+            const int w = C / nch + (c < C % nch ? 1 : 0);
+            GiItem itm;
+            itm.r0 = (short)(2 * D + GI_BM * i); itm.c0 = (short)(c0 * 16); itm.n = (short)(w * 16);
+            pl.items[pl.n_items++] = itm;
+            c0 += w;
+        }
+    }
+    return pl;
+}
+
+int wpe_gram_i8_run(const float2* Y, const double* inv, cd* Raug, double* rdiag, const WpeDims& m, int BF,
+                    const WpeI8Ws& ws, int variant, cudaStream_t st) {
+    const GiDims g = gi_dims(m.D, m.T, m.LD);
+    const GiPlan plan = gi_plan(m.D, m.LD);
+    static bool attr_done = false;
+    if (!attr_done) {
+        GSS_CUDA(cudaFuncSetAttribute(wpe_gram_i8_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, GI_SMEM));
+        attr_done = true;
+    }
+    const int half = g.NRp >> 1;
+    for (int b0 = 0; b0 < BF; b0 += ws.chunk_bins) {
+        const int nb = std::min(ws.chunk_bins, BF - b0);
+        wpe_i8_scale_kernel<<<nb, 256, (size_t)m.T * sizeof(float), st>>>(Y, inv, ws.mu, ws.ex, m, g, (size_t)b0);
+        GSS_LAUNCH_CHECK("wpe_i8_scale_kernel");
+        dim3 sg((half * g.KB + 255) / 256, nb);
+        wpe_i8_slice_kernel<<<sg, 256, 0, st>>>(Y, ws.mu, ws.ex, ws.slices, m, g, (size_t)b0);
+        GSS_LAUNCH_CHECK("wpe_i8_slice_kernel");
+        dim3 gg(plan.n_items, nb);
+        wpe_gram_i8_kernel<<<gg, GI_NT, GI_SMEM, st>>>(ws.slices, ws.ex, Raug, rdiag, m, g, plan, (size_t)b0, variant);
+        GSS_LAUNCH_CHECK("wpe_gram_i8_kernel");
+    }
+    return GSS_OK;
+}
+
+}  // namespace gss
