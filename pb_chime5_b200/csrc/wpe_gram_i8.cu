@@ -36,9 +36,9 @@ constexpr int GI_BM = 128;                               // real rows per tile (
 constexpr int GI_NMAX = 96;                              // real columns per tile: 5 accumulators x 96 <= 512 TMEM columns
 constexpr int GI_STAGES = 5;
 constexpr int GI_NT = 192;                               // warp 0 TMA, warp 1 MMA + TMEM alloc, warps 2..5 epilogue
-constexpr int GI_A_SLICE = 2 * GI_BM * 16;               // one digit plane of the A tile, one k-step (32 frames)
-constexpr int GI_A_STAGE = GI_NS * GI_A_SLICE;           // 20480
-constexpr int GI_B_STAGE = GI_NS * 2 * GI_NMAX * 16;     // 15360
+constexpr int GI_BLK_BYTES = GI_NS * 2 * 128;            // all planes of 8 rows x 32 frames: 1280
+constexpr int GI_A_STAGE = GI_BLK_BYTES * GI_BM / 8;     // 20480
+constexpr int GI_B_STAGE = GI_BLK_BYTES * GI_NMAX / 8;   // 15360
 constexpr int GI_STAGE_BYTES = GI_A_STAGE + GI_B_STAGE;  // 35840
 constexpr int GI_SMEM = GI_STAGES * GI_STAGE_BYTES;      // 179200 (forces one CTA per SM: TMEM is allocated whole)
 constexpr int GI_MAX_ITEMS = 96;
@@ -46,12 +46,20 @@ constexpr int GI_HEADROOM = 37;                          // |x| in [2^37, 2^38) 
 
 struct GiItem { short r0, c0, n; };                      // first real row of the A tile, first real column, width
 struct GiPlan { int n_items; GiItem items[GI_MAX_ITEMS]; };
-struct GiDims { int NRc, NRp, KB; };                     // complex rows D + LD, padded real rows, 16-frame blocks (even)
+struct GiDims { int DP, NRc, NRp, KB; };                 // padded channel rows, complex rows DP + LD, padded real rows, 16-frame blocks (even)
+
+// complex row rc of the digit planes -> (channel d, shift s); d < 0: padding row (zeros)
+__device__ __forceinline__ void gi_row(const WpeDims& m, const GiDims& g, int rc, int& d, int& s) {
+    if (rc < m.D) { d = rc; s = 0; }
+    else if (rc < g.DP || rc >= g.NRc) { d = -1; s = 0; }
+    else { const int i = rc - g.DP, k = i / m.D; d = i - k * m.D; s = m.delay + k; }
+}
 
 static GiDims gi_dims(int D, int T, int LD) {
     GiDims g;
-    g.NRc = D + LD;
-    g.NRp = 2 * D + (2 * LD + GI_BM - 1) / GI_BM * GI_BM;
+    g.DP = (D + 7) / 8 * 8;                                // tap rows start on a 16-real-row boundary
+    g.NRc = g.DP + LD;
+    g.NRp = 2 * g.DP + (2 * LD + GI_BM - 1) / GI_BM * GI_BM;
     g.KB = (T + 31) / 32 * 2;
     return g;
 }
@@ -61,10 +69,10 @@ bool wpe_i8_applicable(int D, int T, int L) {
     const int LD = L * D;
     // the digit sums must fit INT32: 2^14 per product, 5 pairs per order
     if ((long long)(T + 32) * 5 * 16384 >= 2147483647LL) return false;
-    const int tiles = (2 * LD + GI_BM - 1) / GI_BM;
+    const int tiles = (2 * LD + GI_BM - 1) / GI_BM, DP2 = (D + 7) / 8 * 16;
     int items = 0;
     for (int i = 0; i < tiles; ++i) {
-        int C = std::min(2 * D + GI_BM * (i + 1), 2 * D + 2 * LD);
+        int C = std::min(DP2 + GI_BM * (i + 1), DP2 + 2 * LD);
         C = (C + 15) / 16 * 16;
         items += (C + GI_NMAX - 1) / GI_NMAX;
     }
@@ -109,17 +117,16 @@ __global__ void __launch_bounds__(256) wpe_i8_scale_kernel(const float2* __restr
     double* muo = mu + (size_t)blockIdx.x * T;
     for (int t = threadIdx.x; t < T; t += blockDim.x) {
         const double v = t < Tv ? sqrt(iv[t]) : 0.0;
-        muo[t] = v;
+        if (blockIdx.y == 0) muo[t] = v;
         mus[t] = (float)v;
     }
     __syncthreads();
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
-    for (int rc = warp; rc < g.NRc; rc += nw) {
+    for (int rc = warp + nw * blockIdx.y; rc < g.NRc; rc += nw * gridDim.y) {
         int d, s;
-        if (rc < m.D) { d = rc; s = 0; }
-        else { const int k = (rc - m.D) / m.D; d = rc - m.D - k * m.D; s = m.delay + k; }
+        gi_row(m, g, rc, d, s);
         float mx = 0.f;
-        for (int t = s + lane; t < Tv; t += 32) {
+        for (int t = s + lane; d >= 0 && t < Tv; t += 32) {
             const float2 v = __ldg(&Yg[(size_t)d * T + t - s]);
             mx = fmaxf(mx, fmaxf(fabsf(v.x), fabsf(v.y)) * mus[t]);
         }
@@ -133,11 +140,13 @@ __global__ void __launch_bounds__(256) wpe_i8_scale_kernel(const float2* __restr
 }
 
 // ---------------------------------------------------------------------------------------------
-// digit planes.  Layout per bin: [plane p][kb = t / 16][real row][t % 16] int8, i.e. the
-// canonical K-major no-swizzle UMMA layout: a core matrix (8 rows x 16 B) is 128 contiguous
-// bytes, 8-row groups are 128 B apart (SBO), the two 16-frame halves of a k-step (rows x 16 B)
-// apart (LBO).  Real row 2 rc = Re, 2 rc + 1 = Im of complex row rc; rows [0, D) = Y (unshifted),
-// rows [D, D + LD) = the taps.  Thread = (kb, complex row): 16 frames, both real rows.
+// digit planes.  Layout per bin: [k-step = t / 32][8-row block][plane p][half = (t / 16) % 2][row % 8][t % 16]
+// int8: core matrices (8 rows x 16 B = 128 contiguous bytes) of the canonical K-major no-swizzle
+// UMMA layout, the two 16-frame halves of a k-step 128 B apart (LBO), 8-row groups 1280 B apart
+// (SBO), planes 256 B apart -- so ALL planes of any row range of one k-step are one contiguous
+// run: a stage is two bulk copies (the TMA unit is issue-bound on many small copies: 20 copies
+// of 2 KB per stage ran at 7 % tensor activity).  Real row 2 rc = Re, 2 rc + 1 = Im of complex row
+// rc; rows [0, D) = Y (unshifted), rows [D, D + LD) = the taps.  Thread = (kb, complex row).
 // ---------------------------------------------------------------------------------------------
 __device__ __forceinline__ unsigned gi_pack4(unsigned a, unsigned b, unsigned c, unsigned d, int byte) {
     const unsigned sel = 0x0040u | (unsigned)byte | ((unsigned)byte << 4);     // [a.byte, b.byte, -, -]
@@ -156,12 +165,9 @@ __global__ void __launch_bounds__(256) wpe_i8_slice_kernel(const float2* __restr
     const int T = m.T, Tv = wpe_valid_frames(m, bf);
     int8_t* out = slices + bl * gi_slice_bytes_per_bin(g);
     unsigned lo_re[16], hi_re[16], lo_im[16], hi_im[16];
-    bool live = rc < g.NRc;
-    int d = 0, s = 0;
-    if (live) {
-        if (rc < m.D) { d = rc; s = 0; }
-        else { const int k = (rc - m.D) / m.D; d = rc - m.D - k * m.D; s = m.delay + k; }
-    }
+    int d = -1, s = 0;
+    gi_row(m, g, rc, d, s);
+    const bool live = d >= 0;
     if (live) {
         const float2* __restrict__ Yg = Y + bf * (size_t)m.D * T + (size_t)d * T;
         const double* __restrict__ mub = mu + bl * (size_t)T;
@@ -199,7 +205,8 @@ __global__ void __launch_bounds__(256) wpe_i8_slice_kernel(const float2* __restr
             re4 = make_uint4(wr[0], wr[1], wr[2], wr[3]);
             im4 = make_uint4(wi[0], wi[1], wi[2], wi[3]);
         }
-        uint4* dst = reinterpret_cast<uint4*>(out + (((size_t)p * g.KB + kb) * g.NRp + 2 * rc) * 16);
+        const size_t blk = (size_t)(kb >> 1) * (g.NRp >> 3) + (rc >> 2);          // (k-step, 8-row block)
+        uint4* dst = reinterpret_cast<uint4*>(out + ((blk * GI_NS + p) * 2 + (kb & 1)) * 128 + (2 * rc & 7) * 16);
         dst[0] = re4;
         dst[1] = im4;
     }
@@ -264,7 +271,7 @@ __device__ __forceinline__ uint32_t umma_idesc_i8(int n) {
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(GI_NT, 1) wpe_gram_i8_kernel(const int8_t* __restrict__ slices, const int* __restrict__ ex,
                                                                cd* __restrict__ Raug, double* __restrict__ rdiag,
-                                                               WpeDims m, GiDims g, GiPlan plan, size_t bf0, int variant) {
+                                                               WpeDims m, GiDims g, GiPlan plan, size_t bf0, int /*variant*/) {
     extern __shared__ __align__(128) unsigned char smem[];
     __shared__ __align__(8) unsigned long long bar_full[GI_STAGES], bar_empty[GI_STAGES], bar_acc;
     __shared__ uint32_t tmem_slot;
@@ -293,31 +300,25 @@ __global__ void __launch_bounds__(GI_NT, 1) wpe_gram_i8_kernel(const int8_t* __r
 
     if (nk > 0) {
         if (warp == 0) {
-            // ===== TMA producer: 2 x 5 x (A 2 KB + B n*16 B) bulk copies per stage =====
+            // ===== TMA producer: two bulk copies per stage (A: 20 KB, B: n * 160 B) =====
             if (lane == 0) {
-                const uint32_t stage_tx = (uint32_t)(GI_NS * 2 * (GI_BM * 16 + n * 16));
+                const uint32_t stage_tx = (uint32_t)(GI_BLK_BYTES * (GI_BM / 8 + n / 8));
+                const size_t nrb = (size_t)(g.NRp >> 3);
                 for (int ks = 0; ks < nk; ++ks) {
                     const int st = ks % GI_STAGES;
                     if (ks >= GI_STAGES) mbar_wait(smem_u32(&bar_empty[st]), ((ks / GI_STAGES) - 1) & 1);
                     const uint32_t full = smem_u32(&bar_full[st]);
                     mbar_expect_tx(full, stage_tx);
                     const uint32_t a_dst = smem_base + st * GI_STAGE_BYTES, b_dst = a_dst + GI_A_STAGE;
-#pragma unroll
-                    for (int p = 0; p < GI_NS; ++p)
-#pragma unroll
-                        for (int h = 0; h < 2; ++h) {
-                            const size_t row0 = ((size_t)p * g.KB + 2 * ks + h) * g.NRp;
-                            bulk_g2s(a_dst + (p * 2 + h) * (GI_BM * 16), sl + (row0 + it.r0) * 16, GI_BM * 16, full);
-                            bulk_g2s(b_dst + (p * 2 + h) * (n * 16), sl + (row0 + it.c0) * 16, n * 16, full);
-                        }
+                    bulk_g2s(a_dst, sl + ((size_t)ks * nrb + (it.r0 >> 3)) * GI_BLK_BYTES, GI_BLK_BYTES * (GI_BM / 8), full);
+                    bulk_g2s(b_dst, sl + ((size_t)ks * nrb + (it.c0 >> 3)) * GI_BLK_BYTES, GI_BLK_BYTES * (n / 8), full);
                 }
             }
         } else if (warp == 1) {
             // ===== MMA issuer: 15 digit-pair MMAs per stage, accumulator of order p + q at column (p + q) n =====
             if (lane == 0) {
                 const uint32_t idesc = umma_idesc_i8(n);
-                const uint32_t a_lbo = (variant & 1) ? 128u : (uint32_t)(GI_BM * 16), a_sbo = (variant & 1) ? (uint32_t)(GI_BM * 16) : 128u;
-                const uint32_t b_lbo = (variant & 1) ? 128u : (uint32_t)(n * 16), b_sbo = (variant & 1) ? (uint32_t)(n * 16) : 128u;
+                const uint32_t lbo = 128u, sbo = (uint32_t)GI_BLK_BYTES;
                 for (int ks = 0; ks < nk; ++ks) {
                     const int st = ks % GI_STAGES;
                     mbar_wait(smem_u32(&bar_full[st]), (ks / GI_STAGES) & 1);
@@ -327,8 +328,8 @@ __global__ void __launch_bounds__(GI_NT, 1) wpe_gram_i8_kernel(const int8_t* __r
                     for (int p = 0; p < GI_NS; ++p)
 #pragma unroll
                         for (int q = 0; q + p < GI_NS; ++q) {
-                            const uint64_t ad = umma_desc(a_src + p * GI_A_SLICE, a_lbo, a_sbo);
-                            const uint64_t bd = umma_desc(b_src + q * (2 * n * 16), b_lbo, b_sbo);
+                            const uint64_t ad = umma_desc(a_src + p * 256, lbo, sbo);
+                            const uint64_t bd = umma_desc(b_src + q * 256, lbo, sbo);
                             tc_mma_i8(tmem + (uint32_t)((p + q) * n), ad, bd, idesc, (ks > 0 || p > 0) ? 1u : 0u);
                         }
                     tc_commit(smem_u32(&bar_empty[st]));   // stage free once these MMAs have read it
@@ -339,7 +340,7 @@ __global__ void __launch_bounds__(GI_NT, 1) wpe_gram_i8_kernel(const int8_t* __r
             // ===== epilogue: TMEM -> int64 recombination -> complex float64 -> Raug =====
             const int q = warp & 3;                        // TMEM lane quarter this warp may access
             const int a = it.r0 + 32 * q + lane;           // real row (digit-plane numbering)
-            const int rca = a >> 1, i = rca - m.D;
+            const int rca = a >> 1, i = rca - g.DP;
             const bool odd = a & 1;
             const bool row_ok = i >= 0 && i < m.LD;
             const int* __restrict__ exb = ex + bl * (size_t)g.NRc;
@@ -367,12 +368,13 @@ __global__ void __launch_bounds__(GI_NT, 1) wpe_gram_i8_kernel(const int8_t* __r
                     if (!row_ok || cc >= g.NRc) continue;
                     const int eb = exb[cc];
                     double val = (double)comb * __longlong_as_double((long long)(1023 + 32 - ea - eb) << 52);
+                    if (cc >= m.D && cc < g.DP) continue;  // padding rows between Y and the taps
                     if (cc < m.D) {
                         // (tap row i, channel cc): conj goes to the P^H rows of Raug
                         double* dst = reinterpret_cast<double*>(&Rb[(size_t)(m.LD + cc) * m.LD + i]);
                         if (odd) dst[1] = -val; else dst[0] = val;
                     } else {
-                        const int j = cc - m.D;
+                        const int j = cc - g.DP;
                         if (j <= i) {
                             double* dst = reinterpret_cast<double*>(&Rb[(size_t)i * m.LD + j]);
                             if (odd) dst[1] = (i == j) ? 0.0 : val;
@@ -387,12 +389,13 @@ __global__ void __launch_bounds__(GI_NT, 1) wpe_gram_i8_kernel(const int8_t* __r
         }
     } else if (warp >= 2) {
         // no valid frames: the trapezoid is zero
-        const int q = warp & 3, a = it.r0 + 32 * q + lane, i = (a >> 1) - m.D;
+        const int q = warp & 3, a = it.r0 + 32 * q + lane, i = (a >> 1) - g.DP;
         cd* __restrict__ Rb = Raug + bf * (size_t)(m.LD + m.D) * m.LD;
         if (i >= 0 && i < m.LD && !(a & 1)) {
             for (int cc = it.c0 / 2; cc < (it.c0 + n) / 2 && cc < g.NRc; ++cc) {
+                const int j = cc - g.DP;
                 if (cc < m.D) Rb[(size_t)(m.LD + cc) * m.LD + i] = cmake(0.0, 0.0);
-                else if (cc - m.D <= i) { Rb[(size_t)i * m.LD + cc - m.D] = cmake(0.0, 0.0); if (cc - m.D == i && rdiag) rdiag[bf * (size_t)m.LD + i] = 0.0; }
+                else if (j >= 0 && j <= i) { Rb[(size_t)i * m.LD + j] = cmake(0.0, 0.0); if (j == i && rdiag) rdiag[bf * (size_t)m.LD + i] = 0.0; }
             }
         }
     }
@@ -410,17 +413,17 @@ __global__ void __launch_bounds__(GI_NT, 1) wpe_gram_i8_kernel(const int8_t* __r
 static GiPlan gi_plan(int D, int LD) {
     GiPlan pl;
     pl.n_items = 0;
-    const int tiles = (2 * LD + GI_BM - 1) / GI_BM;
+    const int tiles = (2 * LD + GI_BM - 1) / GI_BM, DP2 = (D + 7) / 8 * 16;
     // heavy (wide) row tiles first: better tail behaviour
     for (int i = tiles - 1; i >= 0; --i) {
-        int C = std::min(2 * D + GI_BM * (i + 1), 2 * D + 2 * LD);
+        int C = std::min(DP2 + GI_BM * (i + 1), DP2 + 2 * LD);
         C = (C + 15) / 16;                                 // 16-column units
         const int nch = (C * 16 + GI_NMAX - 1) / GI_NMAX;
         int c0 = 0;
         for (int c = 0; c < nch; ++c) {
             const int w = C / nch + (c < C % nch ? 1 : 0);
             GiItem itm;
-            itm.r0 = (short)(2 * D + GI_BM * i); itm.c0 = (short)(c0 * 16); itm.n = (short)(w * 16);
+            itm.r0 = (short)(DP2 + GI_BM * i); itm.c0 = (short)(c0 * 16); itm.n = (short)(w * 16);
             pl.items[pl.n_items++] = itm;
             c0 += w;
         }
@@ -440,7 +443,7 @@ int wpe_gram_i8_run(const float2* Y, const double* inv, cd* Raug, double* rdiag,
     const int half = g.NRp >> 1;
     for (int b0 = 0; b0 < BF; b0 += ws.chunk_bins) {
         const int nb = std::min(ws.chunk_bins, BF - b0);
-        wpe_i8_scale_kernel<<<nb, 256, (size_t)m.T * sizeof(float), st>>>(Y, inv, ws.mu, ws.ex, m, g, (size_t)b0);
+        wpe_i8_scale_kernel<<<dim3(nb, 8), 256, (size_t)m.T * sizeof(float), st>>>(Y, inv, ws.mu, ws.ex, m, g, (size_t)b0);
         GSS_LAUNCH_CHECK("wpe_i8_scale_kernel");
         dim3 sg((half * g.KB + 255) / 256, nb);
         wpe_i8_slice_kernel<<<sg, 256, 0, st>>>(Y, ws.mu, ws.ex, ws.slices, m, g, (size_t)b0);

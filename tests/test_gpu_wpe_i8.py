@@ -1,0 +1,171 @@
+"""GPU: the INT8 tensor-core WPE correlation build (csrc/wpe_gram_i8.cu, tcgen05 kind::i8,
+exact digit-split integer arithmetic) against a numpy float64 Gram matrix, against the float64
+(DMMA) build, and end to end through gss_wpe_c64 against the oracle -- including the float64
+re-do of ill-conditioned bins."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import gss_oracle as oracle
+from pb_chime5_b200 import _lib, ops, synth
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(autouse=True)
+def _need_cuda(cuda):
+    torch.cuda.set_device(cuda)
+    yield
+    _lib.lib().gss_debug_wpe_config(-1, -1.0)
+
+
+def rel_err(a, b):
+    return float(np.abs(a - b).max() / max(np.abs(b).max(), 1e-30))
+
+
+def make_input(B, F, D, T, seed, spread=0.3):
+    """complex64 frames with a random-walk power envelope (speech-like dynamics) + the WPE weights"""
+    rng = np.random.default_rng(seed)
+    Y = rng.standard_normal((B, F, D, T)) + 1j * rng.standard_normal((B, F, D, T))
+    env = np.exp(np.cumsum(rng.standard_normal((B, F, 1, T)) * spread, axis=-1))
+    gains = np.exp(rng.standard_normal((1, 1, D, 1)))            # unequal channel gains
+    Y = (Y * env * gains).astype(np.complex64)
+    lam = np.mean(np.abs(Y.astype(np.complex128)) ** 2, axis=2)
+    lam = np.maximum(lam, 1e-10 * lam.max(axis=-1, keepdims=True))
+    return Y, 1.0 / lam
+
+
+def ref_gram(Y, inv, taps, delay, Tv=None):
+    """float64 (LD + D, LD): rows [0, LD) = R = Yt L^-1 Yt^H, rows [LD, LD + D) = P^H (wpe.cu contract)"""
+    D, T = Y.shape
+    Tv = T if Tv is None else Tv
+    Yd = Y.astype(np.complex128).copy()
+    Yd[:, Tv:] = 0
+    inv = inv.copy()
+    inv[Tv:] = 0
+    rows = []
+    for k in range(taps):
+        s = delay + k
+        r = np.zeros((D, T), complex)
+        r[:, s:] = Yd[:, :T - s]
+        rows.append(r)
+    A = np.concatenate(rows + [Yd], 0)
+    return (A * inv) @ A[:taps * D].conj().T
+
+
+def run_gram(Yt, invt, mode, taps, delay, frames=None):
+    B, F, D, T = Yt.shape
+    LD = taps * D
+    out = torch.full((B, F, LD + D, LD), float('nan'), dtype=torch.complex128, device=Yt.device)
+    ws = ops.workspace(_lib.workspace_bytes(_lib.OP_WPE, B, F, D, T, 0, taps), Yt.device)
+    fr = None if frames is None else torch.tensor(frames, dtype=torch.int32, device=Yt.device)
+    _lib.check(_lib.lib().gss_debug_wpe_gram(ops._ptr(Yt), ops._ptr(invt), ops._ptr(out), mode, 0, B, F, D, T,
+                                             taps, delay, ops._ptr(fr), ops._ptr(ws), ws.numel(), ops._stream()))
+    torch.cuda.synchronize()
+    return out.cpu().numpy()
+
+
+def scaled_err(got, ref, LD, Y, inv):
+    """max |got - ref| / sqrt(R_ii R_jj) over the lower trapezoid (P^H rows: sqrt(E_d R_jj),
+    E_d = sum_t inv |y_d|^2, the diagonal the unshifted rows would have)"""
+    dg = np.sqrt(np.abs(np.diag(ref[:LD]).real))
+    ed = np.sqrt(np.sum(np.abs(Y.astype(np.complex128)) ** 2 * inv, axis=-1))
+    tril = np.tril(np.ones((LD, LD), bool))
+    e1 = (np.abs(got[:LD] - ref[:LD]) / np.outer(dg, dg))[tril].max()
+    e2 = (np.abs(got[LD:] - ref[LD:]) / np.outer(ed, dg)).max()
+    return float(max(e1, e2))
+
+
+@pytest.mark.parametrize('D,taps,T,F', [(24, 10, 941, 3), (8, 10, 191, 4), (24, 2, 100, 2), (6, 10, 64, 2),
+                                        (5, 12, 333, 2), (24, 20, 700, 1)])
+def test_gram_i8_matches_float64(D, taps, T, F):
+    dev = torch.device('cuda')
+    delay, B = 2, 2
+    Y, inv = make_input(B, F, D, T, seed=D * 100 + taps)
+    Yt, invt = torch.from_numpy(Y).to(dev), torch.from_numpy(inv).to(dev)
+    LD = taps * D
+    g8 = run_gram(Yt, invt, 1, taps, delay)
+    g64 = run_gram(Yt, invt, 0, taps, delay)
+    tril = np.tril(np.ones((LD, LD), bool))
+    for b in range(B):
+        for f in range(F):
+            ref = ref_gram(Y[b, f], inv[b, f], taps, delay)
+            assert np.isfinite(g8[b, f][:LD][tril]).all() and np.isfinite(g8[b, f][LD:]).all()
+            assert scaled_err(g64[b, f], ref, LD, Y[b, f], inv[b, f]) < 1e-13
+            assert scaled_err(g8[b, f], ref, LD, Y[b, f], inv[b, f]) < 2e-9
+            # exact Hermitian structure of the integer path: real diagonal
+            assert np.abs(np.diag(g8[b, f][:LD]).imag).max() == 0.0
+
+
+def test_gram_i8_ragged_and_silent():
+    """per-utterance frame counts; an all-zero channel; a bin without valid frames"""
+    dev = torch.device('cuda')
+    D, taps, T, F, delay = 8, 8, 200, 2, 3
+    Y, inv = make_input(3, F, D, T, seed=5)
+    Y[0, :, 2] = 0                                            # dead channel
+    frames = [200, 77, 0]
+    Yt, invt = torch.from_numpy(Y).to(dev), torch.from_numpy(inv).to(dev)
+    LD = taps * D
+    g8 = run_gram(Yt, invt, 1, taps, delay, frames)
+    tril = np.tril(np.ones((LD, LD), bool))
+    for b, tv in enumerate(frames):
+        for f in range(F):
+            ref = ref_gram(Y[b, f], inv[b, f], taps, delay, tv)
+            scale = max(np.abs(ref).max(), 1e-300)
+            assert np.abs(g8[b, f][:LD] - ref[:LD])[tril].max() <= 2e-9 * scale
+            assert np.abs(g8[b, f][LD:] - ref[LD:]).max() <= 2e-9 * scale
+    low = np.concatenate([tril, np.ones((D, LD), bool)], 0)   # the trapezoid the contract defines
+    assert np.abs(g8[2][:, low]).max() == 0.0
+    dead = np.zeros((LD + D, LD), bool)
+    dead[:, [k * D + 2 for k in range(taps)]] = True
+    dead[[k * D + 2 for k in range(taps)] + [LD + 2], :] = True
+    assert np.abs(g8[0][:, dead & low]).max() == 0.0
+
+
+def test_wpe_i8_equals_float64_path_and_oracle():
+    """well-conditioned benchmark-like input: no bin is re-done, outputs agree with the float64
+    build to rounding and with the oracle to the parity bar"""
+    dev = torch.device('cuda')
+    lib = _lib.lib()
+    Obs, _ = synth.make_utterance(11, D=24, T=300, F=6, K=5)
+    Obs[:, 3:, :] += 0.4 * Obs[:, :-3, :]
+    Y = ops.pack_dtf_to_fdt(torch.from_numpy(Obs).to(dev)[None])
+    lib.gss_debug_wpe_config(0, -1.0)
+    x64 = ops.wpe(Y, 10, 2, 3).cpu().numpy()
+    lib.gss_debug_wpe_config(2, -1.0)
+    lib.gss_debug_wpe_redo_count(1)
+    x8 = ops.wpe(Y, 10, 2, 3).cpu().numpy()
+    assert lib.gss_debug_wpe_redo_count(1) == 0
+    assert rel_err(x8, x64) < 2e-7, rel_err(x8, x64)       # complex64 outputs: identical up to the last bit
+    ref = oracle.wpe_dtf(Obs.astype(np.complex128), 10, 2, 3)
+    got = ops.unpack_fdt_to_dtf(torch.from_numpy(x8).to(dev))[0].cpu().numpy()
+    assert rel_err(got, ref) < 1e-5
+
+
+def test_wpe_i8_illconditioned_bins_are_redone_in_float64():
+    """reverberant, low-noise audio (cond 1e6+): the a-posteriori pivot test flags the bins and the
+    result is the float64 build's, bit for bit; with the test disabled the INT8-only result differs"""
+    dev = torch.device('cuda')
+    lib = _lib.lib()
+    obs, _ = synth.make_reverberant_audio(3, D=8, N=32000, K=3)
+    Y = ops.stft(torch.from_numpy(obs).to(dev)[None])
+    Ysub = Y[:, [5, 40, 129, 300]].contiguous()
+    lib.gss_debug_wpe_config(0, -1.0)
+    x64 = ops.wpe(Ysub, 10, 2, 3).cpu().numpy()
+    lib.gss_debug_wpe_config(2, -1.0)
+    lib.gss_debug_wpe_redo_count(1)
+    x8 = ops.wpe(Ysub, 10, 2, 3).cpu().numpy()
+    redone = lib.gss_debug_wpe_redo_count(1)
+    assert redone > 0
+    if redone == 3 * 4:                                       # every bin, every iteration
+        assert np.array_equal(x8, x64)
+    else:
+        assert rel_err(x8, x64) < 1e-5
+    # threshold 0: nothing is re-done, the INT8 Gram matrix alone still dereverberates sensibly
+    lib.gss_debug_wpe_config(2, 0.0)
+    lib.gss_debug_wpe_redo_count(1)
+    xi = ops.wpe(Ysub, 10, 2, 1).cpu().numpy()
+    assert lib.gss_debug_wpe_redo_count(1) == 0
+    lib.gss_debug_wpe_config(0, -1.0)
+    x1 = ops.wpe(Ysub, 10, 2, 1).cpu().numpy()
+    assert np.isfinite(xi).all() and rel_err(xi, x1) < 1e-3
