@@ -15,17 +15,17 @@
 // where every inner sum is an INT8 x INT8 -> INT32 tensor-core GEMM (exact).  Digit pairs
 // with p + q <= 4 are kept (15 MMAs per k-step, five INT32 accumulators per tile in TMEM,
 // one per order p + q); the dropped pairs are below 2^-38 of the row scales.  The epilogue
-// recombines the five accumulators into one int64 per entry (exact), forms
-// Re = rr + ii and Im = ir - ri between the two lanes of a complex row (exact), converts to
-// float64 once and undoes the row scales.  Measured error vs the float64 Gram matrix:
+// recombines the five accumulators in float64 (Horner in base 256, relative error 2^-53), forms
+// Re = rr + ii and Im = ir - ri between the two lanes of a complex row and undoes the row
+// scales (powers of two).  Measured error vs the float64 Gram matrix:
 // <= 6e-10 sqrt(R_ii R_jj) on adversarial envelopes, ~1e-11 typical (tests/test_gpu_wpe_i8.py);
 // bins whose normal equations are too ill-conditioned for that are re-done by the FP64
 // (DMMA) path, see wpe.cu.
 //
 // Kernels: wpe_i8_scale_kernel (row maxima -> exponents, sqrt(inv)), wpe_i8_slice_kernel
 // (digit planes in the canonical no-swizzle K-major UMMA layout, so tiles are plain 1-D bulk
-// copies), wpe_gram_i8_kernel (TMA producer warp / MMA issuer warp / 4 epilogue warps,
-// 5-stage mbarrier pipeline, TMEM accumulators).
+// copies), wpe_gram_i8_kernel (persistent; TMA producer warp / MMA issuer warp / 8 epilogue
+// warps, 5-stage mbarrier pipeline, TMEM accumulators).
 #include "wpe_i8.cuh"
 #include <algorithm>
 
@@ -35,7 +35,8 @@ constexpr int GI_NS = 5;                                 // int8 digit planes pe
 constexpr int GI_BM = 128;                               // real rows per tile (UMMA M)
 constexpr int GI_NMAX = 96;                              // real columns per tile: 5 accumulators x 96 <= 512 TMEM columns
 constexpr int GI_STAGES = 5;
-constexpr int GI_NT = 192;                               // warp 0 TMA, warp 1 MMA + TMEM alloc, warps 2..5 epilogue
+constexpr int GI_EPI_WARPS = 8;
+constexpr int GI_NT = 64 + 32 * GI_EPI_WARPS;            // warp 0 TMA, warp 1 MMA + TMEM alloc, warps 2..9 epilogue
 constexpr int GI_BLK_BYTES = GI_NS * 2 * 128;            // all planes of 8 rows x 32 frames: 1280
 constexpr int GI_A_STAGE = GI_BLK_BYTES * GI_BM / 8;     // 20480
 constexpr int GI_B_STAGE = GI_BLK_BYTES * GI_NMAX / 8;   // 15360
@@ -267,26 +268,32 @@ __device__ __forceinline__ uint32_t umma_idesc_i8(int n) {
 }
 
 // ---------------------------------------------------------------------------------------------
-// the GEMM.  grid (items, bins of the chunk); one 128 x n output tile per CTA.
+// the GEMM.  Persistent CTAs (one per SM) walk the (bin, tile) work items of the chunk; a tile is
+// 128 real rows x n <= 96 real columns, all five accumulators in TMEM (5 n <= 480 columns).
+// Roles: warp 0 = TMA producer, warp 1 = MMA issuer (+ TMEM alloc), warps 2..9 = epilogue (two
+// warps per TMEM lane quarter, alternating 16-column blocks).  The producer runs ahead into the
+// next tile while the epilogue drains TMEM; the MMA warp waits for the drain (bar_drain).
 // ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+
 __global__ void __launch_bounds__(GI_NT, 1) wpe_gram_i8_kernel(const int8_t* __restrict__ slices, const int* __restrict__ ex,
                                                                cd* __restrict__ Raug, double* __restrict__ rdiag,
-                                                               WpeDims m, GiDims g, GiPlan plan, size_t bf0, int /*variant*/) {
+                                                               WpeDims m, GiDims g, GiPlan plan, size_t bf0, int nbins) {
     extern __shared__ __align__(128) unsigned char smem[];
-    __shared__ __align__(8) unsigned long long bar_full[GI_STAGES], bar_empty[GI_STAGES], bar_acc;
+    __shared__ __align__(8) unsigned long long bar_full[GI_STAGES], bar_empty[GI_STAGES], bar_acc, bar_drain;
     __shared__ uint32_t tmem_slot;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const GiItem it = plan.items[blockIdx.x];
-    const int n = it.n;
-    const size_t bl = blockIdx.y, bf = bf0 + bl;
-    const int Tv = wpe_valid_frames(m, bf);
-    const int nk = min(g.KB >> 1, (Tv + 31) >> 5);          // k-steps of 32 frames
-    const int8_t* __restrict__ sl = slices + bl * ((size_t)GI_NS * g.KB * g.NRp * 16);
     const uint32_t smem_base = smem_u32(smem);
+    const int n_work = nbins * plan.n_items;
+    const size_t bin_bytes = (size_t)GI_NS * g.KB * g.NRp * 16;
+    const size_t nrb = (size_t)(g.NRp >> 3);
 
     if (tid == 0) {
         for (int s = 0; s < GI_STAGES; ++s) { mbar_init(smem_u32(&bar_full[s]), 1); mbar_init(smem_u32(&bar_empty[s]), 1); }
         mbar_init(smem_u32(&bar_acc), 1);
+        mbar_init(smem_u32(&bar_drain), GI_EPI_WARPS);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) {
@@ -298,77 +305,116 @@ __global__ void __launch_bounds__(GI_NT, 1) wpe_gram_i8_kernel(const int8_t* __r
     tc_fence_after();
     const uint32_t tmem = tmem_slot;
 
-    if (nk > 0) {
-        if (warp == 0) {
-            // ===== TMA producer: two bulk copies per stage (A: 20 KB, B: n * 160 B) =====
-            if (lane == 0) {
-                const uint32_t stage_tx = (uint32_t)(GI_BLK_BYTES * (GI_BM / 8 + n / 8));
-                const size_t nrb = (size_t)(g.NRp >> 3);
-                for (int ks = 0; ks < nk; ++ks) {
-                    const int st = ks % GI_STAGES;
-                    if (ks >= GI_STAGES) mbar_wait(smem_u32(&bar_empty[st]), ((ks / GI_STAGES) - 1) & 1);
+    if (warp == 0) {
+        // ===== TMA producer: two bulk copies per stage (A: 20 KB, B: n * 160 B) =====
+        if (lane == 0) {
+            int kg = 0;                                    // k-steps issued so far (all tiles)
+            for (int w = blockIdx.x; w < n_work; w += gridDim.x) {
+                const int bl = w / plan.n_items;
+                const GiItem it = plan.items[w - bl * plan.n_items];
+                const int Tv = wpe_valid_frames(m, bf0 + bl);
+                const int nk = min(g.KB >> 1, (Tv + 31) >> 5);
+                const int8_t* __restrict__ sl = slices + (size_t)bl * bin_bytes;
+                const uint32_t stage_tx = (uint32_t)(GI_BLK_BYTES * (GI_BM / 8 + it.n / 8));
+                for (int ks = 0; ks < nk; ++ks, ++kg) {
+                    const int st = kg % GI_STAGES;
+                    if (kg >= GI_STAGES) mbar_wait(smem_u32(&bar_empty[st]), ((kg / GI_STAGES) - 1) & 1);
                     const uint32_t full = smem_u32(&bar_full[st]);
                     mbar_expect_tx(full, stage_tx);
                     const uint32_t a_dst = smem_base + st * GI_STAGE_BYTES, b_dst = a_dst + GI_A_STAGE;
                     bulk_g2s(a_dst, sl + ((size_t)ks * nrb + (it.r0 >> 3)) * GI_BLK_BYTES, GI_BLK_BYTES * (GI_BM / 8), full);
-                    bulk_g2s(b_dst, sl + ((size_t)ks * nrb + (it.c0 >> 3)) * GI_BLK_BYTES, GI_BLK_BYTES * (n / 8), full);
+                    bulk_g2s(b_dst, sl + ((size_t)ks * nrb + (it.c0 >> 3)) * GI_BLK_BYTES, GI_BLK_BYTES * (it.n / 8), full);
                 }
             }
-        } else if (warp == 1) {
-            // ===== MMA issuer: 15 digit-pair MMAs per stage, accumulator of order p + q at column (p + q) n =====
-            if (lane == 0) {
+        }
+    } else if (warp == 1) {
+        // ===== MMA issuer: 15 digit-pair MMAs per stage, accumulator of order p + q at column (p + q) n =====
+        if (lane == 0) {
+            // descriptor without the address: LBO = 128 B (k halves), SBO = 1280 B (8-row groups), version 1
+            const uint64_t desc_hi = ((uint64_t)((128u >> 4) & 0x3FFFu) << 16) | ((uint64_t)(((uint32_t)GI_BLK_BYTES >> 4) & 0x3FFFu) << 32) |
+                                     ((uint64_t)1 << 46);
+            int kg = 0, tile = 0;
+            for (int w = blockIdx.x; w < n_work; w += gridDim.x) {
+                const int bl = w / plan.n_items;
+                const GiItem it = plan.items[w - bl * plan.n_items];
+                const int n = it.n;
+                const int Tv = wpe_valid_frames(m, bf0 + bl);
+                const int nk = min(g.KB >> 1, (Tv + 31) >> 5);
+                if (nk == 0) continue;
+                if (tile > 0) { mbar_wait(smem_u32(&bar_drain), (tile - 1) & 1); tc_fence_after(); }   // TMEM drained
                 const uint32_t idesc = umma_idesc_i8(n);
-                const uint32_t lbo = 128u, sbo = (uint32_t)GI_BLK_BYTES;
-                for (int ks = 0; ks < nk; ++ks) {
-                    const int st = ks % GI_STAGES;
-                    mbar_wait(smem_u32(&bar_full[st]), (ks / GI_STAGES) & 1);
+                for (int ks = 0; ks < nk; ++ks, ++kg) {
+                    const int st = kg % GI_STAGES;
+                    mbar_wait(smem_u32(&bar_full[st]), (kg / GI_STAGES) & 1);
                     tc_fence_after();
                     const uint32_t a_src = smem_base + st * GI_STAGE_BYTES, b_src = a_src + GI_A_STAGE;
+                    const uint64_t a0 = desc_hi | (uint64_t)((a_src >> 4) & 0x3FFFu), b0 = desc_hi | (uint64_t)((b_src >> 4) & 0x3FFFu);
 #pragma unroll
                     for (int p = 0; p < GI_NS; ++p)
 #pragma unroll
-                        for (int q = 0; q + p < GI_NS; ++q) {
-                            const uint64_t ad = umma_desc(a_src + p * 256, lbo, sbo);
-                            const uint64_t bd = umma_desc(b_src + q * 256, lbo, sbo);
-                            tc_mma_i8(tmem + (uint32_t)((p + q) * n), ad, bd, idesc, (ks > 0 || p > 0) ? 1u : 0u);
-                        }
+                        for (int q = 0; q + p < GI_NS; ++q)   // planes are 256 B apart: +16 in the address field
+                            tc_mma_i8(tmem + (uint32_t)((p + q) * n), a0 + (uint64_t)(p * 16), b0 + (uint64_t)(q * 16), idesc,
+                                      (ks > 0 || p > 0) ? 1u : 0u);
                     tc_commit(smem_u32(&bar_empty[st]));   // stage free once these MMAs have read it
                 }
                 tc_commit(smem_u32(&bar_acc));             // accumulators complete
+                ++tile;
             }
-        } else {
-            // ===== epilogue: TMEM -> int64 recombination -> complex float64 -> Raug =====
-            const int q = warp & 3;                        // TMEM lane quarter this warp may access
+        }
+    } else {
+        // ===== epilogue: TMEM -> float64 recombination -> complex -> Raug =====
+        const int ew = warp - 2;
+        const int q = warp & 3;                            // TMEM lane quarter this warp may access
+        const int sub = ew >> 2;                           // which of the two warps of the quarter
+        int tile = 0;
+        for (int w = blockIdx.x; w < n_work; w += gridDim.x) {
+            const int bl = w / plan.n_items;
+            const GiItem it = plan.items[w - bl * plan.n_items];
+            const int n = it.n;
+            const size_t bf = bf0 + bl;
+            const int Tv = wpe_valid_frames(m, bf);
+            const int nk = min(g.KB >> 1, (Tv + 31) >> 5);
             const int a = it.r0 + 32 * q + lane;           // real row (digit-plane numbering)
             const int rca = a >> 1, i = rca - g.DP;
             const bool odd = a & 1;
             const bool row_ok = i >= 0 && i < m.LD;
-            const int* __restrict__ exb = ex + bl * (size_t)g.NRc;
-            const int ea = (rca < g.NRc) ? exb[rca] : 0;
             cd* __restrict__ Rb = Raug + bf * (size_t)(m.LD + m.D) * m.LD;
-            mbar_wait(smem_u32(&bar_acc), 0);
+            if (nk == 0) {
+                // no valid frames: the trapezoid is zero
+                if (row_ok && !odd && sub == 0) {
+                    for (int cc = it.c0 / 2; cc < (it.c0 + n) / 2 && cc < g.NRc; ++cc) {
+                        const int j = cc - g.DP;
+                        if (cc < m.D) Rb[(size_t)(m.LD + cc) * m.LD + i] = cmake(0.0, 0.0);
+                        else if (j >= 0 && j <= i) { Rb[(size_t)i * m.LD + j] = cmake(0.0, 0.0); if (j == i && rdiag) rdiag[bf * (size_t)m.LD + i] = 0.0; }
+                    }
+                }
+                continue;
+            }
+            const int* __restrict__ exb = ex + (size_t)bl * g.NRc;
+            const int ea = (rca < g.NRc) ? exb[rca] : 0;
+            const double row_scale = __longlong_as_double((long long)(1023 + 32 - ea) << 52);
+            mbar_wait(smem_u32(&bar_acc), tile & 1);
             tc_fence_after();
-            for (int cb = 0; cb < n; cb += 16) {
+            for (int cb = 16 * sub; cb < n; cb += 32) {
                 int acc[GI_NS][16];
 #pragma unroll
                 for (int o = 0; o < GI_NS; ++o) tc_ld16(tmem + ((uint32_t)(32 * q) << 16) + (uint32_t)(o * n + cb), acc[o]);
                 tc_ld_wait();
 #pragma unroll
                 for (int jj = 0; jj < 8; ++jj) {
-                    long long v0 = 0, v1 = 0;              // entries (a, 2 cc) and (a, 2 cc + 1)
+                    // sum_o acc_o 256^(4-o): |.| < 2^57, float64 Horner (relative error 2^-53)
+                    double v0 = (double)acc[0][2 * jj], v1 = (double)acc[0][2 * jj + 1];
 #pragma unroll
-                    for (int o = 0; o < GI_NS; ++o) {
-                        v0 += (long long)acc[o][2 * jj] << (8 * (GI_NS - 1 - o));
-                        v1 += (long long)acc[o][2 * jj + 1] << (8 * (GI_NS - 1 - o));
+                    for (int o = 1; o < GI_NS; ++o) {
+                        v0 = fma(v0, 256.0, (double)acc[o][2 * jj]);
+                        v1 = fma(v1, 256.0, (double)acc[o][2 * jj + 1]);
                     }
                     // even lane holds (rr, ri), odd lane (ir, ii):  Re = rr + ii,  Im = ir - ri
-                    const long long other = __shfl_xor_sync(0xffffffffu, v1, 1);
-                    const long long comb = odd ? v0 - other : v0 + other;
+                    const double other = __shfl_xor_sync(0xffffffffu, v1, 1);
+                    const double comb = odd ? v0 - other : v0 + other;
                     const int cc = (it.c0 + cb) / 2 + jj;  // complex column (digit-plane numbering)
-                    if (!row_ok || cc >= g.NRc) continue;
-                    const int eb = exb[cc];
-                    double val = (double)comb * __longlong_as_double((long long)(1023 + 32 - ea - eb) << 52);
-                    if (cc >= m.D && cc < g.DP) continue;  // padding rows between Y and the taps
+                    if (!row_ok || cc >= g.NRc || (cc >= m.D && cc < g.DP)) continue;
+                    const double val = comb * row_scale * __longlong_as_double((long long)(1023 - exb[cc]) << 52);
                     if (cc < m.D) {
                         // (tap row i, channel cc): conj goes to the P^H rows of Raug
                         double* dst = reinterpret_cast<double*>(&Rb[(size_t)(m.LD + cc) * m.LD + i]);
@@ -386,17 +432,10 @@ __global__ void __launch_bounds__(GI_NT, 1) wpe_gram_i8_kernel(const int8_t* __r
                     }
                 }
             }
-        }
-    } else if (warp >= 2) {
-        // no valid frames: the trapezoid is zero
-        const int q = warp & 3, a = it.r0 + 32 * q + lane, i = (a >> 1) - g.DP;
-        cd* __restrict__ Rb = Raug + bf * (size_t)(m.LD + m.D) * m.LD;
-        if (i >= 0 && i < m.LD && !(a & 1)) {
-            for (int cc = it.c0 / 2; cc < (it.c0 + n) / 2 && cc < g.NRc; ++cc) {
-                const int j = cc - g.DP;
-                if (cc < m.D) Rb[(size_t)(m.LD + cc) * m.LD + i] = cmake(0.0, 0.0);
-                else if (j >= 0 && j <= i) { Rb[(size_t)i * m.LD + j] = cmake(0.0, 0.0); if (j == i && rdiag) rdiag[bf * (size_t)m.LD + i] = 0.0; }
-            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(smem_u32(&bar_drain));   // this warp has read its part of TMEM
+            ++tile;
         }
     }
     tc_fence_before();
@@ -441,15 +480,21 @@ int wpe_gram_i8_run(const float2* Y, const double* inv, cd* Raug, double* rdiag,
         attr_done = true;
     }
     const int half = g.NRp >> 1;
-    for (int b0 = 0; b0 < BF; b0 += ws.chunk_bins) {
-        const int nb = std::min(ws.chunk_bins, BF - b0);
+    // bins per chunk: as many as the scratch holds, rounded down to whole waves of the persistent CTAs
+    int cbins = ws.chunk_bins;
+    {
+        const int waves = cbins * plan.n_items / num_sms();
+        if (waves >= 1) cbins = std::max(1, waves * num_sms() / plan.n_items);
+    }
+    for (int b0 = 0; b0 < BF; b0 += cbins) {
+        const int nb = std::min(cbins, BF - b0);
         wpe_i8_scale_kernel<<<dim3(nb, 8), 256, (size_t)m.T * sizeof(float), st>>>(Y, inv, ws.mu, ws.ex, m, g, (size_t)b0);
         GSS_LAUNCH_CHECK("wpe_i8_scale_kernel");
         dim3 sg((half * g.KB + 255) / 256, nb);
         wpe_i8_slice_kernel<<<sg, 256, 0, st>>>(Y, ws.mu, ws.ex, ws.slices, m, g, (size_t)b0);
         GSS_LAUNCH_CHECK("wpe_i8_slice_kernel");
-        dim3 gg(plan.n_items, nb);
-        wpe_gram_i8_kernel<<<gg, GI_NT, GI_SMEM, st>>>(ws.slices, ws.ex, Raug, rdiag, m, g, plan, (size_t)b0, variant);
+        const int grid = std::min(plan.n_items * nb, num_sms());
+        wpe_gram_i8_kernel<<<grid, GI_NT, GI_SMEM, st>>>(ws.slices, ws.ex, Raug, rdiag, m, g, plan, (size_t)b0, nb);
         GSS_LAUNCH_CHECK("wpe_gram_i8_kernel");
     }
     return GSS_OK;
