@@ -192,6 +192,51 @@ def algorithmic_flops_em(B):
     return alg, executed
 
 
+def measure_wpe_gram(torch, _lib, ops, obs, c):
+    """One WPE correlation build (all bins of the batch) through gss_debug_wpe_gram: the INT8
+    tensor-core path (digit planes + tcgen05 kind::i8 GEMM) and the float64 DMMA kernel."""
+    Y = ops.pack_dtf_to_fdt(obs)
+    B, F, D, T = Y.shape
+    taps, delay, LD = c['taps'], c['delay'], c['taps'] * c['D']
+    inv = 1.0 / (Y.real.double() ** 2 + Y.imag.double() ** 2).mean(dim=2).clamp_min(1e-30)
+    out = torch.empty((B, F, LD + D, LD), dtype=torch.complex128, device=Y.device)
+    ws = ops.workspace(_lib.workspace_bytes(_lib.OP_WPE, B, F, D, T, 0, taps), Y.device)
+    ms = {}
+    for mode in (0, 1):
+        def call():
+            _lib.check(_lib.lib().gss_debug_wpe_gram(ops._ptr(Y), ops._ptr(inv), ops._ptr(out), mode, 0, B, F, D, T,
+                                                     taps, delay, None, ops._ptr(ws), ws.numel(), ops._stream()))
+        for _ in range(2):
+            call()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        e0.record()
+        for _ in range(3):
+            call()
+        e1.record()
+        torch.cuda.synchronize()
+        ms[mode] = e0.elapsed_time(e1) / 3
+    # algorithmic work (SURVEY 8d): 8 (LD)^2 T + 8 LD D T real flops per bin for R and P (full matrices);
+    # executed INT8 work: 15 digit-pair GEMMs over the real-stacked lower trapezoid tiles
+    alg_flops = B * F * (8.0 * LD * LD * T + 8.0 * LD * D * T)
+    tiles = -(-2 * LD // 128)
+    cols = sum(min(2 * 24 + 128 * (i + 1), 2 * 24 + 2 * LD) for i in range(tiles)) if D == 24 else None
+    int8_ops = B * F * 15 * 2.0 * 128 * cols * (-(-T // 32) * 32) if cols else None
+    peaks_file = ROOT / 'MEASURED_PEAKS.json'
+    bf16 = json.loads(peaks_file.read_text()).get('bf16_tflops') if peaks_file.exists() else 1590.0
+    res = {'kernel': 'wpe_i8_scale + wpe_i8_slice + wpe_gram_i8_kernel (tcgen05.mma kind::i8, exact integer Gram)',
+           'bound': 'tensor', 'ms_per_build': ms[1], 'ms_per_build_float64_dmma': ms[0],
+           'algorithmic_tflops': alg_flops / (ms[1] * 1e-3) / 1e12,
+           'algorithmic_tflops_float64_dmma': alg_flops / (ms[0] * 1e-3) / 1e12,
+           'unit': 'TOP/s', 'peak': 2 * bf16,
+           'peak_source': '2 x measured dense bf16 (MEASURED_PEAKS.json; INT8 nominal = 2 x bf16 on B200)',
+           'note': 'the GEMM streams the digit planes from L2 (35 KB per 15 MMAs): L2-bandwidth bound, see DESIGN.md'}
+    if int8_ops:
+        res['achieved'] = int8_ops / (ms[1] * 1e-3) / 1e12
+        res['frac'] = res['achieved'] / res['peak']
+    return res
+
+
 def run_gpu(args):
     import torch
     from pb_chime5_b200 import _lib, core, ops, sharding, synth
@@ -288,6 +333,14 @@ def run_gpu(args):
     sharding.barrier()
     sec_e2e_pipe = sharding.max_over_ranks(e0.elapsed_time(e1) * 1e-3, dev)
 
+    # side measurement: the WPE correlation build alone (INT8 tensor cores vs the float64 DMMA build)
+    wpe_gram = None
+    if c['taps'] and rank == 0:
+        try:
+            wpe_gram = measure_wpe_gram(torch, _lib, ops, dev_obs[0], c)
+        except Exception as ex:  # noqa: BLE001  (diagnostic only, never fails the bench)
+            wpe_gram = {'error': repr(ex)}
+
     total_utts = world * B * args.steps
     value = total_utts / sec
     e2e_value = total_utts / sec_e2e
@@ -344,6 +397,8 @@ def run_gpu(args):
                              'the kernel is FP64-pipe bound at D=24, see DESIGN.md'},
         'clocks': clocks,
     }
+    if wpe_gram is not None:
+        line['roofline_wpe_gram'] = wpe_gram
     if world == 1 and not args.no_cpu:
         import multiprocessing as mp
         procs = os.cpu_count() or 1

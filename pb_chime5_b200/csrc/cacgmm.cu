@@ -68,7 +68,7 @@ struct CacgmmCfg {
     static constexpr size_t E_BYTES = size_t(TE) * YLD * sizeof(float2);
     static constexpr size_t MT_BYTES = size_t(2) * TM * YLD * sizeof(float2);   // double-buffered complex64 M tiles
     static constexpr size_t MS_BYTES = 0;
-    static constexpr size_t SWEEP_BYTES = size_t(K) * NP * sizeof(cd) + size_t(2) * K * DP * sizeof(cd) + 2 * K * 8 + 64;
+    static constexpr size_t SWEEP_BYTES = size_t(K) * NP * sizeof(cd) + size_t(2) * K * DP * sizeof(cd) + 4 * K * 8 + 64;
     static constexpr size_t JAC_BYTES = size_t(3) * DP * JLD * sizeof(cd);
     static constexpr size_t YS_BYTES = cmax(cmax(E_BYTES, MT_BYTES + MS_BYTES), cmax(SWEEP_BYTES, JAC_BYTES));
     static constexpr size_t W_BYTES = size_t(TE) * KP * sizeof(double);
@@ -446,7 +446,8 @@ __global__ void __launch_bounds__(NT, MINB) cacgmm_em_kernel(const CacgmmParams 
         //      (the column of the next pivot is forwarded while the current step is applied).
         cd* S = reinterpret_cast<cd*>(ys_raw);                                  // [K][NP]
         cd* colb = S + K * C::NP;                                               // [2][K][DP] column of the pivot
-        double* pivb = reinterpret_cast<double*>(colb + 2 * K * DP);            // [2][K]
+        double* pivb = reinterpret_cast<double*>(colb + 2 * K * DP);            // [2][K] pivot
+        double* dinvb = pivb + 2 * K;                                           // [2][K] 1 / pivot (0 if not positive): one division per class and step
         const bool need_exact = flags_s[31] != 0;
         if (!need_exact) {
             constexpr int EPT = (K * C::NP + NT - 1) / NT;                      // entries per thread
@@ -468,7 +469,7 @@ __global__ void __launch_bounds__(NT, MINB) cacgmm_em_kernel(const CacgmmParams 
                         S[e] = v;
                         if (c == 0) {                                           // column of the first pivot
                             colb[k * DP + i] = v;
-                            if (i == 0) pivb[k] = v.x;
+                            if (i == 0) { pivb[k] = v.x; dinvb[k] = (v.x > 0.0 && isfinite(v.x)) ? 1.0 / v.x : 0.0; }
                         }
                     }
                 }
@@ -480,14 +481,15 @@ __global__ void __launch_bounds__(NT, MINB) cacgmm_em_kernel(const CacgmmParams 
                 cd* coln = colb + ((j + 1) & 1) * K * DP;
                 const double* piv = pivb + (j & 1) * K;
                 double* pivn = pivb + ((j + 1) & 1) * K;
+                const double* dinv = dinvb + (j & 1) * K;
+                double* dinvn = dinvb + ((j + 1) & 1) * K;
 #pragma unroll
                 for (int n = 0; n < EPT; ++n) {
                     const int meta = ent_meta[n];
                     if (meta < 0) continue;
                     const int k = meta >> 16, i = (meta >> 8) & 255, c = meta & 255;
                     const int e = tid + n * NT;
-                    const double pv = piv[k];
-                    const double d = (pv > 0.0 && isfinite(pv)) ? 1.0 / pv : 0.0;
+                    const double d = dinv[k];
                     // branch-free: entries of row/column j are S*d (the stored value IS the column
                     // entry or its conjugate), the pivot becomes -d, everything else gets the
                     // rank-1 update  S - (u_i d) conj(u_c)
@@ -501,10 +503,13 @@ __global__ void __launch_bounds__(NT, MINB) cacgmm_em_kernel(const CacgmmParams 
                     v.y = (on_i | on_c) ? vs.y : v.y;
                     v.x = (on_i & on_c) ? -d : v.x;
                     v.y = (on_i & on_c) ? 0.0 : v.y;
-                    if (on_i & on_c) pivbuf[k * DP + j] = pv;
+                    if (on_i & on_c) pivbuf[k * DP + j] = piv[k];
                     S[e] = v;
                     // forward the column of the next pivot
-                    if (c == j + 1) { coln[k * DP + i] = v; if (i == j + 1) pivn[k] = v.x; }
+                    if (c == j + 1) {
+                        coln[k * DP + i] = v;
+                        if (i == j + 1) { pivn[k] = v.x; dinvn[k] = (v.x > 0.0 && isfinite(v.x)) ? 1.0 / v.x : 0.0; }
+                    }
                     else if (i == j + 1) coln[k * DP + c] = cconj(v);
                 }
                 __syncthreads();
