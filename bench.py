@@ -318,7 +318,7 @@ def run_gpu(args):
     # the same through the pipelined public API (copies of neighbouring steps overlap the kernels)
     def run_stream(nsteps):
         gen = enh.enhance_stft_host_stream(
-            ((host_obs[i % nsets], host_act[i % nsets], ti, ctx, ctx) for i in range(nsteps)))
+            ((host_obs[i % nsets], host_act[i % nsets], ti, ctx, ctx) for i in range(nsteps)), reuse_outputs=True)
         for res in gen:
             last = res
         return last
@@ -363,6 +363,16 @@ def run_gpu(args):
         except Exception:
             traffic = None
 
+    # headline end-to-end number: host buffers in, host buffers out, every step copied in full;
+    # the faster of the two public host APIs (one synchronous call per batch / the pipelined stream)
+    e2e_sync = {'value': e2e_value, 'ms_per_step': 1e3 * sec_e2e / args.steps,
+                'api': 'Enhancer.enhance_stft_host (pinned host STFT in, X_hat + masks out, one synchronous call per batch)'}
+    e2e_pipe = {'value': total_utts / sec_e2e_pipe, 'ms_per_step': 1e3 * sec_e2e_pipe / args.steps,
+                'api': 'Enhancer.enhance_stft_host_stream (same copies per batch; those of neighbouring batches overlap the kernels)'}
+    best = e2e_pipe if e2e_pipe['value'] > e2e_sync['value'] else e2e_sync
+    e2e = {'value': best['value'], 'unit': 'utterances/s', 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h,
+           'ms_per_step': best['ms_per_step'], 'api': best['api'], 'synchronous': e2e_sync, 'pipelined': e2e_pipe}
+
     if rank != 0:
         sharding.barrier()
         sharding.shutdown()
@@ -376,11 +386,7 @@ def run_gpu(args):
                    'l2': f"inputs {B * c['D'] * c['T'] * c['F'] * 8 // 1000000} MB per step per GPU vs 126 MB L2, two input sets alternated",
                    'value_region': 'inputs resident in HBM in the reference layout (B,D,T,F); timed: pack, WPE, EM, beamformer, unpack',
                    'arithmetic': 'complex64 storage, float64 arithmetic'},
-        'e2e': {'value': e2e_value, 'unit': 'utterances/s', 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h,
-                'ms_per_step': 1e3 * sec_e2e / args.steps,
-                'api': 'Enhancer.enhance_stft_host (pinned host STFT in, X_hat + masks out)',
-                'pipelined': {'value': total_utts / sec_e2e_pipe, 'ms_per_step': 1e3 * sec_e2e_pipe / args.steps,
-                              'api': 'Enhancer.enhance_stft_host_stream (copies of neighbouring steps overlap the kernels)'}},
+        'e2e': e2e,
         'gpu_launches': int(launches),
         'roofline': {'kernel': 'cacgmm_em_kernel (fused EM, all iterations)', 'bound': 'hbm',
                      'achieved': achieved, 'peak': peak, 'unit': 'GB/s', 'frac': achieved / peak,

@@ -375,13 +375,15 @@ class Enhancer:
         torch.cuda.current_stream().synchronize()
         return res
 
-    def enhance_stft_host_stream(self, batches, return_masks=True):
+    def enhance_stft_host_stream(self, batches, return_masks=True, reuse_outputs=False):
         """Pipelined variant of `enhance_stft_host` for a sequence of batches: yields one result
         dict per input batch, in order.  `batches` yields tuples
         (Obs (B,D,T,F) complex64 pinned host tensor, acitivity_freq (B,K,T_act), target_index,
         start_ctx, end_ctx).  The host->device copy of batch i+1 and the device->host copy of
-        batch i-1 run on side streams while batch i is computed (two input slots in HBM, results
-        land in fresh pinned buffers); every batch is still copied in and out in full."""
+        batch i-1 run on side streams while batch i is computed (two input slots in HBM); every
+        batch is still copied in and out in full.  Results land in fresh pinned buffers, or, with
+        `reuse_outputs=True`, in a ring of three pinned slots per shape (no page-locking inside
+        the loop): a yielded result then stays valid until two further results have been yielded."""
         dev = _device()
         compute = torch.cuda.current_stream()
         h2d, d2h = torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev)
@@ -399,14 +401,25 @@ class Enhancer:
                 ready.record(h2d)
             return x, a, vecs, ready
 
+        ring, ring_pos = {}, [0]
+
+        def host_slot(name, like):
+            if not reuse_outputs:
+                return torch.empty(like.shape, dtype=like.dtype, pin_memory=True)
+            key = (name, tuple(like.shape), like.dtype)
+            if key not in ring:
+                ring[key] = [torch.empty(like.shape, dtype=like.dtype, pin_memory=True) for _ in range(3)]
+            return ring[key][ring_pos[0] % 3]
+
         def download(X_tf, m_ktf, done):
             with torch.cuda.stream(d2h):
                 d2h.wait_event(done)
-                res = {'X_hat': torch.empty(X_tf.shape, dtype=X_tf.dtype, pin_memory=True)}
+                res = {'X_hat': host_slot('X_hat', X_tf)}
                 res['X_hat'].copy_(X_tf, non_blocking=True)
                 if m_ktf is not None:
-                    res['masks'] = torch.empty(m_ktf.shape, dtype=m_ktf.dtype, pin_memory=True)
+                    res['masks'] = host_slot('masks', m_ktf)
                     res['masks'].copy_(m_ktf, non_blocking=True)
+                ring_pos[0] += 1
                 fin = torch.cuda.Event()
                 fin.record(d2h)
             return res, fin, (X_tf, m_ktf)        # keep the device tensors alive until the copy is done

@@ -379,6 +379,9 @@ def test_pipelined_host_stream_equals_synchronous_calls():
     for r, g in zip(ref, got):
         assert torch.equal(r['X_hat'], g['X_hat']) and torch.equal(r['masks'], g['masks'])
     assert list(enh.enhance_stft_host_stream(iter([]))) == []
+    # ring of reusable pinned result slots: same values, consumed as they are yielded
+    for r, g in zip(ref, enh.enhance_stft_host_stream(iter(items), reuse_outputs=True)):
+        assert torch.equal(r['X_hat'], g['X_hat']) and torch.equal(r['masks'], g['masks'])
 
 
 @pytest.mark.parametrize('D,K,T,F', [(2, 2, 2, 1), (4, 3, 31, 2), (4, 3, 256, 2), (4, 3, 257, 3), (8, 4, 129, 2),
