@@ -491,27 +491,80 @@ class Enhancer:
                 X_hat=ops.unpack_ft_to_tf(X)[0].cpu().numpy(), x_hat=x_hat.cpu().numpy())
         return _from_device(x_hat, was_np, np.float64)
 
+    def enhance_observation_batch(self, obs_list, ex_array_activities, speaker_ids, exs=None):
+        """B utterances of different lengths in ONE pass of the hot path (what
+        `enhance_observation` does per utterance, core.py:514-571): the samples are zero padded to
+        the longest utterance, the STFT frames beyond an utterance's own count are masked through
+        the ragged-batch interface (`frames`), the iSTFT output is cut back.  Each result is
+        bit-identical to the single-utterance call.  obs_list: B arrays (D, N_b) with the same
+        D; ex_array_activities: B dicts {speaker: (N_b,) bool} with the same number of classes;
+        exs: B example dicts (context frames) or None.  Returns a list of (N'_b,) arrays."""
+        B = len(obs_list)
+        assert B > 0 and len(ex_array_activities) == B and len(speaker_ids) == B
+        dev = _device()
+        was_np = not isinstance(obs_list[0], torch.Tensor)
+        D = int(obs_list[0].shape[0])
+        Ns = [int(o.shape[-1]) for o in obs_list]
+        K = len(ex_array_activities[0])
+        pad = (self.stft_size - self.stft_shift) if self.stft_fading else 0
+        frames = [ops.stft_frames(n, self.stft_size, self.stft_shift, self.stft_fading) for n in Ns]
+        x = torch.zeros((B, D, max(Ns)), dtype=torch.float32, device=dev)
+        for b, o in enumerate(obs_list):
+            assert o.ndim == 2 and o.shape[0] == D, (o.shape, D)
+            x[b, :, :Ns[b]] = _to_device(o, torch.float32)[0]
+        Y = ops.stft(x, self.stft_size, self.stft_shift, self.stft_fading)              # (B,F,D,Tmax)
+        Tmax = Y.shape[3]
+        act = np.zeros((B, K, Tmax), dtype=np.uint8)
+        ti, sc, ec = [], [], []
+        for b in range(B):
+            a = ex_array_activities[b]
+            assert len(a) == K, (len(a), K)
+            af = activity_time_to_frequency(
+                np.array([np.asarray(v) for v in a.values()]), stft_window_length=self.stft_size,
+                stft_shift=self.stft_shift, stft_fading=self.stft_fading, stft_pad=True)
+            n = min(af.shape[-1], Tmax)
+            act[b, :, :n] = af[:, :n]
+            ti.append(tuple(a.keys()).index(speaker_ids[b]))
+            s_ctx = e_ctx = 0
+            if self.bf_drop_context and exs is not None:
+                s_ctx, e_ctx = start_end_context_frames(exs[b], stft_size=self.stft_size,
+                                                        stft_shift=self.stft_shift, stft_fading=self.stft_fading)
+            sc.append(s_ctx)
+            ec.append(min(e_ctx, frames[b]))
+        ivec = lambda v: torch.tensor(v, dtype=torch.int32, device=dev)
+        fr = ivec(frames)
+        X = self.enhance_stft_batch(Y, torch.from_numpy(act).to(dev), ivec(ti), ivec(sc), ivec(ec), frames=fr)
+        x_hat = ops.istft(X, self.stft_size, self.stft_shift, self.stft_fading)        # (B, Nmax')
+        out = []
+        for b in range(B):
+            n_out = frames[b] * self.stft_shift + self.stft_size - self.stft_shift - 2 * pad
+            out.append(_from_device(x_hat[b, :n_out], was_np, np.float64))
+        return out
+
     # ---- data plumbing (out of the hot path; uses the reference's I/O code) --
     def get_iterator(self, session_id):
         return self.db.get_iterator_for_session(
             session_id, audio_read=False, adjust_times=True, drop_unknown_target_speaker=True,
             context_samples=self.context_samples, equal_start_context=True)
 
-    def enhance_session(self, session_ids, audio_dir, dataset_slice=False, audio_dir_exist_ok=False):
-        """core.py:333-394.  Work distribution: one process per GPU; rank r of W takes
-        the examples i with i % W == r (the task farm of dlp_mpi.split_managed becomes
-        a static shard, see pb_chime5_b200/sharding.py)."""
-        from pb_chime5 import mapping
-        from pb_chime5.io import dump_audio
+    def enhance_session(self, session_ids, audio_dir, dataset_slice=False, audio_dir_exist_ok=False,
+                        batch_size=8, skip_existing=False, strict=True):
+        """core.py:333-394.  Work distribution: one process per GPU; rank r of W takes a static
+        shard of the examples (the task farm of dlp_mpi.split_managed, see sharding.py) and runs
+        it through the batching session driver (session.py: length-bucketed batches, audio
+        prefetch, asynchronous wav writing).  `strict` (default, like the reference): the first
+        failing example raises; `skip_existing`: resume an interrupted run."""
         from . import sharding
+        from .session import SessionScheduler
 
         audio_dir = Path(audio_dir)
         it = self.get_iterator(session_ids)
         rank, world = sharding.rank_world()
+        datasets = _session_to_dataset()
         if rank == 0:
-            audio_dir.mkdir(exist_ok=audio_dir_exist_ok)
-            for dataset in set(mapping.session_to_dataset.values()):
-                (audio_dir / dataset).mkdir(exist_ok=audio_dir_exist_ok)
+            audio_dir.mkdir(exist_ok=audio_dir_exist_ok or skip_existing)
+            for dataset in set(datasets.values()):
+                (audio_dir / dataset).mkdir(exist_ok=audio_dir_exist_ok or skip_existing)
         sharding.barrier()
         if dataset_slice is not False:
             if dataset_slice is True:
@@ -522,21 +575,16 @@ class Enhancer:
                 it = it[dataset_slice]
             else:
                 raise ValueError(dataset_slice)
-        for i in sharding.shard_indices(len(it), rank, world):
-            ex = it[i]
-            x_hat = self.enhance_example(ex)
-            dataset = mapping.session_to_dataset[ex['session_id']]
-            if x_hat.ndim == 1:
-                dump_audio(x_hat, audio_dir / f'{dataset}' / f'{ex["example_id"]}.wav')
-            else:
-                raise NotImplementedError(x_hat.shape)
+        mine = [it[i] for i in sharding.shard_indices(len(it), rank, world)]
 
-    def enhance_example(self, ex, debug=False):
-        """core.py:396-512: slice the activity, load the audio of the selected arrays,
-        enhance, cut the context."""
-        from pb_chime5.io import load_audio
+        def path_fn(ex):
+            return audio_dir / datasets.get(ex['session_id'], 'unknown') / f'{ex["example_id"]}.wav'
 
-        session_id = ex['session_id']
+        sched = SessionScheduler(self, self._load_example, path_fn, self._finish_example,
+                                 batch_size=batch_size, skip_existing=skip_existing, strict=strict)
+        return sched.run(mine)
+
+    def _reference_array(self, ex):
         reference_array = self.reference_array
         if reference_array is None:
             try:
@@ -550,7 +598,16 @@ class Enhancer:
                     '\tpython -m ... with ... reference_array=U06\n'
                     'In case of multiarray, the reference array is used for the'
                     'projection of the human annotations.') from None
-        speaker_id = ex['speaker_id']
+        return reference_array
+
+    def _load_example(self, ex):
+        """core.py:396-498: slice the activity, load the audio of the selected arrays ->
+        (obs (D, N) float64, ex_array_activity {speaker: (N,) bool}, speaker_id)."""
+        from .audio_io import load_audio
+        from .session import stack_arrays
+
+        session_id = ex['session_id']
+        reference_array = self._reference_array(ex)
         array_start = ex['start']['observation'][reference_array]
         array_end = ex['end']['observation'][reference_array]
         ex_array_activity = {
@@ -558,33 +615,52 @@ class Enhancer:
             for k, arr in self.activity[session_id][reference_array].items()}
 
         def load(array):
-            return load_audio(ex['audio_path']['observation'][array],
-                              start=ex['start']['observation'][array],
-                              stop=ex['end']['observation'][array])
+            x = load_audio(ex['audio_path']['observation'][array],
+                           start=ex['start']['observation'][array],
+                           stop=ex['end']['observation'][array])
+            return x[None] if x.ndim == 1 else x
 
-        selectors = {True: slice(None), 'outer_array_mics': (0, -1), 'first_array_mics': (0,)}
         if self.multiarray is False:
             obs = load(reference_array)
-        elif self.multiarray in selectors and self.multiarray is not False:
-            arrays = [load(a) for a in sorted(ex['audio_path']['observation'].keys())]
-            assert {v.ndim for v in arrays} == {2}, [v.shape for v in arrays]
-            n = min(v.shape[-1] for v in arrays)       # arrays may differ in length by a few samples
-            sel = selectors[self.multiarray]
-            obs = np.concatenate([v[sel, :n] for v in arrays], axis=0)     # 'ACN->A*CN'
         else:
-            raise ValueError(self.multiarray)
+            obs = stack_arrays([load(a) for a in sorted(ex['audio_path']['observation'].keys())],
+                               self.multiarray)                              # 'ACN->A*CN'
+        return obs, ex_array_activity, ex['speaker_id']
 
-        x_hat = self.enhance_observation(obs, ex_array_activity=ex_array_activity,
-                                         speaker_id=speaker_id, ex=ex, debug=debug)
+    def _finish_example(self, ex, x_hat):
+        """cut the context again (core.py:500-505)"""
         if self.context_samples > 0:
+            reference_array = self._reference_array(ex)
             start_orig = ex['start_orig']['observation'][reference_array]
             start = ex['start']['observation'][reference_array]
             start_context = start_orig - start
             num_samples_orig = ex['num_samples_orig']['observation'][reference_array]
             x_hat = x_hat[..., start_context:start_context + num_samples_orig]
+        return x_hat
+
+    def enhance_example(self, ex, debug=False):
+        """core.py:396-512: slice the activity, load the audio of the selected arrays,
+        enhance, cut the context."""
+        obs, ex_array_activity, speaker_id = self._load_example(ex)
+        x_hat = self.enhance_observation(obs, ex_array_activity=ex_array_activity,
+                                         speaker_id=speaker_id, ex=ex, debug=debug)
+        x_hat = self._finish_example(ex, x_hat)
         if debug:
             self.enhance_example_locals = dict(obs=obs, ex_array_activity=ex_array_activity, x_hat=x_hat)
         return x_hat
+
+
+def _session_to_dataset():
+    """session -> dataset directory names (constants of pb_chime5/mapping.py:1-297, taken from the
+    reference package when it is importable; otherwise the CHiME-5 table restated here)."""
+    try:
+        from pb_chime5 import mapping
+        return dict(mapping.session_to_dataset)
+    except Exception:  # noqa: BLE001
+        table = {'train': ['S03', 'S04', 'S05', 'S06', 'S07', 'S08', 'S12', 'S13', 'S16', 'S17', 'S18', 'S19',
+                           'S20', 'S22', 'S23', 'S24'],
+                 'dev': ['S02', 'S09'], 'eval': ['S01', 'S21']}
+        return {s: d for d, ss in table.items() for s in ss}
 
 
 def get_enhancer(

@@ -409,3 +409,61 @@ def test_shape_boundaries(D, K, T, F):
         assert rel_err(X, refX) < 1e-4
     else:
         assert np.isfinite(X).all()
+
+
+def _disk_session(tmp_path, n_examples=5, arrays=('U01', 'U02'), channels=2, total=90000):
+    """a small on-disk 'session': one wav per array, examples with context like the reference's
+    AddContext (database.py:713-1053) produces them"""
+    from pb_chime5_b200 import audio_io
+    rng = np.random.default_rng(7)
+    spk = ['P05', 'P06']
+    src = rng.standard_normal((len(spk), total)) * (np.sin(np.arange(total) / 900.0 + np.arange(len(spk))[:, None] * 2) > 0)
+    paths = {}
+    for a in arrays:
+        mix = rng.standard_normal((channels, len(spk))) @ src + 0.05 * rng.standard_normal((channels, total))
+        paths[a] = tmp_path / f'S02_{a}.wav'
+        audio_io.dump_audio(0.2 * mix / np.abs(mix).max(), paths[a], normalize=False)
+    activity = {'S02': {a: {s: np.abs(src[i]) > 0 for i, s in enumerate(spk)} | {'Noise': np.ones(total, bool)}
+                        for a in arrays}}
+    exs = []
+    for i in range(n_examples):
+        s_orig = 9000 + 13000 * i
+        n_orig = 5000 + 1700 * i
+        ctx = 4000
+        start, end = s_orig - ctx, s_orig + n_orig + ctx
+        exs.append({'example_id': f'P05_S02_{i:04d}', 'session_id': 'S02', 'speaker_id': spk[i % 2],
+                    'reference_array': arrays[0],
+                    'audio_path': {'observation': {a: str(paths[a]) for a in arrays}},
+                    'start': {'original': start, 'observation': {a: start for a in arrays}},
+                    'end': {'original': end, 'observation': {a: end for a in arrays}},
+                    'start_orig': {'original': s_orig, 'observation': {a: s_orig for a in arrays}},
+                    'end_orig': {'original': s_orig + n_orig, 'observation': {a: s_orig + n_orig for a in arrays}},
+                    'num_samples_orig': {'observation': {a: n_orig for a in arrays}},
+                    'num_samples': {'observation': {a: end - start for a in arrays}}})
+    return exs, activity
+
+
+@pytest.mark.parametrize('multiarray', [False, True])
+def test_session_scheduler_equals_example_by_example(tmp_path, multiarray):
+    """rows f2/f3: batched, prefetching session driver == enhance_example + dump_audio per example"""
+    from pb_chime5_b200 import audio_io
+    from pb_chime5_b200.session import SessionScheduler
+    exs, activity = _disk_session(tmp_path)
+    enh = core.get_enhancer(multiarray=multiarray, context_samples=4000, wpe_tabs=2, wpe_iterations=1,
+                            bss_iterations=3)
+    enh.activity = activity
+    ref_dir, out_dir = tmp_path / 'ref', tmp_path / 'out'
+    ref_dir.mkdir()
+    for ex in exs:
+        x = enh.enhance_example(ex)
+        assert x.shape == (ex['num_samples_orig']['observation']['U01'],)
+        audio_io.dump_audio(x, ref_dir / f"{ex['example_id']}.wav")
+    sched = SessionScheduler(enh, enh._load_example, lambda ex: out_dir / f"{ex['example_id']}.wav",
+                             enh._finish_example, batch_size=3, window=8)
+    rep = sched.run(exs)
+    assert rep.done == len(exs) and not rep.failed and rep.batches == 2
+    for ex in exs:
+        a = (ref_dir / f"{ex['example_id']}.wav").read_bytes()
+        b = (out_dir / f"{ex['example_id']}.wav").read_bytes()
+        assert a == b, ex['example_id']
+    assert sched.run(exs).skipped == len(exs)                 # resume: nothing left to do

@@ -1,0 +1,139 @@
+"""CPU: wav I/O restatement (audio_io.py vs the reference's doctests), batch planning and the
+session driver's control flow (resume, failure isolation) with a stand-in enhancer."""
+import struct
+
+import numpy as np
+import pytest
+
+from pb_chime5_b200 import audio_io
+from pb_chime5_b200.session import SessionScheduler, plan_batches, stack_arrays
+
+
+def test_dump_audio_matches_reference_doctest(tmp_path):
+    # pb_chime5/io/audiowrite.py:32-38: [1, 2, -4, 4] -> peak normalised 16-bit PCM
+    p = tmp_path / 'a.wav'
+    audio_io.dump_audio(np.array([1, 2, -4, 4], dtype=np.float32), p)
+    got = audio_io.load_audio(p)
+    np.testing.assert_allclose(got, [0.24996948, 0.49996948, -0.99996948, 0.99996948], atol=1e-8)
+    assert audio_io.wav_info(p).bits == 16 and audio_io.wav_info(p).channels == 1
+    # audiowrite.py:40-46: without normalisation float values in [-1, 1) are written as they are
+    a = np.arange(10, dtype=np.float32) / 32
+    audio_io.dump_audio(a, p, normalize=False)
+    np.testing.assert_array_equal(audio_io.load_audio(p), a.astype(np.float64))
+    with pytest.raises(TypeError):
+        audio_io.dump_audio(np.array(['a']), p)
+
+
+def test_load_audio_slices_and_channels(tmp_path):
+    rng = np.random.default_rng(0)
+    x = (rng.integers(-32768, 32767, size=(3, 1000))).astype(np.int16)
+    p = tmp_path / 'm.wav'
+    audio_io.dump_audio(x, p, normalize=False)
+    full = audio_io.load_audio(p)
+    assert full.shape == (3, 1000) and full.dtype == np.float64
+    np.testing.assert_array_equal(full, x / 32768.0)
+    np.testing.assert_array_equal(audio_io.load_audio(p, start=100, stop=350), full[:, 100:350])
+    np.testing.assert_array_equal(audio_io.load_audio(p, start=900, stop=5000), full[:, 900:])
+    np.testing.assert_array_equal(audio_io.load_audio(p, start=10, frames=5), full[:, 10:15])
+    np.testing.assert_array_equal(audio_io.load_audio(p, dtype=np.int16), x)
+    y, sr = audio_io.load_audio(p, return_sample_rate=True)
+    assert sr == 16000
+    with pytest.raises(ValueError):
+        audio_io.load_audio(p, expected_sample_rate=8000)
+    out = np.empty((3, 250))
+    assert audio_io.load_audio(p, start=100, stop=350, out=out) is out
+    # IEEE float file with an extra chunk before the data
+    f32 = np.linspace(-1, 1, 64, dtype='<f4')
+    q = tmp_path / 'f.wav'
+    body = (b'WAVE' + b'fmt ' + struct.pack('<IHHIIHH', 16, 3, 1, 16000, 64000, 4, 32) +
+            b'LIST' + struct.pack('<I', 4) + b'abcd' + b'data' + struct.pack('<I', f32.nbytes) + f32.tobytes())
+    q.write_bytes(b'RIFF' + struct.pack('<I', len(body)) + body)
+    np.testing.assert_array_equal(audio_io.load_audio(q), f32.astype(np.float64))
+    bad = tmp_path / 'bad.wav'
+    bad.write_bytes(b'NIST_1A\n   1024\n' + bytes(100))
+    with pytest.raises(RuntimeError):
+        audio_io.load_audio(bad)
+
+
+def test_plan_batches_properties():
+    rng = np.random.default_rng(1)
+    lengths = [int(v) for v in rng.integers(5000, 400000, size=203)]
+    keys = [('S02',) if i % 3 else ('S09',) for i in range(203)]
+    batches = plan_batches(lengths, keys, batch_size=8, window=64, max_batch_samples=8 * 200000)
+    flat = [i for b in batches for i in b]
+    assert sorted(flat) == list(range(203))
+    for b in batches:
+        assert 1 <= len(b) <= 8
+        assert len({keys[i] for i in b}) == 1
+        assert len(b) * max(lengths[i] for i in b) <= 8 * 200000 or len(b) == 1
+        assert [lengths[i] for i in b] == sorted((lengths[i] for i in b), reverse=True)
+        assert max(b) // 64 == min(b) // 64                     # never crosses a window
+    assert plan_batches(lengths, keys, 8, 64, 8 * 200000) == batches
+    # padding waste stays small compared with taking the examples in order
+    waste = sum(len(b) * lengths[b[0]] - sum(lengths[i] for i in b) for b in batches) / sum(lengths)
+    naive = plan_batches(lengths, keys, 8, 1)                  # window 1: one example per batch
+    assert len(naive) == 203 and waste < 0.25
+    assert plan_batches([], None) == []
+
+
+def test_stack_arrays():
+    a, b = np.arange(8.).reshape(4, 2), np.arange(12.).reshape(4, 3)
+    assert stack_arrays([a, b], True).shape == (8, 2)
+    np.testing.assert_array_equal(stack_arrays([a, b], 'outer_array_mics'), np.concatenate([a[[0, -1], :2], b[[0, -1], :2]]))
+    assert stack_arrays([a, b], 'first_array_mics').shape == (2, 2)
+    with pytest.raises(ValueError):
+        stack_arrays([a, b], 'nope')
+
+
+class _FakeEnhancer:
+    def __init__(self):
+        self.calls = []
+
+    def enhance_observation_batch(self, obs_list, acts, spk, exs=None):
+        self.calls.append([e['example_id'] for e in exs])
+        if any(e.get('poison') for e in exs):
+            raise FloatingPointError('poisoned batch')
+        return [0.5 * o[0] for o in obs_list]
+
+
+def _examples(tmp_path, n):
+    exs = []
+    for i in range(n):
+        exs.append({'example_id': f'ex{i}', 'session_id': 'S02', 'num_samples': 1000 + 37 * i,
+                    'start': {'observation': {'U01': 0}}, 'end': {'observation': {'U01': 1000 + 37 * i}}})
+    return exs
+
+
+def test_session_scheduler_resume_and_failure_isolation(tmp_path):
+    exs = _examples(tmp_path, 11)
+    exs[4]['poison'] = True
+    exs[7]['missing'] = True
+
+    def load(ex):
+        if ex.get('missing'):
+            raise FileNotFoundError(ex['example_id'])
+        n = ex['num_samples']
+        return np.full((2, n), 0.25) * np.sign(np.sin(np.arange(n))), {'P05': np.ones(n, bool), 'Noise': np.ones(n, bool)}, 'P05'
+
+    path = lambda ex: tmp_path / 'out' / f"{ex['example_id']}.wav"     # noqa: E731
+    enh = _FakeEnhancer()
+    rep = SessionScheduler(enh, load, path, batch_size=4, window=8, skip_existing=True).run(exs)
+    assert rep.done == 9 and rep.skipped == 0
+    assert sorted(e for e, _ in rep.failed) == ['ex4', 'ex7']
+    for i in range(11):
+        assert path(exs[i]).exists() == (i not in (4, 7))
+    x = audio_io.load_audio(path(exs[3]))
+    assert x.shape == (1000 + 37 * 3,) and abs(np.abs(x).max() - 32767 / 32768) < 1e-9      # dump_audio normalisation
+    # the poisoned batch was retried example by example
+    assert any(c == ['ex4'] for c in enh.calls)
+    # resume: only the two failures are tried again
+    for e in exs:
+        e.pop('poison', None), e.pop('missing', None)
+    enh2 = _FakeEnhancer()
+    rep2 = SessionScheduler(enh2, load, path, batch_size=4, window=8, skip_existing=True).run(exs)
+    assert rep2.skipped == 9 and rep2.done == 2 and not rep2.failed
+    assert sorted(i for c in enh2.calls for i in c) == ['ex4', 'ex7']
+    # strict mode keeps the reference behaviour: the first failure raises
+    exs[0]['missing'] = True
+    with pytest.raises(FileNotFoundError):
+        SessionScheduler(_FakeEnhancer(), load, path, batch_size=4, skip_existing=False, strict=True).run(exs)
