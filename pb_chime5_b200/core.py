@@ -472,8 +472,7 @@ class Enhancer:
         target_speaker_index = tuple(ex_array_activity.keys()).index(speaker_id)
         sc = ec = 0
         if self.bf_drop_context:
-            sc, ec = start_end_context_frames(ex, stft_size=self.stft_size, stft_shift=self.stft_shift,
-                                              stft_fading=self.stft_fading)
+            sc, ec = self._context_frames(ex)
         ivec = lambda v: torch.tensor([v], dtype=torch.int32, device=Y.device)
         X, post = self.enhance_stft_batch(Y, act, ivec(target_speaker_index), ivec(sc), ivec(min(ec, T)),
                                           return_masks=True)
@@ -527,8 +526,7 @@ class Enhancer:
             ti.append(tuple(a.keys()).index(speaker_ids[b]))
             s_ctx = e_ctx = 0
             if self.bf_drop_context and exs is not None:
-                s_ctx, e_ctx = start_end_context_frames(exs[b], stft_size=self.stft_size,
-                                                        stft_shift=self.stft_shift, stft_fading=self.stft_fading)
+                s_ctx, e_ctx = self._context_frames(exs[b])
             sc.append(s_ctx)
             ec.append(min(e_ctx, frames[b]))
         ivec = lambda v: torch.tensor(v, dtype=torch.int32, device=dev)
@@ -600,41 +598,57 @@ class Enhancer:
                     'projection of the human annotations.') from None
         return reference_array
 
+    # -- example-dict layout (CHiME-5 json: per-array sample indices; core_chime6.py overrides) --
+    def _context_frames(self, ex):
+        return start_end_context_frames(ex, stft_size=self.stft_size, stft_shift=self.stft_shift,
+                                        stft_fading=self.stft_fading)
+
+    def _bounds(self, ex, array):
+        """(start, stop) samples of the segment (with context) in `array`'s recording"""
+        return ex['start']['observation'][array], ex['end']['observation'][array]
+
+    def _orig(self, ex, reference_array):
+        """(start_orig, num_samples_orig) of the utterance without context"""
+        return (ex['start_orig']['observation'][reference_array],
+                ex['num_samples_orig']['observation'][reference_array])
+
+    def _session_activity(self, ex, reference_array):
+        return self.activity[ex['session_id']][reference_array]
+
     def _load_example(self, ex):
         """core.py:396-498: slice the activity, load the audio of the selected arrays ->
         (obs (D, N) float64, ex_array_activity {speaker: (N,) bool}, speaker_id)."""
         from .audio_io import load_audio
         from .session import stack_arrays
 
-        session_id = ex['session_id']
-        reference_array = self._reference_array(ex)
-        array_start = ex['start']['observation'][reference_array]
-        array_end = ex['end']['observation'][reference_array]
+        reference_array = self._reference_array(ex) if self._needs_reference_array() else None
+        array_start, array_end = self._bounds(ex, reference_array)
         ex_array_activity = {
             k: arr[array_start:min(array_end, len(arr))]
-            for k, arr in self.activity[session_id][reference_array].items()}
+            for k, arr in self._session_activity(ex, reference_array).items()}
 
         def load(array):
-            x = load_audio(ex['audio_path']['observation'][array],
-                           start=ex['start']['observation'][array],
-                           stop=ex['end']['observation'][array])
+            start, stop = self._bounds(ex, array)
+            x = load_audio(ex['audio_path']['observation'][array], start=start, stop=stop)
             return x[None] if x.ndim == 1 else x
 
         if self.multiarray is False:
-            obs = load(reference_array)
+            obs = load(self._reference_array(ex))
         else:
             obs = stack_arrays([load(a) for a in sorted(ex['audio_path']['observation'].keys())],
                                self.multiarray)                              # 'ACN->A*CN'
         return obs, ex_array_activity, ex['speaker_id']
 
+    def _needs_reference_array(self):
+        return True          # CHiME-5: activity and sample indices are per array
+
     def _finish_example(self, ex, x_hat):
         """cut the context again (core.py:500-505)"""
         if self.context_samples > 0:
-            reference_array = self._reference_array(ex)
-            start_orig = ex['start_orig']['observation'][reference_array]
-            start = ex['start']['observation'][reference_array]
+            reference_array = self._reference_array(ex) if self._needs_reference_array() else None
+            start_orig, num_samples_orig = self._orig(ex, reference_array)
+            start, _ = self._bounds(ex, reference_array)
             start_context = start_orig - start
-            num_samples_orig = ex['num_samples_orig']['observation'][reference_array]
             x_hat = x_hat[..., start_context:start_context + num_samples_orig]
         return x_hat
 

@@ -98,12 +98,17 @@ class SessionScheduler:
     # -- planning ---------------------------------------------------------------------------
     @staticmethod
     def example_length(ex):
-        """samples of the reference array's segment (metadata only, no file access)"""
+        """samples of the segment (metadata only, no file access): CHiME-6 style flat indices,
+        CHiME-5 style per-array indices, else 'num_samples', else 0 (unknown: keeps the order)"""
         try:
-            arr = ex.get('reference_array') or sorted(ex['start']['observation'])[0]
-            return int(ex['end']['observation'][arr]) - int(ex['start']['observation'][arr])
-        except (KeyError, TypeError, AttributeError):
-            return int(ex.get('num_samples', 0)) if isinstance(ex, dict) else 0
+            start, end = ex['start'], ex['end']
+            if isinstance(start, dict):
+                arr = ex.get('reference_array') or sorted(start['observation'])[0]
+                start, end = start['observation'][arr], end['observation'][arr]
+            return int(end) - int(start)
+        except (KeyError, TypeError, AttributeError, ValueError):
+            n = ex.get('num_samples', 0) if isinstance(ex, dict) else 0
+            return int(n) if isinstance(n, (int, float)) else 0
 
     def plan(self, examples):
         todo, skipped = [], 0

@@ -95,6 +95,28 @@ def test_reference_signature_if_available():
     assert [f.name for f in dataclasses.fields(core.Enhancer)] == json.loads(out[-1])
 
 
+def test_chime6_front_door_signature_if_available():
+    """pb_chime5/core_chime6.py:573-635: keyword order and defaults are API (sacred reads them)"""
+    from pb_chime5_b200 import core_chime6
+    assert core_chime6.WPE is core.WPE and core_chime6.GSS is core.GSS and core_chime6.Beamformer is core.Beamformer
+    assert list(core_chime6.signature_defaults())[:3] == ['multiarray', 'context_samples', 'reference_array']
+    assert core_chime6.signature_defaults()['database_path'].endswith('chime6.json')
+    ex = {'start': 1000, 'end': 9000, 'start_orig': 3000, 'end_orig': 8000}
+    assert core_chime6.start_end_context_frames(ex, 1024, 256, True) == \
+        (core.samples_to_stft_frames(2000, 1024, 256, fading=True), core.samples_to_stft_frames(1000, 1024, 256, fading=True))
+    from oracle import refboot
+    if not refboot.available():
+        return
+    code = ("import warnings; warnings.filterwarnings('ignore');"
+            "from oracle import refboot; refboot.boot();"
+            "import inspect, pb_chime5.core_chime6 as c, json;"
+            "print(json.dumps([[k, repr(v.default)] for k, v in inspect.signature(c.get_enhancer).parameters.items() if k != 'database_path']))")
+    out = subprocess.run([sys.executable, '-c', code], cwd=ROOT, capture_output=True, text=True, check=True).stdout.splitlines()
+    import json
+    mine = [[k, repr(v)] for k, v in core_chime6.signature_defaults().items() if k != 'database_path']
+    assert mine == json.loads(out[-1])
+
+
 def test_activity_framing_matches_oracle_and_doctest():
     vad = np.array([0, 0, 0, 0, 0, 1, 1, 0, 1, 0, 0, 0, 0, 0])
     assert core.activity_time_to_frequency(vad, 4, 2, True).tolist() == \
