@@ -170,3 +170,49 @@ def test_wpe_i8_illconditioned_bins_are_redone_in_float64():
     lib.gss_debug_wpe_config(0, -1.0)
     x1 = ops.wpe(Ysub, 10, 2, 1).cpu().numpy()
     assert np.isfinite(xi).all() and rel_err(xi, x1) < 1e-3
+
+
+def test_cfg3_like_ragged_batch_through_int8_path():
+    """BASELINE configs[2] scaled down: 24 channels, dev-shaped (ragged) utterance lengths, full
+    WPE (INT8 correlation build) + GSS + GEV+BAN: every utterance of the padded batch equals its
+    single-utterance run bit for bit, and the single runs meet the parity bar against the oracle."""
+    from pb_chime5_b200 import core
+    dev = torch.device('cuda')
+    lib = _lib.lib()
+    lens = [941, 520, 333]
+    Tmax, D, F, K = 941, 24, 3, 5
+    enh = core.get_enhancer(wpe_tabs=10, wpe_iterations=3, bss_iterations=10, bf='gev_ban')
+    Ypad = torch.zeros((len(lens), F, D, Tmax), dtype=torch.complex64, device=dev)
+    Apad = torch.zeros((len(lens), K, Tmax), dtype=torch.uint8, device=dev)
+    singles, inputs = [], []
+    iv = lambda v: torch.tensor([v], dtype=torch.int32, device=dev)   # noqa: E731
+    lib.gss_debug_wpe_redo_count(1)
+    for b, T in enumerate(lens):
+        obs, act = synth.make_utterance(900 + b, D=D, T=T, F=F, K=K)
+        Y = ops.pack_dtf_to_fdt(torch.from_numpy(obs).to(dev)[None])
+        A = torch.from_numpy(act.astype(np.uint8))[None].to(dev)
+        Ypad[b, :, :, :T] = Y[0]
+        Ypad[b, :, :, T:] = 3.0
+        Apad[b, :, :T] = A[0]
+        singles.append(enh.enhance_stft_batch(Y, A, iv(0), iv(3), iv(3), return_masks=True))
+        inputs.append((obs, act))
+    redone_single = lib.gss_debug_wpe_redo_count(1)
+    ti = torch.zeros(len(lens), dtype=torch.int32, device=dev)
+    c3 = torch.full((len(lens),), 3, dtype=torch.int32, device=dev)
+    X, post = enh.enhance_stft_batch(Ypad, Apad, ti, c3, c3, return_masks=True, frames=lens)
+    assert lib.gss_debug_wpe_redo_count(1) == redone_single
+    for b, T in enumerate(lens):
+        Xs, ps = singles[b]
+        assert torch.equal(post[b, :, :, :T], ps[0]) and torch.equal(X[b, :, :T], Xs[0])
+        assert float(post[b, :, :, T:].abs().max()) == 0 and float(X[b, :, T:].abs().max()) == 0
+    # oracle parity of the longest utterance (WPE + guided EM masks; GEV output by magnitude)
+    obs, act = inputs[0]
+    ref = oracle.enhance_stft(obs.astype(np.complex128), act, 0,
+                              wpe=dict(taps=10, delay=2, iterations=3, psd_context=0), gss_iterations=10,
+                              bf='gev_ban', start_context_frames=3, end_context_frames=3)
+    m = ops.unpack_fkt_to_ktf(singles[0][1])[0].cpu().numpy()
+    m[:, :3] = 0
+    m[:, -3:] = 0
+    assert np.abs(m - ref['masks']).max() < 1e-4
+    Xd = ops.unpack_ft_to_tf(singles[0][0])[0].cpu().numpy()
+    assert rel_err(np.abs(Xd), np.abs(ref['X_hat'])) < 1e-4
