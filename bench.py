@@ -6,7 +6,7 @@
 Metric (BASELINE.json): utterances/sec for 15 s, 24-channel, 513-bin STFT
 segments.  Workload = BASELINE.json configs[1] ("cfg2"): D=24, T=941, F=513,
 K=5 classes, WPE taps=10 delay=2 iterations=3, 100 EM iterations, MVDR-Souden
-+ BAN -- `--batch` such utterances per GPU and step.
++ BAN -- `--batch` such utterances per GPU and step (default 8).
 
 One JSON line on stdout (rank 0).  See DESIGN.md "Measurement" for the meaning
 of every field.  A "step" is one pass of the hot path over one batch.
@@ -426,7 +426,7 @@ def main():
     ap.add_argument('--steps', type=int, default=4)
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
-    ap.add_argument('--batch', type=int, default=0, help='utterances per GPU per step (0: 4 for cfg2, 32 for cfg1, 1 for cfg5)')
+    ap.add_argument('--batch', type=int, default=0, help='utterances per GPU per step (0: 8 for cfg2, 32 for cfg1, 1 for cfg5)')
     ap.add_argument('--cpu-bins', type=int, default=0, help='frequency bins per process in a CPU sample (0 = 8 for the cpu_baseline of the GPU arm, 4 per step for --impl reference)')
     ap.add_argument('--no-cpu', action='store_true')
     ap.add_argument('--workload', default='cfg2', choices=sorted(WORKLOADS),
@@ -435,7 +435,7 @@ def main():
     global CFG, WORKLOAD
     CFG, WORKLOAD = WORKLOADS[args.workload]
     if args.batch <= 0:
-        args.batch = {'cfg2': 4, 'cfg1': 32, 'cfg5': 1}[args.workload]
+        args.batch = {'cfg2': 8, 'cfg1': 32, 'cfg5': 1}[args.workload]
     if args.impl == 'reference':
         run_reference(args)
     else:

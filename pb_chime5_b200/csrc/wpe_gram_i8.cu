@@ -474,11 +474,7 @@ int wpe_gram_i8_run(const float2* Y, const double* inv, cd* Raug, double* rdiag,
                     const WpeI8Ws& ws, int variant, cudaStream_t st) {
     const GiDims g = gi_dims(m.D, m.T, m.LD);
     const GiPlan plan = gi_plan(m.D, m.LD);
-    static bool attr_done = false;
-    if (!attr_done) {
-        GSS_CUDA(cudaFuncSetAttribute(wpe_gram_i8_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, GI_SMEM));
-        attr_done = true;
-    }
+    GSS_CUDA(cudaFuncSetAttribute(wpe_gram_i8_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, GI_SMEM));   // per device
     const int half = g.NRp >> 1;
     // bins per chunk: as many as the scratch holds, rounded down to whole waves of the persistent CTAs
     int cbins = ws.chunk_bins;

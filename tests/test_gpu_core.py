@@ -499,3 +499,22 @@ def test_chime6_front_door_equals_chime5_layout(tmp_path):
     r = SessionScheduler(enh6, enh6._load_example, lambda e: out / f"{e['example_id']}.wav", enh6._finish_example,
                          batch_size=2).run(flats)
     assert r.done == 2 and not r.failed
+
+
+def test_rttm_front_door_session(tmp_path):
+    """row f4: core_chime6_rttm.get_enhancer(...).enhance_session on a small fake CHiME-6 tree:
+    one wav per RTTM segment, equal to enhance_example + dump_audio"""
+    from pb_chime5_b200 import audio_io, core_chime6_rttm as r
+    from test_session_io import _fake_chime6
+    chime6_dir, rttm = _fake_chime6(tmp_path)
+    enh = r.get_enhancer(str(rttm), str(rttm), chime6_dir=str(chime6_dir), multiarray=True, context_samples=4000,
+                         wpe_tabs=2, wpe_iterations=1, bss_iterations=3)
+    out = tmp_path / 'enh'
+    rep = enh.enhance_session('S02', out, batch_size=2)
+    assert rep.done == 3 and not rep.failed
+    for ex in enh.get_iterator('S02'):
+        x = enh.enhance_example(ex)
+        assert x.shape == (ex['num_samples_orig'],)
+        ref = tmp_path / 'ref.wav'
+        audio_io.dump_audio(x, ref)
+        assert (out / 'S02' / f"{ex['example_id']}.wav").read_bytes() == ref.read_bytes()

@@ -77,7 +77,7 @@ def scaled_err(got, ref, LD, Y, inv):
 
 
 @pytest.mark.parametrize('D,taps,T,F', [(24, 10, 941, 3), (8, 10, 191, 4), (24, 2, 100, 2), (6, 10, 64, 2),
-                                        (5, 12, 333, 2), (24, 20, 700, 1)])
+                                        (5, 12, 333, 2), (24, 20, 700, 1), (8, 6, 17, 2), (12, 4, 33, 1)])
 def test_gram_i8_matches_float64(D, taps, T, F):
     dev = torch.device('cuda')
     delay, B = 2, 2
@@ -204,7 +204,8 @@ def test_cfg3_like_ragged_batch_through_int8_path():
     for b, T in enumerate(lens):
         Xs, ps = singles[b]
         assert torch.equal(post[b, :, :, :T], ps[0]) and torch.equal(X[b, :, :T], Xs[0])
-        assert float(post[b, :, :, T:].abs().max()) == 0 and float(X[b, :, T:].abs().max()) == 0
+        if T < Tmax:
+            assert float(post[b, :, :, T:].abs().max()) == 0 and float(X[b, :, T:].abs().max()) == 0
     # oracle parity of the longest utterance (WPE + guided EM masks; GEV output by magnitude)
     obs, act = inputs[0]
     ref = oracle.enhance_stft(obs.astype(np.complex128), act, 0,

@@ -1,6 +1,7 @@
 """CPU: wav I/O restatement (audio_io.py vs the reference's doctests), batch planning and the
 session driver's control flow (resume, failure isolation) with a stand-in enhancer."""
 import struct
+from pathlib import Path
 
 import numpy as np
 import pytest
@@ -137,3 +138,47 @@ def test_session_scheduler_resume_and_failure_isolation(tmp_path):
     exs[0]['missing'] = True
     with pytest.raises(FileNotFoundError):
         SessionScheduler(_FakeEnhancer(), load, path, batch_size=4, skip_existing=False, strict=True).run(exs)
+
+
+def _fake_chime6(tmp_path, total=60000):
+    """audio/dev/S02_U0{1,2}.CH{1,2}.wav + an RTTM with two speakers"""
+    rng = np.random.default_rng(3)
+    d = tmp_path / 'CHiME6' / 'audio' / 'dev'
+    d.mkdir(parents=True)
+    src = rng.standard_normal((2, total)) * (np.sin(np.arange(total) / 700.0 + np.array([[0.0], [2.0]])) > 0)
+    for a in ('U01', 'U02'):
+        for c in ('CH1', 'CH2'):
+            x = rng.standard_normal(2) @ src + 0.05 * rng.standard_normal(total)
+            audio_io.dump_audio(0.3 * x / np.abs(x).max(), d / f'S02_{a}.{c}.wav', normalize=False)
+    audio_io.dump_audio(np.zeros(10), d / 'S02_P05.wav', normalize=False)     # worn microphone: ignored
+    rttm = tmp_path / 'rttm'
+    rttm.write_text('SPEAKER S02_U06.ENH 1 0.50 0.60 <NA> <NA> 1 <NA> <NA>\n'
+                    'SPEAKER S02_U06.ENH 1 1.40 0.45 <NA> <NA> 2 <NA> <NA>\n'
+                    'SPEAKER S02_U06.ENH 1 2.20 0.70 <NA> <NA> 1 <NA> <NA>\n')
+    return tmp_path / 'CHiME6', rttm
+
+
+def test_rttm_front_door_plumbing(tmp_path):
+    from pb_chime5_b200 import core_chime6_rttm as r
+    chime6_dir, rttm = _fake_chime6(tmp_path)
+    assert r.parse_rttm(rttm) == {'S02_U06.ENH': {'1': [(8000, 17600), (35200, 46400)], '2': [(22400, 29600)]}}
+    assert r.RTTMDatabase.example_id('S02', 1, 100, 200) == 'S02_U06.-1-000000100_000000200'     # rttm.py:437
+    files = r.get_chime6_files(chime6_dir)
+    assert sorted(files['S02']) == ['U01', 'U02'] and [Path(f).name for f in files['S02']['U01']] == ['S02_U01.CH1.wav', 'S02_U01.CH2.wav']
+    assert len(r.get_chime6_files(chime6_dir, flat=True)['S02']) == 4
+    assert list(r.get_chime6_files(chime6_dir, worn=True)['S02']) == ['P05']
+    db = r.get_database(chime6_dir, rttm, 'first_array_mics')
+    exs = db.get_dataset_for_session('S02', audio_read=True, context_samples=4000)
+    assert [e['speaker_id'] for e in exs] == ['1', '1', '2'] and exs[0]['example_id'] == 'S02_U06.-1-000008000_000017600'
+    ex = exs[1]
+    assert (ex['start'], ex['end'], ex['start_orig'], ex['num_samples_orig']) == (31200, 50400, 35200, 11200)
+    assert ex['audio_data'].shape == (2, 19200) and [Path(p).name for p in ex['audio_path']] == ['S02_U01.CH1.wav', 'S02_U02.CH1.wav']
+    act = r.Activity(garbage_class=True, rttm=str(rttm))['S02']
+    assert list(act) == ['1', '2', 'Noise']
+    a = act['1'][7990:8010]
+    assert a.tolist() == [False] * 10 + [True] * 10 and act['Noise'][0:5].all() and not act['2'][0:100].any()
+    assert not r.Activity(garbage_class=False, rttm=str(rttm))['S02']['Noise'][0:9].any()
+    assert 'Noise' not in r.Activity(garbage_class=None, rttm=str(rttm))['S02']
+    sig = r.signature_defaults()
+    assert list(sig)[:5] == ['database_rttm', 'activity_rttm', 'chime6_dir', 'multiarray', 'context_samples']
+    assert sig['multiarray'] == 'outer_array_mics' and sig['activity_garbage_class'] is True
