@@ -230,7 +230,7 @@ def measure_wpe_gram(torch, _lib, ops, obs, c):
            'algorithmic_tflops_float64_dmma': alg_flops / (ms[0] * 1e-3) / 1e12,
            'unit': 'TOP/s', 'peak': 2 * bf16,
            'peak_source': '2 x measured dense bf16 (MEASURED_PEAKS.json; INT8 nominal = 2 x bf16 on B200)',
-           'note': 'the GEMM streams the digit planes from L2 (35 KB per 15 MMAs): L2-bandwidth bound, see DESIGN.md'}
+           'note': 'whole build (row scales + digit planes + GEMM); the GEMM is shared-memory-bandwidth bound at N = 96 tiles (TMEM holds five accumulators per tile), see DESIGN.md 4.3 and profiles/r1_mma_rate_probe.txt'}
     if int8_ops:
         res['achieved'] = int8_ops / (ms[1] * 1e-3) / 1e12
         res['frac'] = res['achieved'] / res['peak']
