@@ -31,8 +31,11 @@ def init_process_group(backend=None):
         os.environ.setdefault('MASTER_ADDR', '127.0.0.1')
         os.environ.setdefault('MASTER_PORT', '29500')
         if backend == 'nccl':
-            torch.cuda.set_device(int(os.environ.get('LOCAL_RANK', 0)))
-        dist.init_process_group(backend=backend)
+            local = int(os.environ.get('LOCAL_RANK', 0))
+            torch.cuda.set_device(local)
+            dist.init_process_group(backend=backend, device_id=torch.device('cuda', local))
+        else:
+            dist.init_process_group(backend=backend)
     return rank_world()
 
 
