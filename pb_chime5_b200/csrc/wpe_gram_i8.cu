@@ -33,8 +33,9 @@ namespace gss {
 
 constexpr int GI_NS = 5;                                 // int8 digit planes per value
 constexpr int GI_BM = 128;                               // real rows per tile (UMMA M)
-constexpr int GI_NMAX = 96;                              // real columns per tile: 5 accumulators x 96 <= 512 TMEM columns
-constexpr int GI_STAGES = 5;
+constexpr int GI_NMAX = 80;                              // real columns per tile: 5 accumulators x 80 + 2 x 40 columns of A planes <= 512 TMEM columns
+constexpr int GI_TMEM_A = GI_NS * GI_NMAX;               // first TMEM column of the A-plane buffers (two, 8 columns per plane)
+constexpr int GI_STAGES = 6;
 constexpr int GI_EPI_WARPS = 8;
 constexpr int GI_NT = 64 + 32 * GI_EPI_WARPS;            // warp 0 TMA, warp 1 MMA + TMEM alloc, warps 2..9 epilogue
 constexpr int GI_BLK_BYTES = GI_NS * 2 * 128;            // all planes of 8 rows x 32 frames: 1280
@@ -75,8 +76,7 @@ bool wpe_i8_applicable(int D, int T, int L) {
     for (int i = 0; i < tiles; ++i) {
         int C = std::min(DP2 + GI_BM * (i + 1), DP2 + 2 * LD);
         C = (C + 15) / 16 * 16;
-        const int nch = (C + GI_NMAX - 1) / GI_NMAX;
-        items += nch + (nch & 1);
+        items += (C + GI_NMAX - 1) / GI_NMAX;
     }
     return LD >= 48 && items <= GI_MAX_ITEMS;
 }
@@ -236,29 +236,22 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                  ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
 }
-// same, delivered to the same shared-memory offset (and mbarrier) of every CTA in `mask`
-__device__ __forceinline__ void bulk_g2s_mc(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar, uint16_t mask) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1], %2, [%3], %4;"
-                 ::"r"(dst), "l"(src), "r"(bytes), "r"(bar), "h"(mask) : "memory");
-}
-__device__ __forceinline__ uint32_t cluster_ctarank() {
-    uint32_t r;
-    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
-    return r;
-}
-__device__ __forceinline__ void cluster_sync_all() {
-    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
-}
-__device__ __forceinline__ void tc_commit_mc(uint32_t bar, uint16_t mask) {
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
-                 ::"r"(bar), "h"(mask) : "memory");
-}
 // one elected lane of a converged warp (the compiler then knows the region is single-threaded:
 // no uniformisation loops around the UTC* instructions)
 __device__ __forceinline__ bool elect_one() {
     uint32_t pred;
     asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
     return pred != 0;
+}
+// shared memory -> TMEM, 128 rows x 32 B (one digit plane of the A tile for one k-step): 8 TMEM columns
+__device__ __forceinline__ void tc_cp_128x256b(uint32_t taddr, uint64_t sdesc) {
+    asm volatile("tcgen05.cp.cta_group::1.128x256b [%0], %1;" ::"r"(taddr), "l"(sdesc) : "memory");
+}
+// D[tmem] (+)= A[tmem] B[smem]^T
+__device__ __forceinline__ void tc_mma_i8_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                 "tcgen05.mma.cta_group::1.kind::i8 [%0], [%1], %2, %3, p;\n\t}"
+                 ::"r"(tmem_d), "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
 }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
@@ -294,7 +287,8 @@ __device__ __forceinline__ uint32_t umma_idesc_i8(int n) {
 
 // ---------------------------------------------------------------------------------------------
 // the GEMM.  Persistent CTAs (one per SM) walk the (bin, tile) work items of the chunk; a tile is
-// 128 real rows x n <= 96 real columns, all five accumulators in TMEM (5 n <= 480 columns).
+// 128 real rows x n <= 80 real columns, all five accumulators in TMEM (5 n <= 400 columns) plus two
+// buffers of A planes (2 x 40 columns).
 // Roles: warp 0 = TMA producer, warp 1 = MMA issuer (+ TMEM alloc), warps 2..9 = epilogue (two
 // warps per TMEM lane quarter, alternating 16-column blocks).  The producer runs ahead into the
 // next tile while the epilogue drains TMEM; the MMA warp waits for the drain (bar_drain).
@@ -303,7 +297,7 @@ __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
 
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GI_NT, 1) wpe_gram_i8_kernel(const int8_t* __restrict__ slices, const int* __restrict__ ex,
+__global__ void __launch_bounds__(GI_NT, 1) wpe_gram_i8_kernel(const int8_t* __restrict__ slices, const int* __restrict__ ex,
                                                                cd* __restrict__ Raug, double* __restrict__ rdiag,
                                                                WpeDims m, GiDims g, GiPlan plan, size_t bf0, int nbins) {
     extern __shared__ __align__(128) unsigned char smem[];
@@ -311,18 +305,12 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GI_NT, 1) wpe_gram_i
     __shared__ uint32_t tmem_slot;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const uint32_t smem_base = smem_u32(smem);
-    // CTA pair (cluster of 2): both CTAs work on the same bin and row tile, on neighbouring column
-    // chunks; each loads half of the A planes and multicasts it to both (25 instead of 35 KB of
-    // L2 reads per CTA and stage).  Work index = (bin, pair of items).
-    const uint32_t crank = cluster_ctarank();
-    const int n_pairs = plan.n_items >> 1;
-    const int n_work = nbins * n_pairs;
-    const int w0 = blockIdx.x >> 1, wstep = gridDim.x >> 1;
+    const int n_work = nbins * plan.n_items;
     const size_t bin_bytes = (size_t)GI_NS * g.KB * g.NRp * 16;
     const size_t nrb = (size_t)(g.NRp >> 3);
 
     if (tid == 0) {
-        for (int s = 0; s < GI_STAGES; ++s) { mbar_init(smem_u32(&bar_full[s]), 1); mbar_init(smem_u32(&bar_empty[s]), 2); }
+        for (int s = 0; s < GI_STAGES; ++s) { mbar_init(smem_u32(&bar_full[s]), 1); mbar_init(smem_u32(&bar_empty[s]), 1); }
         mbar_init(smem_u32(&bar_acc), 1);
         mbar_init(smem_u32(&bar_drain), GI_EPI_WARPS);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -333,7 +321,6 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GI_NT, 1) wpe_gram_i
     }
     tc_fence_before();
     __syncthreads();
-    cluster_sync_all();                                    // the peer's barriers are initialised before anything is sent to them
     tc_fence_after();
     const uint32_t tmem = tmem_slot;
 
@@ -341,9 +328,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GI_NT, 1) wpe_gram_i
         // ===== TMA producer: two bulk copies per stage (A: 20 KB, B: n * 160 B) =====
         if (lane == 0) {
             int kg = 0;                                    // k-steps issued so far (all tiles)
-            for (int w = w0; w < n_work; w += wstep) {
-                const int bl = w / n_pairs;
-                const GiItem it = plan.items[2 * (w - bl * n_pairs) + crank];
+            for (int w = blockIdx.x; w < n_work; w += gridDim.x) {
+                const int bl = w / plan.n_items;
+                const GiItem it = plan.items[w - bl * plan.n_items];
                 const int Tv = wpe_valid_frames(m, bf0 + bl);
                 const int nk = min(g.KB >> 1, (Tv + 31) >> 5);
                 const int8_t* __restrict__ sl = slices + (size_t)bl * bin_bytes;
@@ -354,24 +341,25 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GI_NT, 1) wpe_gram_i
                     const uint32_t full = smem_u32(&bar_full[st]);
                     mbar_expect_tx(full, stage_tx);
                     const uint32_t a_dst = smem_base + st * GI_STAGE_BYTES, b_dst = a_dst + GI_A_STAGE;
-                    // my half of the A planes (64 rows) to both CTAs, my B planes to me
-                    bulk_g2s_mc(a_dst + crank * (GI_A_STAGE / 2),
-                                sl + ((size_t)ks * nrb + (it.r0 >> 3) + crank * (GI_BM / 16)) * GI_BLK_BYTES, GI_A_STAGE / 2, full, 3);
+                    bulk_g2s(a_dst, sl + ((size_t)ks * nrb + (it.r0 >> 3)) * GI_BLK_BYTES, GI_BLK_BYTES * (GI_BM / 8), full);
                     bulk_g2s(b_dst, sl + ((size_t)ks * nrb + (it.c0 >> 3)) * GI_BLK_BYTES, GI_BLK_BYTES * (it.n / 8), full);
                 }
             }
         }
     } else if (warp == 1) {
-        // ===== MMA issuer: 15 digit-pair MMAs per stage, accumulator of order p + q at column (p + q) n.
+        // ===== MMA issuer.  Per stage: the five A planes go shared memory -> TMEM once (tcgen05.cp),
+        // then the 15 digit-pair MMAs read A from TMEM and only B from shared memory (with A in shared
+        // memory every MMA re-read 4 KB of it and the kernel was shared-memory-bandwidth bound).
+        // Accumulator of order p + q at TMEM column (p + q) n; A planes double buffered at GI_TMEM_A.
         // The whole warp walks the loop (waits), one elected lane issues.
         {
             // descriptor without the address: LBO = 128 B (k halves), SBO = 1280 B (8-row groups), version 1
             const uint64_t desc_hi = ((uint64_t)((128u >> 4) & 0x3FFFu) << 16) | ((uint64_t)(((uint32_t)GI_BLK_BYTES >> 4) & 0x3FFFu) << 32) |
                                      ((uint64_t)1 << 46);
             int kg = 0, tile = 0;
-            for (int w = w0; w < n_work; w += wstep) {
-                const int bl = w / n_pairs;
-                const GiItem it = plan.items[2 * (w - bl * n_pairs) + crank];
+            for (int w = blockIdx.x; w < n_work; w += gridDim.x) {
+                const int bl = w / plan.n_items;
+                const GiItem it = plan.items[w - bl * plan.n_items];
                 const int n = it.n;
                 const int Tv = wpe_valid_frames(m, bf0 + bl);
                 const int nk = min(g.KB >> 1, (Tv + 31) >> 5);
@@ -385,14 +373,17 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GI_NT, 1) wpe_gram_i
                     if (elect_one()) {
                         const uint32_t a_src = smem_base + st * GI_STAGE_BYTES, b_src = a_src + GI_A_STAGE;
                         const uint64_t a0 = desc_hi | (uint64_t)((a_src >> 4) & 0x3FFFu), b0 = desc_hi | (uint64_t)((b_src >> 4) & 0x3FFFu);
+                        const uint32_t ta = tmem + (uint32_t)(GI_TMEM_A + (kg & 1) * (GI_NS * 8));
                         const uint32_t acc0 = ks > 0 ? 1u : 0u;
+#pragma unroll
+                        for (int p = 0; p < GI_NS; ++p) tc_cp_128x256b(ta + (uint32_t)(p * 8), a0 + (uint64_t)(p * 16));
 #pragma unroll
                         for (int p = 0; p < GI_NS; ++p)
 #pragma unroll
                             for (int q = 0; q + p < GI_NS; ++q)   // planes are 256 B apart: +16 in the address field
-                                tc_mma_i8(tmem + (uint32_t)((p + q) * n), a0 + (uint64_t)(p * 16), b0 + (uint64_t)(q * 16), idesc,
-                                          p > 0 ? 1u : acc0);
-                        tc_commit_mc(smem_u32(&bar_empty[st]), 3);   // stage free (in both CTAs) once these MMAs have read it
+                                tc_mma_i8_ts(tmem + (uint32_t)((p + q) * n), ta + (uint32_t)(p * 8), b0 + (uint64_t)(q * 16), idesc,
+                                             p > 0 ? 1u : acc0);
+                        tc_commit(smem_u32(&bar_empty[st]));   // stage free once the copies and MMAs have read it
                     }
                     __syncwarp();
                 }
@@ -407,9 +398,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GI_NT, 1) wpe_gram_i
         const int q = warp & 3;                            // TMEM lane quarter this warp may access
         const int sub = ew >> 2;                           // which of the two warps of the quarter
         int tile = 0;
-        for (int w = w0; w < n_work; w += wstep) {
-            const int bl = w / n_pairs;
-            const GiItem it = plan.items[2 * (w - bl * n_pairs) + crank];
+        for (int w = blockIdx.x; w < n_work; w += gridDim.x) {
+            const int bl = w / plan.n_items;
+            const GiItem it = plan.items[w - bl * plan.n_items];
             const int n = it.n;
             const size_t bf = bf0 + bl;
             const int Tv = wpe_valid_frames(m, bf);
@@ -480,7 +471,6 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GI_NT, 1) wpe_gram_i
     }
     tc_fence_before();
     __syncthreads();
-    cluster_sync_all();                                    // nothing is in flight to the peer any more
     if (warp == 1) {
         tc_fence_after();
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(512) : "memory");
@@ -498,9 +488,7 @@ static GiPlan gi_plan(int D, int LD) {
     for (int i = tiles - 1; i >= 0; --i) {
         int C = std::min(DP2 + GI_BM * (i + 1), DP2 + 2 * LD);
         C = (C + 15) / 16;                                 // 16-column units
-        int nch = (C * 16 + GI_NMAX - 1) / GI_NMAX;
-        nch += nch & 1;                                    // CTA pairs: chunks 2p and 2p + 1 share the row tile
-        if (nch > C) nch = C;                              // (C >= 2 always: at least 32 columns)
+        const int nch = (C * 16 + GI_NMAX - 1) / GI_NMAX;
         int c0 = 0;
         for (int c = 0; c < nch; ++c) {
             const int w = C / nch + (c < C % nch ? 1 : 0);
@@ -522,9 +510,8 @@ int wpe_gram_i8_run(const float2* Y, const double* inv, cd* Raug, double* rdiag,
     // bins per chunk: as many as the scratch holds, rounded down to whole waves of the persistent CTAs
     int cbins = ws.chunk_bins;
     {
-        const int pairs = plan.n_items / 2, clusters = num_sms() / 2;
-        const int waves = cbins * pairs / clusters;
-        if (waves >= 1) cbins = std::max(1, waves * clusters / pairs);
+        const int waves = cbins * plan.n_items / num_sms();
+        if (waves >= 1) cbins = std::max(1, waves * num_sms() / plan.n_items);
     }
     for (int b0 = 0; b0 < BF; b0 += cbins) {
         const int nb = std::min(cbins, BF - b0);
@@ -533,7 +520,7 @@ int wpe_gram_i8_run(const float2* Y, const double* inv, cd* Raug, double* rdiag,
         dim3 sg((half * g.KB + 255) / 256, nb);
         wpe_i8_slice_kernel<<<sg, 256, 0, st>>>(Y, ws.mu, ws.ex, ws.slices, m, g, (size_t)b0);
         GSS_LAUNCH_CHECK("wpe_i8_slice_kernel");
-        const int grid = 2 * std::min((plan.n_items / 2) * nb, num_sms() / 2);        // CTA pairs
+        const int grid = std::min(plan.n_items * nb, num_sms());
         wpe_gram_i8_kernel<<<grid, GI_NT, GI_SMEM, st>>>(ws.slices, ws.ex, Raug, rdiag, m, g, plan, (size_t)b0, nb);
         GSS_LAUNCH_CHECK("wpe_gram_i8_kernel");
     }
