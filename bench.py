@@ -220,7 +220,7 @@ def measure_wpe_gram(torch, _lib, ops, obs, c):
     # executed INT8 work: 15 digit-pair GEMMs over the real-stacked lower trapezoid tiles
     alg_flops = B * F * (8.0 * LD * LD * T + 8.0 * LD * D * T)
     tiles = -(-2 * LD // 128)
-    cols = sum(min(2 * 24 + 128 * (i + 1), 2 * 24 + 2 * LD) for i in range(tiles)) if D == 24 else None
+    cols = sum(min(2 * 24 + 128 * (i + 1), 2 * 24 + 2 * LD) for i in range(tiles)) if D == 24 else None   # D = 24: no row padding
     int8_ops = B * F * 15 * 2.0 * 128 * cols * (-(-T // 32) * 32) if cols else None
     peaks_file = ROOT / 'MEASURED_PEAKS.json'
     bf16 = json.loads(peaks_file.read_text()).get('bf16_tflops') if peaks_file.exists() else 1590.0
@@ -230,7 +230,7 @@ def measure_wpe_gram(torch, _lib, ops, obs, c):
            'algorithmic_tflops_float64_dmma': alg_flops / (ms[0] * 1e-3) / 1e12,
            'unit': 'TOP/s', 'peak': 2 * bf16,
            'peak_source': '2 x measured dense bf16 (MEASURED_PEAKS.json; INT8 nominal = 2 x bf16 on B200)',
-           'note': 'whole build (row scales + digit planes + GEMM); the GEMM is shared-memory-bandwidth bound at N = 96 tiles (TMEM holds five accumulators per tile), see DESIGN.md 4.3 and profiles/r1_mma_rate_probe.txt'}
+           'note': 'whole build (row scales + digit planes + GEMM); GEMM tiles are 128 x 80 (TMEM holds five accumulators + the A planes), epilogue not overlapped; see DESIGN.md 4.3 and profiles/r1_mma_rate_probe.txt'}
     if int8_ops:
         res['achieved'] = int8_ops / (ms[1] * 1e-3) / 1e12
         res['frac'] = res['achieved'] / res['peak']

@@ -25,7 +25,7 @@
 // Kernels: wpe_i8_scale_kernel (row maxima -> exponents, sqrt(inv)), wpe_i8_slice_kernel
 // (digit planes in the canonical no-swizzle K-major UMMA layout, so tiles are plain 1-D bulk
 // copies), wpe_gram_i8_kernel (persistent; TMA producer warp / MMA issuer warp / 8 epilogue
-// warps, 5-stage mbarrier pipeline, TMEM accumulators).
+// warps, 6-stage mbarrier pipeline, A planes and accumulators in TMEM).
 #include "wpe_i8.cuh"
 #include <algorithm>
 
@@ -156,7 +156,7 @@ __device__ __forceinline__ unsigned gi_pack4(unsigned a, unsigned b, unsigned c,
     return __byte_perm(ab, cdv, 0x5410) ^ 0x80808080u;     // offset-binary digit -> two's complement
 }
 
-__global__ void __launch_bounds__(256) wpe_i8_slice_kernel(const float2* __restrict__ Y, const double* __restrict__ mu,
+__global__ void __launch_bounds__(256, 3) wpe_i8_slice_kernel(const float2* __restrict__ Y, const double* __restrict__ mu,
                                                            const int* __restrict__ ex, int8_t* __restrict__ slices,
                                                            WpeDims m, GiDims g, size_t bf0) {
     const int half = g.NRp >> 1;
