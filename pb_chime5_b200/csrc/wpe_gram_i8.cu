@@ -258,12 +258,6 @@ __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::
 __device__ __forceinline__ void tc_commit(uint32_t bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
-// D[tmem] (+)= A[smem] B[smem]^T, INT8 x INT8 -> INT32, M = 128, K = 32
-__device__ __forceinline__ void tc_mma_i8(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
-    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
-                 "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n\t}"
-                 ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
-}
 __device__ __forceinline__ void tc_ld16(uint32_t taddr, int (&v)[16]) {
     asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
                  : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
@@ -272,13 +266,10 @@ __device__ __forceinline__ void tc_ld16(uint32_t taddr, int (&v)[16]) {
 }
 __device__ __forceinline__ void tc_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
-// shared-memory matrix descriptor, K-major, no swizzle (cute::UMMA::SmemDescriptor, mma_sm100_desc.hpp):
-// start address, leading byte offset (between the two 16 B k-chunks), stride byte offset (between
-// 8-row groups), all >> 4; version 1 (bits 46..47); layout type 0 (bits 61..63).
-__device__ __forceinline__ uint64_t umma_desc(uint32_t saddr, uint32_t lbo, uint32_t sbo) {
-    return (uint64_t)((saddr >> 4) & 0x3FFFu) | ((uint64_t)((lbo >> 4) & 0x3FFFu) << 16) |
-           ((uint64_t)((sbo >> 4) & 0x3FFFu) << 32) | ((uint64_t)1 << 46);
-}
+// Shared-memory matrix descriptors (cute::UMMA::SmemDescriptor, mma_sm100_desc.hpp), K-major, no
+// swizzle: start address, leading byte offset (between the two 16 B k-chunks), stride byte offset
+// (between 8-row groups), all >> 4; version 1 (bits 46..47); layout type 0 (bits 61..63).  Built in
+// the issue loop from a constant upper part and the stage / plane address.
 // instruction descriptor (cute::UMMA::InstrDescriptor): D = S32 (2 << 4), A = B = signed 8 bit (1 << 7, 1 << 10),
 // both K-major, N >> 3 at bit 17, M >> 4 at bit 24.
 __device__ __forceinline__ uint32_t umma_idesc_i8(int n) {
@@ -502,7 +493,7 @@ static GiPlan gi_plan(int D, int LD) {
 }
 
 int wpe_gram_i8_run(const float2* Y, const double* inv, cd* Raug, double* rdiag, const WpeDims& m, int BF,
-                    const WpeI8Ws& ws, int variant, cudaStream_t st) {
+                    const WpeI8Ws& ws, int /*variant*/, cudaStream_t st) {
     const GiDims g = gi_dims(m.D, m.T, m.LD);
     const GiPlan plan = gi_plan(m.D, m.LD);
     GSS_CUDA(cudaFuncSetAttribute(wpe_gram_i8_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, GI_SMEM));   // per device
