@@ -210,3 +210,52 @@ def test_synth_is_seeded_and_shaped():
     assert np.array_equal(a1, a2) and np.array_equal(m1, m2)
     assert m1[-1].all()                              # 'Noise' garbage class always active
     assert (m1[:-1].sum(axis=1) >= 8).all()          # >= 2*D active frames per speaker
+
+
+def test_int8_digit_split_scheme_bounds():
+    """The arithmetic of csrc/wpe_gram_i8.cu restated in numpy (no GPU): 40-bit fixed point per
+    power-whitened row, five balanced base-256 digits, digit pairs of order p + q <= 4, exact integer
+    sums.  Checks the digit identity, the INT32 accumulator range and the error bound the design
+    quotes (<= 1e-9 sqrt(R_ii R_jj) even for white, heavy-tailed power envelopes)."""
+    rng = np.random.default_rng(0)
+    D, T, L, delay, NS = 6, 500, 8, 2, 5
+    Y = (rng.standard_normal((D, T)) + 1j * rng.standard_normal((D, T))) * np.exp(2.0 * rng.standard_normal(T))
+    Y = Y.astype(np.complex64).astype(np.complex128)
+    lam = np.mean(np.abs(Y) ** 2, axis=0)
+    mu = np.sqrt(1.0 / np.maximum(lam, 1e-10 * lam.max()))
+    rows = [Y]
+    for k in range(L):
+        r = np.zeros((D, T), complex)
+        r[:, delay + k:] = Y[:, :T - delay - k]
+        rows.append(r)
+    U = np.concatenate(rows, 0) * mu
+    Rex = U @ U.conj().T
+    mrow = np.maximum(np.abs(U.real).max(1), np.abs(U.imag).max(1))
+    sc = 2.0 ** (37 - np.floor(np.log2(mrow)))
+
+    def planes(x):
+        X = np.rint(x * sc[:, None]).astype(np.int64)
+        assert np.abs(X).max() < 2 ** 38
+        Xb = X + 0x8080808080                                  # the bias folded into the FMA's magic constant
+        dig = [(((Xb >> (8 * s)) & 0xFF) ^ 0x80).astype(np.uint8).view(np.int8).astype(np.int64) for s in range(NS)]
+        assert all((-128 <= d).all() and (d <= 127).all() for d in dig)
+        assert (sum(d << (8 * s) for s, d in enumerate(dig)) == X).all()
+        return dig[::-1]                                       # plane p = digit of weight 256^(4 - p)
+
+    Ar, Ai = planes(U.real), planes(U.imag)
+
+    def prod(A, B):
+        acc = [np.zeros((A[0].shape[0],) * 2, np.int64) for _ in range(NS)]
+        for p in range(NS):
+            for q in range(NS - p):
+                acc[p + q] += A[p] @ B[q].T
+        assert max(np.abs(a).max() for a in acc) < 2 ** 31     # INT32 accumulators of the tensor core
+        v = acc[0].astype(np.float64)
+        for o in range(1, NS):
+            v = v * 256.0 + acc[o]                             # float64 Horner of the epilogue
+        return v * 2.0 ** 32 / np.outer(sc, sc)
+
+    R = (prod(Ar, Ar) + prod(Ai, Ai)) + 1j * (prod(Ai, Ar) - prod(Ar, Ai))
+    d = np.sqrt(np.diag(Rex).real)
+    assert (np.abs(R - Rex) / np.outer(d, d)).max() < 1e-9
+    assert np.abs(np.diag(R).imag).max() == 0.0
