@@ -55,6 +55,7 @@ _SIGNATURES = {
     'gss_istft_f32': (_i, [_p, _p, _i, _i, _i, _i, _i, _p, _sz, _p]),
     'gss_debug_wpe_config': (_i, [_i, _d]),
     'gss_debug_wpe_redo_count': (_i, [_i]),
+    'gss_debug_mstep_i8': (_i, [_p, _p, _p, _i, _i, _i, _i, _i, _p, _p, _sz, _p]),
     'gss_debug_wpe_gram': (_i, [_p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _i, _p, _p, _sz, _p]),
 }
 

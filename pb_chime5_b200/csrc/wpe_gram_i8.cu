@@ -27,24 +27,21 @@
 // copies), wpe_gram_i8_kernel (persistent; TMA producer warp / MMA issuer warp / 8 epilogue
 // warps, 6-stage mbarrier pipeline, A planes and accumulators in TMEM).
 #include "wpe_i8.cuh"
+#include "tc_i8.cuh"
 #include <algorithm>
 
 namespace gss {
 
-constexpr int GI_NS = 5;                                 // int8 digit planes per value
-constexpr int GI_BM = 128;                               // real rows per tile (UMMA M)
 constexpr int GI_NMAX = 80;                              // real columns per tile: 5 accumulators x 80 + 2 x 40 columns of A planes <= 512 TMEM columns
 constexpr int GI_TMEM_A = GI_NS * GI_NMAX;               // first TMEM column of the A-plane buffers (two, 8 columns per plane)
 constexpr int GI_STAGES = 6;
 constexpr int GI_EPI_WARPS = 8;
 constexpr int GI_NT = 64 + 32 * GI_EPI_WARPS;            // warp 0 TMA, warp 1 MMA + TMEM alloc, warps 2..9 epilogue
-constexpr int GI_BLK_BYTES = GI_NS * 2 * 128;            // all planes of 8 rows x 32 frames: 1280
 constexpr int GI_A_STAGE = GI_BLK_BYTES * GI_BM / 8;     // 20480
 constexpr int GI_B_STAGE = GI_BLK_BYTES * GI_NMAX / 8;   // 15360
 constexpr int GI_STAGE_BYTES = GI_A_STAGE + GI_B_STAGE;  // 35840
 constexpr int GI_SMEM = GI_STAGES * GI_STAGE_BYTES;      // 179200 (forces one CTA per SM: TMEM is allocated whole)
 constexpr int GI_MAX_ITEMS = 96;
-constexpr int GI_HEADROOM = 37;                          // |x| in [2^37, 2^38) at the row maximum
 
 struct GiItem { short r0, c0, n; };                      // first real row of the A tile, first real column, width
 struct GiPlan { int n_items; GiItem items[GI_MAX_ITEMS]; };
@@ -150,11 +147,6 @@ __global__ void __launch_bounds__(256) wpe_i8_scale_kernel(const float2* __restr
 // of 2 KB per stage ran at 7 % tensor activity).  Real row 2 rc = Re, 2 rc + 1 = Im of complex row
 // rc; rows [0, D) = Y (unshifted), rows [D, D + LD) = the taps.  Thread = (kb, complex row).
 // ---------------------------------------------------------------------------------------------
-__device__ __forceinline__ unsigned gi_pack4(unsigned a, unsigned b, unsigned c, unsigned d, int byte) {
-    const unsigned sel = 0x0040u | (unsigned)byte | ((unsigned)byte << 4);     // [a.byte, b.byte, -, -]
-    const unsigned ab = __byte_perm(a, b, sel), cdv = __byte_perm(c, d, sel);
-    return __byte_perm(ab, cdv, 0x5410) ^ 0x80808080u;     // offset-binary digit -> two's complement
-}
 
 __global__ void __launch_bounds__(256, 3) wpe_i8_slice_kernel(const float2* __restrict__ Y, const double* __restrict__ mu,
                                                            const int* __restrict__ ex, int8_t* __restrict__ slices,
@@ -175,8 +167,7 @@ __global__ void __launch_bounds__(256, 3) wpe_i8_slice_kernel(const float2* __re
         const double* __restrict__ mub = mu + bl * (size_t)T;
         const int e = ex[bl * g.NRc + rc];
         const double sc = __longlong_as_double((long long)(1023 + e) << 52);
-        // 1.5 * 2^52 + 0x8080808080: the low 40 mantissa bits of fma(y, w, magic) are x + bias
-        const double magic = 6755399441055744.0 + 551911719040.0;
+        const double magic = GI_MAGIC;
 #pragma unroll
         for (int tt = 0; tt < 16; ++tt) {
             const int t = kb * 16 + tt, ts = t - s;
@@ -214,67 +205,6 @@ __global__ void __launch_bounds__(256, 3) wpe_i8_slice_kernel(const float2* __re
     }
 }
 
-// ---------------------------------------------------------------------------------------------
-// PTX wrappers (sm_100a)
-// ---------------------------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-    uint32_t done = 0;
-    for (unsigned spin = 0; !done; ++spin) {
-        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
-                     : "=r"(done) : "r"(bar), "r"(parity) : "memory");
-        if (spin > (1u << 26)) __trap();                  // a lost arrival must not hang the GPU
-    }
-}
-__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                 ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
-}
-// one elected lane of a converged warp (the compiler then knows the region is single-threaded:
-// no uniformisation loops around the UTC* instructions)
-__device__ __forceinline__ bool elect_one() {
-    uint32_t pred;
-    asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
-    return pred != 0;
-}
-// shared memory -> TMEM, 128 rows x 32 B (one digit plane of the A tile for one k-step): 8 TMEM columns
-__device__ __forceinline__ void tc_cp_128x256b(uint32_t taddr, uint64_t sdesc) {
-    asm volatile("tcgen05.cp.cta_group::1.128x256b [%0], %1;" ::"r"(taddr), "l"(sdesc) : "memory");
-}
-// D[tmem] (+)= A[tmem] B[smem]^T
-__device__ __forceinline__ void tc_mma_i8_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
-    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
-                 "tcgen05.mma.cta_group::1.kind::i8 [%0], [%1], %2, %3, p;\n\t}"
-                 ::"r"(tmem_d), "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
-}
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_commit(uint32_t bar) {
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void tc_ld16(uint32_t taddr, int (&v)[16]) {
-    asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
-                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
-                   "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
-                 : "r"(taddr) : "memory");
-}
-__device__ __forceinline__ void tc_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
-
-// Shared-memory matrix descriptors (cute::UMMA::SmemDescriptor, mma_sm100_desc.hpp), K-major, no
-// swizzle: start address, leading byte offset (between the two 16 B k-chunks), stride byte offset
-// (between 8-row groups), all >> 4; version 1 (bits 46..47); layout type 0 (bits 61..63).  Built in
-// the issue loop from a constant upper part and the stage / plane address.
-// instruction descriptor (cute::UMMA::InstrDescriptor): D = S32 (2 << 4), A = B = signed 8 bit (1 << 7, 1 << 10),
-// both K-major, N >> 3 at bit 17, M >> 4 at bit 24.
-__device__ __forceinline__ uint32_t umma_idesc_i8(int n) {
-    return (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(GI_BM >> 4) << 24);
-}
 
 // ---------------------------------------------------------------------------------------------
 // the GEMM.  Persistent CTAs (one per SM) walk the (bin, tile) work items of the chunk; a tile is
@@ -284,9 +214,6 @@ __device__ __forceinline__ uint32_t umma_idesc_i8(int n) {
 // warps per TMEM lane quarter, alternating 16-column blocks).  The producer runs ahead into the
 // next tile while the epilogue drains TMEM; the MMA warp waits for the drain (bar_drain).
 // ---------------------------------------------------------------------------------------------
-__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
-}
 
 __global__ void __launch_bounds__(GI_NT, 1) wpe_gram_i8_kernel(const int8_t* __restrict__ slices, const int* __restrict__ ex,
                                                                cd* __restrict__ Raug, double* __restrict__ rdiag,
