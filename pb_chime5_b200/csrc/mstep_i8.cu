@@ -11,7 +11,8 @@
 // with bulk copies.
 //
 // One CTA per (utterance, bin): warp 0 = TMA producer (B planes), warp 1 = MMA issuer + TMEM,
-// warps 2..9 = A-plane generators during the main loop, epilogue afterwards.  Two M tiles of 128
+// warps 2..17 = A-plane generators during the main loop (two threads per row), warps 2..9 the epilogue
+// afterwards.  Two M tiles of 128
 // rows x N = 2 D columns x 5 accumulators = 480 TMEM columns.  Row scales: one power of two per
 // class (max_t w_kt max_d |y_td|) and one per channel.
 #include "tc_i8.cuh"
@@ -20,7 +21,7 @@
 namespace gss {
 
 constexpr int MS_STAGES = 4;
-constexpr int MS_GEN_WARPS = 8;
+constexpr int MS_GEN_WARPS = 16;
 constexpr int MS_NT = 64 + 32 * MS_GEN_WARPS;
 constexpr int MS_A_STAGE = 2 * (GI_BM / 8) * GI_BLK_BYTES;      // two M tiles: 40960
 constexpr int MS_YLD = 33;                                       // row stride (float2) of the staged raw frames
@@ -191,26 +192,27 @@ __global__ void __launch_bounds__(MS_NT, 1) mstep_i8_kernel(const float2* __rest
         if (elect_one()) tc_commit(smem_u32(&bar_acc));
         __syncwarp();
     } else {
-        // ===== A-plane generators: thread = one row (k, d, re/im) of the 256-row A tile pair.  The raw
-        // frames (D x 32 complex64) and the scaled weights (K x 32) of a k-step are staged in shared
-        // memory by the same 256 threads (coalesced, prefetched one k-step ahead into registers). =====
-        const int r = tid - 64;                                   // 0..255
+        // ===== A-plane generators: thread = (row (k, d, re/im) of the 256-row A tile pair, 16-frame half).
+        // The raw frames (D x 32 complex64) and the scaled weights (K x 32) of a k-step are staged in
+        // shared memory by the same 512 threads (coalesced, prefetched one k-step ahead into registers). =====
+        const int gid = tid - 64;                                 // 0..511
+        const int r = gid >> 1, h = gid & 1;
         const bool live = r < rows;
         const int k = live ? r / N : 0, rem = r - k * N, d = rem >> 1, c = rem & 1;
         const float2* __restrict__ Yb = Y + bf * (size_t)D * T;
         const double* __restrict__ wb = w + bf * (size_t)K * T;
-        float2* yraw = reinterpret_cast<float2*>(smem + MS_STAGES * stage_bytes);          // [2][D][MS_YLD] (odd row stride: the 16 channels a warp reads hit 16 bank pairs)
+        float2* yraw = reinterpret_cast<float2*>(smem + MS_STAGES * stage_bytes);          // [2][D][MS_YLD] (odd row stride: the channels a warp reads hit distinct bank pairs)
         double* wraw = reinterpret_cast<double*>(yraw + 2 * D * MS_YLD);                   // [2][K][32]
         const uint32_t row_off = (uint32_t)(((r >> 7) * (GI_BM / 8) + ((r & 127) >> 3)) * GI_BLK_BYTES + (r & 7) * 16);
-        // staging role: elements e = r + 256 j of the (D x 32) frame tile, element r of the (K x 32) weight tile
-        float2 py[3];
+        // staging role: elements e = gid + 512 j of the (D x 32) frame tile, element gid of the (K x 32) weight tile
+        float2 py[2];
         double pw = 0.0;
-        const int wk_k = r >> 5, wk_t = r & 31;
+        const int wk_k = gid >> 5, wk_t = gid & 31;
         const double wk_sc = (wk_k < K) ? __longlong_as_double((long long)(1023 + ek[bf * K + wk_k]) << 52) : 0.0;
         auto prefetch = [&](int ks) {
 #pragma unroll
-            for (int j = 0; j < 3; ++j) {
-                const int e = r + 256 * j, dd = e >> 5, t = ks * 32 + (e & 31);
+            for (int j = 0; j < 2; ++j) {
+                const int e = gid + 512 * j, dd = e >> 5, t = ks * 32 + (e & 31);
                 py[j] = (dd < D && t < Tv) ? __ldg(&Yb[(size_t)dd * T + t]) : make_float2(0.f, 0.f);
             }
             const int t = ks * 32 + wk_t;
@@ -218,47 +220,45 @@ __global__ void __launch_bounds__(MS_NT, 1) mstep_i8_kernel(const float2* __rest
         };
         auto stash = [&](int buf) {
 #pragma unroll
-            for (int j = 0; j < 3; ++j) {
-                const int e = r + 256 * j;
+            for (int j = 0; j < 2; ++j) {
+                const int e = gid + 512 * j;
                 if (e < D * 32) yraw[buf * D * MS_YLD + (e >> 5) * MS_YLD + (e & 31)] = py[j];
             }
-            if (wk_k < K) wraw[buf * K * 32 + r] = pw;
+            if (wk_k < K) wraw[buf * K * 32 + gid] = pw;
         };
         prefetch(0);
         stash(0);
-        asm volatile("bar.sync 1, 256;" ::: "memory");
+        asm volatile("bar.sync 1, 512;" ::: "memory");
         for (int ks = 0; ks < nk; ++ks) {
             const int st = ks % MS_STAGES, buf = ks & 1;
             if (ks + 1 < nk) prefetch(ks + 1);
             if (ks >= MS_STAGES) mbar_wait(smem_u32(&bar_empty[st]), ((ks / MS_STAGES) - 1) & 1);
             unsigned char* a_dst = smem + st * stage_bytes + row_off;
-            const float2* yr = yraw + buf * D * MS_YLD + d * MS_YLD;
-            const double* wr = wraw + buf * K * 32 + k * 32;
+            const float2* yr = yraw + buf * D * MS_YLD + d * MS_YLD + h * 16;
+            const double* wr = wraw + buf * K * 32 + k * 32 + h * 16;
+            unsigned lo[16], hi[16];
 #pragma unroll
-            for (int h = 0; h < 2; ++h) {
-                unsigned lo[16], hi[16];
+            for (int tt = 0; tt < 16; ++tt) {
+                const float2 v = yr[tt];
+                const double z = live ? fma((double)(c ? v.y : v.x), wr[tt], GI_MAGIC) : GI_MAGIC;
+                lo[tt] = (unsigned)__double2loint(z); hi[tt] = (unsigned)__double2hiint(z);
+            }
 #pragma unroll
-                for (int tt = 0; tt < 16; ++tt) {
-                    const float2 v = yr[h * 16 + tt];
-                    const double z = live ? fma((double)(c ? v.y : v.x), wr[h * 16 + tt], GI_MAGIC) : GI_MAGIC;
-                    lo[tt] = (unsigned)__double2loint(z); hi[tt] = (unsigned)__double2hiint(z);
-                }
+            for (int p = 0; p < GI_NS; ++p) {
+                unsigned wd[4];
 #pragma unroll
-                for (int p = 0; p < GI_NS; ++p) {
-                    unsigned wd[4];
-#pragma unroll
-                    for (int q = 0; q < 4; ++q)
-                        wd[q] = p == 0 ? gi_pack4(hi[4 * q], hi[4 * q + 1], hi[4 * q + 2], hi[4 * q + 3], 0)
-                                       : gi_pack4(lo[4 * q], lo[4 * q + 1], lo[4 * q + 2], lo[4 * q + 3], 4 - p);
-                    *reinterpret_cast<uint4*>(a_dst + (p * 2 + h) * 128) = make_uint4(wd[0], wd[1], wd[2], wd[3]);
-                }
+                for (int q = 0; q < 4; ++q)
+                    wd[q] = p == 0 ? gi_pack4(hi[4 * q], hi[4 * q + 1], hi[4 * q + 2], hi[4 * q + 3], 0)
+                                   : gi_pack4(lo[4 * q], lo[4 * q + 1], lo[4 * q + 2], lo[4 * q + 3], 4 - p);
+                *reinterpret_cast<uint4*>(a_dst + (p * 2 + h) * 128) = make_uint4(wd[0], wd[1], wd[2], wd[3]);
             }
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> visible to the tensor core
             __syncwarp();
             if (lane == 0) mbar_arrive(smem_u32(&bar_a[st]));
             if (ks + 1 < nk) stash(buf ^ 1);                      // the other raw buffer: last read in k-step ks - 1
-            asm volatile("bar.sync 1, 256;" ::: "memory");
+            asm volatile("bar.sync 1, 512;" ::: "memory");
         }
+        if (warp >= 10) goto done;                                // the epilogue needs 8 warps (2 M tiles x 4 lane quarters)
         // ===== epilogue: the same warps; warp -> (M tile, TMEM lane quarter) =====
         const int q = warp & 3, mt = (warp - 2) >> 2;
         const int a = mt * GI_BM + 32 * q + lane;                 // A row = (class, channel, re/im)
@@ -268,13 +268,13 @@ __global__ void __launch_bounds__(MS_NT, 1) mstep_i8_kernel(const float2* __rest
         const double row_scale = __longlong_as_double((long long)(1023 + 32 - (row_ok ? ek[bf * K + ka] : 0)) << 52);
         mbar_wait(smem_u32(&bar_acc), 0);
         tc_fence_after();
-        for (int cb = 0; cb < N; cb += 16) {
-            int acc[GI_NS][16];
+        for (int cb = 0; cb < N; cb += 8) {
+            int acc[GI_NS][8];
 #pragma unroll
-            for (int o = 0; o < GI_NS; ++o) tc_ld16(tmem + ((uint32_t)(32 * q) << 16) + (uint32_t)((mt * GI_NS + o) * N + cb), acc[o]);
+            for (int o = 0; o < GI_NS; ++o) tc_ld8(tmem + ((uint32_t)(32 * q) << 16) + (uint32_t)((mt * GI_NS + o) * N + cb), acc[o]);
             tc_ld_wait();
 #pragma unroll
-            for (int jj = 0; jj < 8; ++jj) {
+            for (int jj = 0; jj < 4; ++jj) {
                 double v0 = (double)acc[0][2 * jj], v1 = (double)acc[0][2 * jj + 1];
 #pragma unroll
                 for (int o = 1; o < GI_NS; ++o) {
@@ -292,6 +292,7 @@ __global__ void __launch_bounds__(MS_NT, 1) mstep_i8_kernel(const float2* __rest
             }
         }
     }
+done:
     tc_fence_before();
     __syncthreads();
     if (warp == 1) {
