@@ -11,7 +11,8 @@ mkdir -p build
 pids=()
 for f in *.cu; do
   o=build/${f%.cu}.o
-  if [ ! -f "$o" ] || [ "$f" -nt "$o" ] || [ -n "$(find . -maxdepth 1 -name '*.cuh' -newer "$o")" ] || [ ../../include/gss.h -nt "$o" ] || [ -n "$EXTRA" -a ! -f build/.fast ] || [ -z "$EXTRA" -a -f build/.fast ]; then
+  dep=""; case "$f" in cacgmm_part*) dep=cacgmm.cu;; esac
+  if [ ! -f "$o" ] || [ "$f" -nt "$o" ] || [ -n "$dep" -a "$dep" -nt "$o" ] || [ -n "$(find . -maxdepth 1 -name '*.cuh' -newer "$o")" ] || [ ../../include/gss.h -nt "$o" ] || [ -n "$EXTRA" -a ! -f build/.fast ] || [ -z "$EXTRA" -a -f build/.fast ]; then
     ( $NVCC $FLAGS $EXTRA -c "$f" -o "$o" ) &
     pids+=($!)
   fi

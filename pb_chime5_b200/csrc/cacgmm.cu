@@ -17,8 +17,22 @@
 #include "common.cuh"
 #include "smallmat.cuh"
 
-#ifndef GSS_DP_LIST
-#define GSS_DP_LIST GSS_CASE(2) GSS_CASE(4) GSS_CASE(6) GSS_CASE(8) GSS_CASE(10) GSS_CASE(12) GSS_CASE(16) GSS_CASE(20) GSS_CASE(24)
+// The padded channel counts are instantiated in three translation units so that the build is
+// parallel (cacgmm.cu = part 0 with the dispatch and the C entry point; cacgmm_part1.cu and
+// cacgmm_part2.cu include this file with GSS_EM_PART set).  -DGSS_DP_LIST=... (developer builds)
+// puts everything into part 0.
+#ifndef GSS_EM_PART
+#define GSS_EM_PART 0
+#endif
+#ifdef GSS_DP_LIST
+#define GSS_DP_PART0 GSS_DP_LIST
+#define GSS_DP_PART1
+#define GSS_DP_PART2
+#else
+#define GSS_DP_PART0 GSS_CASE(2) GSS_CASE(4) GSS_CASE(6) GSS_CASE(8) GSS_CASE(10) GSS_CASE(12)
+#define GSS_DP_PART1 GSS_CASE(16) GSS_CASE(20)
+#define GSS_DP_PART2 GSS_CASE(24)
+#define GSS_DP_LIST GSS_DP_PART0 GSS_DP_PART1 GSS_DP_PART2
 #endif
 
 namespace gss {
@@ -670,7 +684,7 @@ static int launch_cacgmm_dk(const CacgmmParams& p, cudaStream_t st) {
 }
 
 template <int DP>
-static int launch_cacgmm_d(const CacgmmParams& p, int K, cudaStream_t st) {
+int launch_cacgmm_d(const CacgmmParams& p, int K, cudaStream_t st) {
     switch (K) {
         case 2: return launch_cacgmm_dk<DP, 2>(p, st);
         case 3: return launch_cacgmm_dk<DP, 3>(p, st);
@@ -681,6 +695,25 @@ static int launch_cacgmm_d(const CacgmmParams& p, int K, cudaStream_t st) {
     }
 }
 
+// explicit instantiations of this part, declarations of the others
+#if GSS_EM_PART == 0
+#define GSS_CASE(dp) template int launch_cacgmm_d<dp>(const CacgmmParams&, int, cudaStream_t);
+GSS_DP_PART0
+#undef GSS_CASE
+#define GSS_CASE(dp) extern template int launch_cacgmm_d<dp>(const CacgmmParams&, int, cudaStream_t);
+GSS_DP_PART1 GSS_DP_PART2
+#undef GSS_CASE
+#elif GSS_EM_PART == 1
+#define GSS_CASE(dp) template int launch_cacgmm_d<dp>(const CacgmmParams&, int, cudaStream_t);
+GSS_DP_PART1
+#undef GSS_CASE
+#else
+#define GSS_CASE(dp) template int launch_cacgmm_d<dp>(const CacgmmParams&, int, cudaStream_t);
+GSS_DP_PART2
+#undef GSS_CASE
+#endif
+
+#if GSS_EM_PART == 0
 int cacgmm_dispatch(const CacgmmParams& p, int K, cudaStream_t st) {
     const int DP = (p.D + 1) & ~1;
     switch (DP) {
@@ -690,9 +723,11 @@ int cacgmm_dispatch(const CacgmmParams& p, int K, cudaStream_t st) {
         default: return fail(GSS_ERR_UNSUPPORTED, "gss_cacgmm_c64: D=%d not built", p.D);
     }
 }
+#endif
 
 }  // namespace gss
 
+#if GSS_EM_PART == 0
 extern "C" int gss_cacgmm_c64(const gss_c64* Y, const uint8_t* activity, float* posterior,
                               int iterations, int iterations_post,
                               double affiliation_eps, double eigenvalue_floor,
@@ -731,3 +766,4 @@ extern "C" int gss_cacgmm_c64(const gss_c64* Y, const uint8_t* activity, float* 
     p.eps = affiliation_eps; p.floor_ = eigenvalue_floor;
     return cacgmm_dispatch(p, K, (cudaStream_t)stream);
 }
+#endif  // GSS_EM_PART == 0
