@@ -94,15 +94,13 @@ __device__ __forceinline__ void cp_async8(void* smem_dst, const void* gsrc) {
 
 constexpr int CT_SLD = 20;     // staging row stride in float2 (40 words = 8 mod 32: conflict-free fragment loads)
 
-__global__ void __launch_bounds__(CT_NT) wpe_corr_kernel(const float2* __restrict__ Y, const double* __restrict__ inv,
-                                                         cd* __restrict__ Raug, WpeDims m, const int* __restrict__ redo) {
+__device__ __forceinline__ void wpe_corr_body(const size_t bf, const float2* __restrict__ Y, const double* __restrict__ inv,
+                                              cd* __restrict__ Raug, const WpeDims& m) {
     const int rt = blockIdx.y, ct = blockIdx.z;
     if (ct > rt || ct * CT_BM >= m.LD || rt * CT_BM >= m.LD + m.D) return;
-    if (redo != nullptr && redo[blockIdx.x] == 0) return;      // second pass: flagged bins only
     // raw complex64 staging, double buffered: [buf][A|B][row][frame]; weights per frame
     __shared__ __align__(16) float2 st[2][2][CT_BM][CT_SLD];
     __shared__ double wsm[2][CT_BK];
-    const size_t bf = blockIdx.x;
     const float2* __restrict__ Yg = Y + bf * m.D * m.T;
     const double* __restrict__ iv = inv + bf * m.T;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -192,6 +190,23 @@ __global__ void __launch_bounds__(CT_NT) wpe_corr_kernel(const float2* __restric
     }
 }
 
+// Kernel wrappers of the factorisation chain: one CTA (row) per bin in the first pass; in the
+// float64 re-do pass of the INT8 path (redo_list != null) a small grid walks the compacted list of
+// flagged bins, so an empty list costs a handful of CTAs instead of one per bin.
+#define GSS_WPE_REDO_LOOP(CALL)                                                                           \
+    {   const int n_bins = redo_list ? *redo_count : (int)gridDim.x;                                       \
+        for (int li = blockIdx.x; li < n_bins; li += gridDim.x) {                                          \
+            const size_t bf = redo_list ? (size_t)redo_list[li] : (size_t)li;                              \
+            CALL;                                                                                          \
+            __syncthreads();                                                                               \
+        } }
+
+__global__ void __launch_bounds__(CT_NT) wpe_corr_kernel(const float2* __restrict__ Y, const double* __restrict__ inv,
+                                                         cd* __restrict__ Raug, WpeDims m,
+                                                         const int* __restrict__ redo_list, const int* __restrict__ redo_count) {
+    GSS_WPE_REDO_LOOP(wpe_corr_body(bf, Y, inv, Raug, m))
+}
+
 // ---------------------------------------------------------------------------
 // Blocked right-looking Cholesky of R (in place, lower) with the P^H rows riding
 // along, as two kernels per block column of width WS_NB:
@@ -222,12 +237,9 @@ __device__ inline void warp_tri_inverse_deflated(cd* Dg, int nb, int lane) {
 
 // One warp per bin: Cholesky of the diagonal block (zero-pivot deflation), L11 written back,
 // its inverse (packed lower) to `Minv` for the panel rows and the back substitution.
-__global__ void __launch_bounds__(32) wpe_diag_kernel(cd* __restrict__ Raug, cd* __restrict__ Minv,
-                                                      int* __restrict__ info, WpeDims m, int j0, int jb,
-                                                      const int* __restrict__ redo) {
+__device__ __forceinline__ void wpe_diag_body(const size_t bf, cd* __restrict__ Raug, cd* __restrict__ Minv,
+                                              int* __restrict__ info, const WpeDims& m, int j0, int jb) {
     __shared__ __align__(16) cd Dg[WS_NB * (WS_NB + 1) / 2];
-    const size_t bf = blockIdx.x;
-    if (redo != nullptr && redo[bf] == 0) return;
     const int lane = threadIdx.x;
     const int n = m.LD, nrows = m.LD + m.D;
     const int nb = min(WS_NB, n - j0);
@@ -274,13 +286,17 @@ __global__ void __launch_bounds__(32) wpe_diag_kernel(cd* __restrict__ Raug, cd*
     if (lane == 0 && any_bad && info) atomicMax(&info[bf / m.F], GSS_INFO_SINGULAR | ((int)(bf % m.F) << 8));
 }
 
+__global__ void __launch_bounds__(32) wpe_diag_kernel(cd* __restrict__ Raug, cd* __restrict__ Minv,
+                                                      int* __restrict__ info, WpeDims m, int j0, int jb,
+                                                      const int* __restrict__ redo_list, const int* __restrict__ redo_count) {
+    GSS_WPE_REDO_LOOP(wpe_diag_body(bf, Raug, Minv, info, m, j0, jb))
+}
+
 // panel rows below the diagonal block:  L[r, jblock] = A[r, jblock] * L11^{-H}; one thread per row
 constexpr int PR_NT = 128;
-__global__ void __launch_bounds__(PR_NT) wpe_panel_rows_kernel(cd* __restrict__ Raug, const cd* __restrict__ Minv,
-                                                               WpeDims m, int j0, int jb, const int* __restrict__ redo) {
+__device__ __forceinline__ void wpe_panel_rows_body(const size_t bf, cd* __restrict__ Raug, const cd* __restrict__ Minv,
+                                                    const WpeDims& m, int j0, int jb) {
     __shared__ __align__(16) cd Dg[WS_NB * (WS_NB + 1) / 2];
-    const size_t bf = blockIdx.x;
-    if (redo != nullptr && redo[bf] == 0) return;
     const int tid = threadIdx.x;
     const int n = m.LD, nrows = m.LD + m.D;
     const int nb = min(WS_NB, n - j0);
@@ -311,19 +327,22 @@ __global__ void __launch_bounds__(PR_NT) wpe_panel_rows_kernel(cd* __restrict__ 
         if (c < nb) row[c] = acc[c];
 }
 
+__global__ void __launch_bounds__(PR_NT) wpe_panel_rows_kernel(cd* __restrict__ Raug, const cd* __restrict__ Minv,
+                                                               WpeDims m, int j0, int jb,
+                                                               const int* __restrict__ redo_list, const int* __restrict__ redo_count) {
+    GSS_WPE_REDO_LOOP(wpe_panel_rows_body(bf, Raug, Minv, m, j0, jb))
+}
+
 // A22 -= L21 L21^H on the trailing matrix (origin j1 = j0 + nb).  Same tiling / MMA
 // mapping as wpe_corr_kernel; the k dimension is the nb <= 24 columns of the panel.
-__global__ void __launch_bounds__(CT_NT) wpe_trail_kernel(cd* __restrict__ Raug, WpeDims m, int j0,
-                                                          const int* __restrict__ redo) {
+__device__ __forceinline__ void wpe_trail_body(const size_t bf, cd* __restrict__ Raug, const WpeDims& m, int j0) {
     const int rt = blockIdx.y, ct = blockIdx.z;
     if (ct > rt) return;
-    if (redo != nullptr && redo[blockIdx.x] == 0) return;
     const int n = m.LD, nrows = m.LD + m.D;
     const int nb = min(WS_NB, n - j0), j1 = j0 + nb;
     const int i0 = j1 + rt * CT_BM, c0 = j1 + ct * CT_BM;
     if (i0 >= nrows || c0 >= n) return;
     __shared__ __align__(16) double Are[WS_NB][CT_LD], Aim[WS_NB][CT_LD], Bre[WS_NB][CT_LD], Bim[WS_NB][CT_LD];
-    const size_t bf = blockIdx.x;
     cd* A = Raug + bf * (size_t)nrows * n;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int g = lane >> 2, tg = lane & 3;
@@ -391,14 +410,20 @@ __global__ void __launch_bounds__(CT_NT) wpe_trail_kernel(cd* __restrict__ Raug,
     }
 }
 
+__global__ void __launch_bounds__(CT_NT) wpe_trail_kernel(cd* __restrict__ Raug, WpeDims m, int j0,
+                                                          const int* __restrict__ redo_list, const int* __restrict__ redo_count) {
+    GSS_WPE_REDO_LOOP(wpe_trail_body(bf, Raug, m, j0))
+}
+
 // INT8 Gram path, a-posteriori check.  After the Cholesky factorisation L_jj^2 / R_jj is
 // 1 - (squared multiple correlation of row j with the rows before it), a scale-invariant
 // measure of how much of the pivot survived the elimination.  A bin whose smallest ratio is
-// below `tau` (or not finite: dead channels, failures) is flagged and re-done in float64.
+// below `tau` (or not finite: dead channels, failures) is put on the re-do list and re-done in float64.
 __device__ int g_wpe_redo_total = 0;
 
 __global__ void __launch_bounds__(32) wpe_flag_kernel(const cd* __restrict__ Raug, const double* __restrict__ rdiag,
-                                                      int* __restrict__ flag, WpeDims m, double tau) {
+                                                      int* __restrict__ redo_list, int* __restrict__ redo_count,
+                                                      WpeDims m, double tau) {
     const size_t bf = blockIdx.x;
     const int n = m.LD, lane = threadIdx.x;
     const cd* A = Raug + bf * (size_t)(m.LD + m.D) * n;
@@ -408,7 +433,10 @@ __global__ void __launch_bounds__(32) wpe_flag_kernel(const cd* __restrict__ Rau
         if (!(l * l >= tau * r) || !(r > 0.0) || !isfinite(l)) bad = true;
     }
     bad = __any_sync(0xffffffffu, bad);
-    if (lane == 0) { flag[bf] = bad ? 1 : 0; if (bad) atomicAdd(&g_wpe_redo_total, 1); }
+    if (lane == 0 && bad) {                                 // compacted list (order irrelevant: bins are independent)
+        redo_list[atomicAdd(redo_count, 1)] = (int)bf;
+        atomicAdd(&g_wpe_redo_total, 1);
+    }
 }
 
 // Blocked right-looking back substitution  L^H G = Z  (Z^H sits in rows [n, n + D) of Raug).
@@ -578,7 +606,7 @@ __global__ void __launch_bounds__(AP_NT) wpe_apply_kernel(const float2* __restri
         }
 }
 
-struct WpeWs { double* power; double* inv; cd* Raug; cd* G; cd* Minv; double* rdiag; int* flag; WpeI8Ws i8; bool has_i8; size_t bytes; };
+struct WpeWs { double* power; double* inv; cd* Raug; cd* G; cd* Minv; double* rdiag; int* redo_list; int* redo_count; WpeI8Ws i8; bool has_i8; size_t bytes; };
 
 static WpeWs wpe_ws_layout(void* ws, int Bc, int F, int D, int T, int L) {
     const int LD = L * D;
@@ -590,10 +618,11 @@ static WpeWs wpe_ws_layout(void* ws, int Bc, int F, int D, int T, int L) {
     w.G = a.take<cd>((size_t)Bc * F * LD * D);
     w.Minv = a.take<cd>((size_t)Bc * F * ((LD + WS_NB - 1) / WS_NB) * (WS_NB * (WS_NB + 1) / 2));
     w.has_i8 = wpe_i8_applicable(D, T, L);
-    w.rdiag = nullptr; w.flag = nullptr;
+    w.rdiag = nullptr; w.redo_list = nullptr; w.redo_count = nullptr;
     if (w.has_i8) {
         w.rdiag = a.take<double>((size_t)Bc * F * LD);
-        w.flag = a.take<int>((size_t)Bc * F);
+        w.redo_list = a.take<int>((size_t)Bc * F);
+        w.redo_count = a.take<int>(1);
         const size_t used = wpe_i8_ws_layout(ws ? (char*)ws + a.off : nullptr, F, D, T, L, &w.i8);
         a.off += align_up(used);
     }
@@ -624,27 +653,31 @@ static double wpe_i8_tau() {
 }
 
 // blocked Cholesky of Raug with the P^H rows riding along (all bins, or the flagged ones)
-static int wpe_factor(const WpeWs& w, const WpeDims& m, int BF, int* infoc, const int* redo, cudaStream_t st) {
+// redo == false: all BF bins; redo == true: the bins of w.redo_list (a grid of at most one CTA row per SM walks it)
+static int wpe_factor(const WpeWs& w, const WpeDims& m, int BF, int* infoc, bool redo, cudaStream_t st) {
     const int LD = m.LD, D = m.D;
+    const int gx = redo ? std::min(BF, num_sms()) : BF;
+    const int* rl = redo ? w.redo_list : nullptr;
+    const int* rc = redo ? w.redo_count : nullptr;
     for (int j0 = 0, jb = 0; j0 < LD; j0 += WS_NB, ++jb) {
-        wpe_diag_kernel<<<BF, 32, 0, st>>>(w.Raug, w.Minv, infoc, m, j0, jb, redo);
+        wpe_diag_kernel<<<gx, 32, 0, st>>>(w.Raug, w.Minv, infoc, m, j0, jb, rl, rc);
         GSS_LAUNCH_CHECK("wpe_diag_kernel");
         const int j1 = std::min(j0 + WS_NB, LD);
-        dim3 pg(BF, (LD + D - j1 + PR_NT - 1) / PR_NT);
-        wpe_panel_rows_kernel<<<pg, PR_NT, 0, st>>>(w.Raug, w.Minv, m, j0, jb, redo);
+        dim3 pg(gx, (LD + D - j1 + PR_NT - 1) / PR_NT);
+        wpe_panel_rows_kernel<<<pg, PR_NT, 0, st>>>(w.Raug, w.Minv, m, j0, jb, rl, rc);
         GSS_LAUNCH_CHECK("wpe_panel_rows_kernel");
         if (j1 < LD) {
-            dim3 tg(BF, (LD + D - j1 + CT_BM - 1) / CT_BM, (LD - j1 + CT_BM - 1) / CT_BM);
-            wpe_trail_kernel<<<tg, CT_NT, 0, st>>>(w.Raug, m, j0, redo);
+            dim3 tg(gx, (LD + D - j1 + CT_BM - 1) / CT_BM, (LD - j1 + CT_BM - 1) / CT_BM);
+            wpe_trail_kernel<<<tg, CT_NT, 0, st>>>(w.Raug, m, j0, rl, rc);
             GSS_LAUNCH_CHECK("wpe_trail_kernel");
         }
     }
     return GSS_OK;
 }
 
-static int wpe_corr_f64(const float2* Yc, const WpeWs& w, const WpeDims& m, int BF, const int* redo, cudaStream_t st) {
-    dim3 grid(BF, (m.LD + m.D + CT_BM - 1) / CT_BM, (m.LD + CT_BM - 1) / CT_BM);
-    wpe_corr_kernel<<<grid, CT_NT, 0, st>>>(Yc, w.inv, w.Raug, m, redo);
+static int wpe_corr_f64(const float2* Yc, const WpeWs& w, const WpeDims& m, int BF, bool redo, cudaStream_t st) {
+    dim3 grid(redo ? std::min(BF, num_sms()) : BF, (m.LD + m.D + CT_BM - 1) / CT_BM, (m.LD + CT_BM - 1) / CT_BM);
+    wpe_corr_kernel<<<grid, CT_NT, 0, st>>>(Yc, w.inv, w.Raug, m, redo ? w.redo_list : nullptr, redo ? w.redo_count : nullptr);
     GSS_LAUNCH_CHECK("wpe_corr_kernel");
     return GSS_OK;
 }
@@ -709,18 +742,19 @@ extern "C" int gss_wpe_c64(const gss_c64* Y, gss_c64* X, int taps, int delay, in
             GSS_LAUNCH_CHECK("wpe_invpower_kernel");
             int rcf;
             if (gram_mode == 0) {
-                if ((rcf = wpe_corr_f64(Yc, w, m, BF, nullptr, st))) return rcf;
-                if ((rcf = wpe_factor(w, m, BF, infoc, nullptr, st))) return rcf;
+                if ((rcf = wpe_corr_f64(Yc, w, m, BF, false, st))) return rcf;
+                if ((rcf = wpe_factor(w, m, BF, infoc, false, st))) return rcf;
             } else {
                 // INT8 tensor-core Gram matrix; ill-conditioned bins are flagged after the
                 // factorisation and re-done (Gram + factorisation) in float64
                 if ((rcf = wpe_gram_i8_run(Yc, w.inv, w.Raug, w.rdiag, m, BF, w.i8, 0, st))) return rcf;
-                if ((rcf = wpe_factor(w, m, BF, gram_mode == 2 ? nullptr : infoc, nullptr, st))) return rcf;
+                if ((rcf = wpe_factor(w, m, BF, gram_mode == 2 ? nullptr : infoc, false, st))) return rcf;
                 if (gram_mode == 2) {
-                    wpe_flag_kernel<<<BF, 32, 0, st>>>(w.Raug, w.rdiag, w.flag, m, wpe_i8_tau());
+                    GSS_CUDA(cudaMemsetAsync(w.redo_count, 0, sizeof(int), st));
+                    wpe_flag_kernel<<<BF, 32, 0, st>>>(w.Raug, w.rdiag, w.redo_list, w.redo_count, m, wpe_i8_tau());
                     GSS_LAUNCH_CHECK("wpe_flag_kernel");
-                    if ((rcf = wpe_corr_f64(Yc, w, m, BF, w.flag, st))) return rcf;
-                    if ((rcf = wpe_factor(w, m, BF, infoc, w.flag, st))) return rcf;
+                    if ((rcf = wpe_corr_f64(Yc, w, m, BF, true, st))) return rcf;
+                    if ((rcf = wpe_factor(w, m, BF, infoc, true, st))) return rcf;
                 }
             }
             {
@@ -770,7 +804,7 @@ extern "C" int gss_debug_wpe_gram(const gss_c64* Y, const double* inv, double* R
         WpeWs w{};
         w.inv = const_cast<double*>(inv);
         w.Raug = reinterpret_cast<cd*>(Raug);
-        return wpe_corr_f64((const float2*)Y, w, m, BF, nullptr, st);
+        return wpe_corr_f64((const float2*)Y, w, m, BF, false, st);
     }
     GSS_REQUIRE(wpe_i8_applicable(D, T, taps), GSS_ERR_UNSUPPORTED, "gss_debug_wpe_gram: INT8 path not built for D=%d taps=%d T=%d", D, taps, T);
     WpeI8Ws i8;
