@@ -447,8 +447,9 @@ template <int NT, int DMAX>
 __global__ void __launch_bounds__(NT) wpe_backsub_kernel(const cd* __restrict__ Raug, const cd* __restrict__ Minv,
                                                          cd* __restrict__ G, WpeDims m) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    cd* S = reinterpret_cast<cd*>(smem_raw);                       // [n][D]
-    cd* Gj = S + (size_t)m.LD * m.D;                               // [WS_NB][D]
+    const int SLD = m.D | 1;                                       // odd row stride: thread-per-row accesses hit distinct banks
+    cd* S = reinterpret_cast<cd*>(smem_raw);                       // [n][SLD]
+    cd* Gj = S + (size_t)m.LD * SLD;                               // [WS_NB][D]
     cd* Dg = Gj + WS_NB * m.D;                                     // packed inverse of the diagonal block
     const size_t bf = blockIdx.x;
     const int tid = threadIdx.x;
@@ -458,7 +459,7 @@ __global__ void __launch_bounds__(NT) wpe_backsub_kernel(const cd* __restrict__ 
     const int nblk = (n + WS_NB - 1) / WS_NB;
     for (int e = tid; e < n * D; e += NT) {
         const int d = e / n, i = e - d * n;                        // coalesced along i
-        S[i * D + d] = cconj(A[(size_t)(n + d) * n + i]);
+        S[i * SLD + d] = cconj(A[(size_t)(n + d) * n + i]);
     }
     for (int jb = nblk - 1; jb >= 0; --jb) {
         const int j0 = jb * WS_NB, nb = min(WS_NB, n - j0);
@@ -469,7 +470,7 @@ __global__ void __launch_bounds__(NT) wpe_backsub_kernel(const cd* __restrict__ 
         for (int e = tid; e < nb * D; e += NT) {
             const int i = e / D, d = e - i * D;
             cd s = cmake(0.0, 0.0);
-            for (int q = i; q < nb; ++q) cfma(s, cconj(Dg[tri(q, i)]), S[(j0 + q) * D + d]);
+            for (int q = i; q < nb; ++q) cfma(s, cconj(Dg[tri(q, i)]), S[(j0 + q) * SLD + d]);
             Gj[i * D + d] = s;
             Gb[(size_t)(j0 + i) * D + d] = s;
         }
@@ -478,7 +479,7 @@ __global__ void __launch_bounds__(NT) wpe_backsub_kernel(const cd* __restrict__ 
         for (int i = tid; i < j0; i += NT) {
             cd acc[DMAX];
 #pragma unroll
-            for (int d = 0; d < DMAX; ++d) acc[d] = d < D ? S[i * D + d] : cmake(0.0, 0.0);
+            for (int d = 0; d < DMAX; ++d) acc[d] = d < D ? S[i * SLD + d] : cmake(0.0, 0.0);
             for (int q = 0; q < nb; ++q) {
                 const cd l = cconj(A[(size_t)(j0 + q) * n + i]);
 #pragma unroll
@@ -487,7 +488,7 @@ __global__ void __launch_bounds__(NT) wpe_backsub_kernel(const cd* __restrict__ 
             }
 #pragma unroll
             for (int d = 0; d < DMAX; ++d)
-                if (d < D) S[i * D + d] = acc[d];
+                if (d < D) S[i * SLD + d] = acc[d];
         }
         __syncthreads();
     }
@@ -714,7 +715,7 @@ extern "C" int gss_wpe_c64(const gss_c64* Y, gss_c64* X, int taps, int delay, in
                 "gss_wpe_c64: taps=%d delay=%d iterations=%d psd_context=%d", taps, delay, iterations, psd_context);
     GSS_REQUIRE(D <= 32, GSS_ERR_UNSUPPORTED, "gss_wpe_c64: D=%d > 32 not built", D);
     const int LD = taps * D;
-    GSS_REQUIRE(((size_t)LD * D + 24 * D + 300) * sizeof(cd) <= 220 * 1024, GSS_ERR_UNSUPPORTED,
+    GSS_REQUIRE(((size_t)LD * (D | 1) + 24 * D + 300) * sizeof(cd) <= 220 * 1024, GSS_ERR_UNSUPPORTED,
                 "gss_wpe_c64: taps*D*D=%d too large for the back-substitution tile", LD * D);
     cudaStream_t st = (cudaStream_t)stream;
     if (B == 0 || F == 0) return GSS_OK;
@@ -758,7 +759,7 @@ extern "C" int gss_wpe_c64(const gss_c64* Y, gss_c64* X, int taps, int delay, in
                 }
             }
             {
-                const size_t bs_smem = ((size_t)LD * D + WS_NB * D + WS_NB * (WS_NB + 1) / 2) * sizeof(cd);
+                const size_t bs_smem = ((size_t)LD * (D | 1) + WS_NB * D + WS_NB * (WS_NB + 1) / 2) * sizeof(cd);
                 int rc2;
                 if (D <= 8) rc2 = launch_backsub<8>(w.Raug, w.Minv, w.G, m, BF, bs_smem, st);
                 else if (D <= 16) rc2 = launch_backsub<16>(w.Raug, w.Minv, w.G, m, BF, bs_smem, st);
