@@ -410,7 +410,7 @@ __device__ __forceinline__ void wpe_trail_body(const size_t bf, cd* __restrict__
     }
 }
 
-__global__ void __launch_bounds__(CT_NT) wpe_trail_kernel(cd* __restrict__ Raug, WpeDims m, int j0,
+__global__ void __launch_bounds__(CT_NT, 4) wpe_trail_kernel(cd* __restrict__ Raug, WpeDims m, int j0,
                                                           const int* __restrict__ redo_list, const int* __restrict__ redo_count) {
     GSS_WPE_REDO_LOOP(wpe_trail_body(bf, Raug, m, j0))
 }
