@@ -143,7 +143,12 @@ int gss_beamform_from_posterior_c64(const gss_c64* Y, const float* posterior,
 
 /* ---- WPE dereverberation (WPE.__call__, core.py:48-88 -> nara_wpe.wpe.wpe_v8,
  * third party) ---------------------------------------------------------------
- * Y, X (B,F,D,T) c64 (X may not alias Y). */
+ * Y, X (B,F,D,T) c64 (X may not alias Y).
+ * The correlation build R = Yt L^-1 Yt^H, P = Yt L^-1 Y^H runs on the INT8 tensor cores
+ * (tcgen05.mma kind::i8, exact digit-split integer arithmetic, float64 recombination) when
+ * taps * D >= 48; bins whose normal equations are too ill conditioned for its 2^-38 truncation are
+ * detected after the factorisation and re-done with the float64 (FP64 MMA) build inside the same
+ * call, still asynchronously.  Environment: GSS_WPE_GRAM=f64|i8, GSS_WPE_I8_TAU (re-do threshold). */
 int gss_wpe_c64(const gss_c64* Y, gss_c64* X, int taps, int delay, int iterations,
                 int psd_context, int B, int F, int D, int T, const int* T_per_utt,
                 int* info, void* ws, size_t ws_bytes, void* stream);
