@@ -81,7 +81,7 @@ bool wpe_i8_applicable(int D, int T, int L) {
 static int gi_chunk_bins(int F, int D, int T, int L) {
     const GiDims g = gi_dims(D, T, L * D);
     const size_t per = gi_slice_bytes_per_bin(g);
-    int n = (int)((size_t)96 << 20) / (int)per;          // keep one chunk of digit planes inside L2 (126 MB)
+    int n = (int)((size_t)104 << 20) / (int)per;         // keep one chunk of digit planes inside L2 (126 MB)
     return std::max(1, std::min(n, 64));
 }
 
@@ -425,11 +425,16 @@ int wpe_gram_i8_run(const float2* Y, const double* inv, cd* Raug, double* rdiag,
     const GiPlan plan = gi_plan(m.D, m.LD);
     GSS_CUDA(cudaFuncSetAttribute(wpe_gram_i8_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, GI_SMEM));   // per device
     const int half = g.NRp >> 1;
-    // bins per chunk: as many as the scratch holds, rounded down to whole waves of the persistent CTAs
-    int cbins = ws.chunk_bins;
+    // bins per chunk: at most what the scratch holds; the count whose work items fill whole waves of
+    // the persistent CTAs best (ties: the larger chunk)
+    int cbins = 1;
     {
-        const int waves = cbins * plan.n_items / num_sms();
-        if (waves >= 1) cbins = std::max(1, waves * num_sms() / plan.n_items);
+        double best = 0.0;
+        for (int c = 1; c <= ws.chunk_bins; ++c) {
+            const int items = c * plan.n_items, waves = (items + num_sms() - 1) / num_sms();
+            const double util = (double)items / ((double)waves * num_sms());
+            if (util >= best - 1e-9) { best = util; cbins = c; }
+        }
     }
     for (int b0 = 0; b0 < BF; b0 += cbins) {
         const int nb = std::min(cbins, BF - b0);
