@@ -196,7 +196,7 @@ int gss_debug_wpe_gram(const gss_c64* Y, const double* inv, double* Raug, int mo
  * any other entry point: the CACGMM M-step covariance Phi[b,f,k] = sum_t w[b,f,k,t] y y^H
  * (complex_angular_central_gaussian.py:293-300) on the INT8 tensor cores with exact digit-split
  * arithmetic.  Y (B,F,D,T) c64, w (B,F,K,T) f64 >= 0, Phi (B,F,K,D,D) c128 (full Hermitian).
- * Built for D % 4 == 0, D <= 24, K * 2 D <= 256; workspace B F (ceil(T/32) 320 D + 4 (D + K)) + 1 KiB. */
+ * Built for D in {4, 8, 16, 24}, K * 2 D <= 256; workspace B F (ceil(T/32) 320 D + 4 (D + K)) + 1 KiB. */
 int gss_debug_mstep_i8(const gss_c64* Y, const double* w, double* Phi, int B, int F, int D, int T, int K,
                        const int* T_per_utt, void* ws, size_t ws_bytes, void* stream);
 

@@ -304,14 +304,14 @@ done:
 }  // namespace gss
 
 // Phi (B,F,K,D,D) c128 = sum_t w[b,f,k,t] y y^H  with Y (B,F,D,T) c64, w (B,F,K,T) f64 >= 0.
-// Built for D % 4 == 0, D <= 24, K * 2 D <= 256.  Workspace: B F (ceil(T/32) 2 D 160 + 4 (D + K)) bytes.
+// Built for D in {4, 8, 16, 24}, K * 2 D <= 256.  Workspace: B F (ceil(T/32) 2 D 160 + 4 (D + K)) bytes.
 extern "C" int gss_debug_mstep_i8(const gss_c64* Y, const double* w, double* Phi, int B, int F, int D, int T, int K,
                                   const int* T_per_utt, void* ws, size_t ws_bytes, void* stream) {
     using namespace gss;
     GSS_REQUIRE(Y && w && Phi, GSS_ERR_ARG, "gss_debug_mstep_i8: null pointer");
     GSS_REQUIRE(B > 0 && F > 0 && T > 0 && K > 0, GSS_ERR_ARG, "gss_debug_mstep_i8: bad dims");
-    GSS_REQUIRE(D % 4 == 0 && D >= 4 && D <= 24 && K * 2 * D <= 256, GSS_ERR_UNSUPPORTED,
-                "gss_debug_mstep_i8: built for D %% 4 == 0, D <= 24, K * 2 D <= 256 (D=%d K=%d)", D, K);
+    GSS_REQUIRE((D == 4 || D == 8 || D == 16 || D == 24) && K * 2 * D <= 256, GSS_ERR_UNSUPPORTED,
+                "gss_debug_mstep_i8: built for D in {4, 8, 16, 24} (UMMA N = 2 D), K * 2 D <= 256 (D=%d K=%d)", D, K);
     GSS_REQUIRE((long long)(T + 32) * 5 * 16384 < 2147483647LL, GSS_ERR_UNSUPPORTED, "gss_debug_mstep_i8: T=%d too long for INT32 sums", T);
     cudaStream_t st = (cudaStream_t)stream;
     MsDims m{F, D, T, K, (T + 31) / 32 * 2, T_per_utt};
