@@ -259,3 +259,25 @@ def test_int8_digit_split_scheme_bounds():
     d = np.sqrt(np.diag(Rex).real)
     assert (np.abs(R - Rex) / np.outer(d, d)).max() < 1e-9
     assert np.abs(np.diag(R).imag).max() == 0.0
+
+
+def test_cfg4_sized_work_list_shards_evenly():
+    """BASELINE configs[3]: 20 000 dev-shaped utterances over 8 ranks.  Every utterance exactly once;
+    with known lengths the greedy longest-first deal balances the audio seconds to < 0.1 %, the strided
+    deal (kaldi_run.py:73-76) the utterance counts to +-1; session batches cover a shard exactly once."""
+    from pb_chime5_b200.session import plan_batches
+    rng = np.random.default_rng(4)
+    n, world = 20000, 8
+    lengths = (np.clip(rng.lognormal(np.log(2.0), 0.8, size=n), 0.3, 20.0) * 16000 + 2 * 240000).astype(int).tolist()
+    shards = [sharding.shard_indices(n, r, world, lengths) for r in range(world)]
+    assert sorted(i for s in shards for i in s) == list(range(n))
+    load = [sum(lengths[i] for i in s) for s in shards]
+    assert (max(load) - min(load)) / max(load) < 1e-3
+    strided = [sharding.shard_indices(n, r, world) for r in range(world)]
+    assert sorted(i for s in strided for i in s) == list(range(n))
+    assert max(len(s) for s in strided) - min(len(s) for s in strided) <= 1
+    mine = shards[3]
+    batches = plan_batches([lengths[i] for i in mine], None, batch_size=8, window=64, max_batch_samples=8 * 60 * 16000)
+    assert sorted(j for b in batches for j in b) == list(range(len(mine)))
+    padded = sum(len(b) * lengths[mine[b[0]]] for b in batches)
+    assert sum(lengths[i] for i in mine) / padded > 0.97        # length bucketing keeps the padding below 3 %
