@@ -412,7 +412,7 @@ def canonical_phase(w, psd_n, ref=0):
 
 
 def beamform(Obs, target_mask, distortion_mask, bf='mvdrSouden_ban',
-             postfilter=None, return_aux=False):
+             postfilter=None, return_aux=False, ref_channel=None):
     """Beamformer.__call__: Obs (D,T,F), masks (T,F) -> X_hat (T,F).
     core.py:246-278; beamforming_wrapper.py:11-124, 192-208."""
     Obs = np.asarray(Obs)
@@ -426,7 +426,11 @@ def beamform(Obs, target_mask, distortion_mask, bf='mvdrSouden_ban',
         cov_x = psd_matrix(Y, Xm)
         cov_n = psd_matrix(Y, Nm)
         if bf.startswith('mvdrSouden'):
-            w, ref = mvdr_souden(cov_x, cov_n, eps=1e-10, return_ref_channel=True)
+            # ref_channel=None: the reference's arg-max over ALL bins of the call
+            # (beamformer.py:535-543); a caller that checks a subset of bins passes the
+            # channel the full-band run selected
+            w, ref = mvdr_souden(cov_x, cov_n, ref_channel=ref_channel, eps=1e-10,
+                                 return_ref_channel=True)
             aux['ref_channel'] = ref
         else:
             w = canonical_phase(gev_vector(cov_x, cov_n), cov_n)
@@ -456,7 +460,7 @@ def beamform(Obs, target_mask, distortion_mask, bf='mvdrSouden_ban',
 def enhance_stft(Obs, activity_freq, target_index, *, wpe=None, gss_iterations=20,
                  gss_iterations_post=1, bf='mvdrSouden_ban', postfilter=None,
                  start_context_frames=0, end_context_frames=0, bf_drop_context=True,
-                 loop_over_bins=False):
+                 loop_over_bins=False, ref_channel=None):
     """STFT-domain part of Enhancer.enhance_observation (core.py:524-564).
     wpe: None or dict(taps, delay, iterations, psd_context).
     Returns dict with Obs (after WPE), masks, X_hat."""
@@ -471,7 +475,8 @@ def enhance_stft(Obs, activity_freq, target_index, *, wpe=None, gss_iterations=2
             masks[:, -end_context_frames:, :] = 0
     target_mask = masks[target_index]
     distortion_mask = np.sum(np.delete(masks, target_index, axis=0), axis=0)
-    X_hat = beamform(Obs, target_mask, distortion_mask, bf, postfilter)
+    X_hat = beamform(Obs, target_mask, distortion_mask, bf, postfilter,
+                     ref_channel=ref_channel)
     return dict(Obs=Obs, masks=masks, target_mask=target_mask,
                 distortion_mask=distortion_mask, X_hat=X_hat)
 

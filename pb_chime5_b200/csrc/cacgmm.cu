@@ -72,32 +72,31 @@ struct CacgmmCfg {
     static constexpr int NW = NT / 32;
     static constexpr int JLD = DP + 1;                    // leading dim of Jacobi matrices
     static constexpr int TE = NT;                         // frames per E step = super tile (complex64 tile)
-#ifndef GSS_TM
-#define GSS_TM 128
-#endif
-    static constexpr int TM = GSS_TM;                     // frames per M tile (complex64, double buffered)
     static constexpr int SB = sub_block(DP);
     static constexpr int NS = DP / SB;
     static constexpr int NSB = NS * (NS + 1) / 2;
-    static constexpr size_t E_BYTES = size_t(TE) * YLD * sizeof(float2);
-    static constexpr size_t MT_BYTES = size_t(2) * TM * YLD * sizeof(float2);   // double-buffered complex64 M tiles
-    static constexpr size_t MS_BYTES = 0;
+    static constexpr size_t E_BYTES = size_t(TE) * YLD * sizeof(float2);       // ONE resident super tile (E and M phase)
     static constexpr size_t SWEEP_BYTES = size_t(K) * NP * sizeof(cd) + size_t(2) * K * DP * sizeof(cd) + 4 * K * 8 + 64;
     static constexpr size_t JAC_BYTES = size_t(3) * DP * JLD * sizeof(cd);
-    static constexpr size_t YS_BYTES = cmax(cmax(E_BYTES, MT_BYTES + MS_BYTES), cmax(SWEEP_BYTES, JAC_BYTES));
+    static constexpr size_t YS_BYTES = cmax(E_BYTES, cmax(SWEEP_BYTES, JAC_BYTES));
     static constexpr size_t W_BYTES = size_t(TE) * KP * sizeof(double);
     static constexpr size_t B_BYTES = size_t(NP) * K * sizeof(cd);
     static constexpr size_t ACC_BYTES = size_t(K) * NP * sizeof(cd);
-    // misc: logdet[32] pi[32] tr[32] | gred[NW*K] | jred[64] | col[K*DP] cd | piv[K*DP] | rot[16] | flags[32] | table[NP] u16
-    static constexpr size_t MISC_BYTES = (96 + NW * K + 64) * 8 + size_t(K) * DP * 8
+    // misc: logdet[32] pi[32] tr[32] apri[32] | gred[NW*K] | jred[64] | col[K*DP] cd | piv[K*DP] | rot[16] | flags[32] | table[NP] u16
+    static constexpr size_t MISC_BYTES = (128 + NW * K + 64) * 8 + size_t(K) * DP * 8
                                          + 16 * sizeof(JacobiRot) + 32 * 4 + ((NP * 2 + 15) / 16) * 16;
     static constexpr size_t SMEM = YS_BYTES + W_BYTES + B_BYTES + ACC_BYTES + MISC_BYTES;
     static_assert(DP % 2 == 0 && DP <= 32, "padded channel count must be even and <= 32");
     static_assert(DP % SB == 0, "sub-block must divide DP");
     static_assert(NG >= 1, "block too small for the M-phase mapping");
-    static_assert(TE % TM == 0, "M tiles must tile the super tile");
     static_assert(K < 20, "cacgmm.py:247");
 };
+
+// Position of channel d inside a frame row of the resident tile: even channels first, then the odd
+// ones ("planar"), so that the 2x2 blocks of consecutive M-phase lanes read consecutive 8 B chunks.
+// The E phase indexes the row with compile-time channel numbers, so the permutation is free there.
+template <int DP>
+__host__ __device__ constexpr int ypos(int d) { return (d & 1) * (DP / 2) + (d >> 1); }
 
 // q_k += sum over the pairs of sub-block (I,J) of B'_k[d,e] . P[d,e]
 template <int DP, int K, int SB, int I, int J>
@@ -105,11 +104,11 @@ __device__ __forceinline__ void quad_subblock(const float2* __restrict__ yrow, c
                                               double (&qa)[K], double (&qb)[K]) {
     double rr[SB], ri[SB], cr[SB], ci[SB];
 #pragma unroll
-    for (int a = 0; a < SB; ++a) { const float2 v = yrow[I * SB + a]; rr[a] = (double)v.x; ri[a] = (double)v.y; }
+    for (int a = 0; a < SB; ++a) { const float2 v = yrow[ypos<DP>(I * SB + a)]; rr[a] = (double)v.x; ri[a] = (double)v.y; }
 #pragma unroll
     for (int c = 0; c < SB; ++c) {
         if (I == J) { cr[c] = rr[c]; ci[c] = ri[c]; }
-        else { const float2 v = yrow[J * SB + c]; cr[c] = (double)v.x; ci[c] = (double)v.y; }
+        else { const float2 v = yrow[ypos<DP>(J * SB + c)]; cr[c] = (double)v.x; ci[c] = (double)v.y; }
     }
 #pragma unroll
     for (int a = 0; a < SB; ++a) {
@@ -150,18 +149,10 @@ struct QuadAll<DP, K, NSB, NSB> {
     static __device__ __forceinline__ void run(const float2*, const cd*, double (&)[K], double (&)[K]) {}
 };
 
-__device__ __forceinline__ void cp_async8(void* smem_dst, const void* gsrc) {
-    const unsigned s = (unsigned)__cvta_generic_to_shared(smem_dst);
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"(s), "l"(gsrc) : "memory");
-}
-__device__ __forceinline__ void cp_async_commit_wait_all() {
-    asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;\n" ::: "memory");
-}
-
 template <int DP, int K, int NT, int MINB>
 __global__ void __launch_bounds__(NT, MINB) cacgmm_em_kernel(const CacgmmParams p) {
     using C = CacgmmCfg<DP, K, NT>;
-    constexpr int TE = C::TE, TM = C::TM;
+    constexpr int TE = C::TE;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     unsigned char* sp = smem_raw;
     unsigned char* ys_raw = sp;                     sp += C::YS_BYTES;   // frame tiles / matrix scratch
@@ -171,14 +162,14 @@ __global__ void __launch_bounds__(NT, MINB) cacgmm_em_kernel(const CacgmmParams 
     double* logdet_s = reinterpret_cast<double*>(sp);                    // [32]
     double* pi_s = logdet_s + 32;                                        // [32]
     double* tr_s = logdet_s + 64;                                        // [32]
-    double* gred = logdet_s + 96;                                        // [NW][K]
+    double* apri_s = logdet_s + 96;                                      // [32] pi_k exp(min_j logdet_j - logdet_k)
+    double* gred = logdet_s + 128;                                       // [NW][K]
     double* jred = gred + C::NW * K;                                     // [64]
     double* pivbuf = jred + 64;                                          // [K][DP] sweep pivots
     JacobiRot* jrot = reinterpret_cast<JacobiRot*>(pivbuf + K * DP);     // [16]
     int* flags_s = reinterpret_cast<int*>(jrot + 16);                    // [K] slow-path flags, [31] exact flag
     unsigned short* tri_tab = reinterpret_cast<unsigned short*>(flags_s + 32);   // [NP] (i << 8 | c)
-    float2* yf = reinterpret_cast<float2*>(ys_raw);                      // E tile [TE][YLD] complex64
-    float2* ym = reinterpret_cast<float2*>(ys_raw);                      // M tiles [2][TM][YLD] complex64
+    float2* yf = reinterpret_cast<float2*>(ys_raw);                      // resident super tile [TE][YLD] complex64, planar rows
 
     const int tid = threadIdx.x;
     const int lane = tid & 31, warp = tid >> 5;
@@ -232,7 +223,7 @@ __global__ void __launch_bounds__(NT, MINB) cacgmm_em_kernel(const CacgmmParams 
                 const int d = i / TE, t = i - d * TE;
                 float2 v = make_float2(0.f, 0.f);
                 if (d < D && s0 + t < T) v = __ldg(&Yg[(size_t)d * Ts + s0 + t]);
-                yf[t * C::YLD + d] = v;
+                yf[t * C::YLD + ypos<DP>(d)] = v;
             }
             __syncthreads();
             {
@@ -260,29 +251,58 @@ __global__ void __launch_bounds__(NT, MINB) cacgmm_em_kernel(const CacgmmParams 
 #pragma unroll
                         for (int k = 0; k < K; ++k) { g[k] /= tot; w[k] = g[k] * s; }
                     } else {
-                        double lp[K], qn[K];
-                        double mx = -INFINITY;
+                        // gamma_k ~ pi_k exp(-logdet_k) q_k^-D  (mixture_model_utils.py:32-53 with
+                        // log_pdf = -D log q - logdet).  The softmax is invariant to a common factor, so
+                        // instead of K logarithms and K exponentials: r_k = q_min / q_k <= 1, r_k^D by
+                        // repeated squaring, times the per-pass class constants apri_k <= 1 -- no overflow,
+                        // relative error ~D eps.  Frames where every active term is below 1e-200 (the
+                        // reference's own max-subtraction keeps up to e^(logdet spread) more range there)
+                        // take the reference's log / exp form.
+                        double qn[K], iq[K];
+                        double qmin = INFINITY;
 #pragma unroll
                         for (int k = 0; k < K; ++k) {
                             const double q = fmax(fabs(qa[k] + qb[k]) * s, GSS_F64_TINY);
                             qn[k] = q;
-                            lp[k] = -(double)D * log(q) - logdet_s[k];
-                            mx = fmax(mx, lp[k]);
+                            qmin = fmin(qmin, q);
+                        }
+                        double u[K], bp[K];
+#pragma unroll
+                        for (int k = 0; k < K; ++k) { iq[k] = 1.0 / qn[k]; bp[k] = qmin * iq[k]; u[k] = 1.0; }
+                        for (int e = D; e; e >>= 1) {
+#pragma unroll
+                            for (int k = 0; k < K; ++k) { if (e & 1) u[k] *= bp[k]; bp[k] *= bp[k]; }
                         }
                         double den = 0.0;
 #pragma unroll
                         for (int k = 0; k < K; ++k) {
-                            double a = exp(lp[k] - mx) * pi_s[k];
+                            double a = u[k] * apri_s[k];
                             if (guided && !act[(size_t)k * p.T_act + t]) a = 0.0;
                             g[k] = a; den += a;
                         }
-                        den = fmax(den, GSS_F64_TINY);
+                        if (!(den > 1e-200)) {
+                            double lp[K];
+                            double mx = -INFINITY;
+#pragma unroll
+                            for (int k = 0; k < K; ++k) {
+                                lp[k] = -(double)D * log(qn[k]) - logdet_s[k];
+                                mx = fmax(mx, lp[k]);
+                            }
+                            den = 0.0;
+#pragma unroll
+                            for (int k = 0; k < K; ++k) {
+                                double a = exp(lp[k] - mx) * pi_s[k];
+                                if (guided && !act[(size_t)k * p.T_act + t]) a = 0.0;
+                                g[k] = a; den += a;
+                            }
+                        }
+                        const double iden = 1.0 / fmax(den, GSS_F64_TINY);
 #pragma unroll
                         for (int k = 0; k < K; ++k) {
-                            double v = g[k] / den;
+                            double v = g[k] * iden;
                             if (eps != 0.0) v = fmin(fmax(v, eps), 1.0 - eps);
                             g[k] = v;
-                            w[k] = v * s / qn[k];
+                            w[k] = v * s * iq[k];
                         }
                     }
                     if (is_final) {
@@ -303,65 +323,48 @@ __global__ void __launch_bounds__(NT, MINB) cacgmm_em_kernel(const CacgmmParams 
             for (int a = 0; a < 4; ++a)
 #pragma unroll
                 for (int k = 0; k < K; ++k) macc[a][k] = cmake(0.0, 0.0);
-            // M tiles: raw complex64, double buffered, cp.async straight into planar rows (even channels
-            // first, then odd ones: the 2x2 blocks of consecutive lanes read consecutive 8 B chunks);
-            // float32 -> float64 happens on read (XU pipe) -- the tile traffic on the shared-memory
-            // pipe, which bounds this kernel together with the FP64 pipe, is halved.
-            auto stage_m = [&](int buf, int tbase) {
-                float2* dst = ym + buf * (TM * C::YLD);
-                for (int i = tid; i < DP * TM; i += NT) {
-                    const int d = i / TM, t = i - d * TM;
-                    float2* q = &dst[t * C::YLD + (d & 1) * (DP / 2) + (d >> 1)];
-                    if (d < D && tbase + t < T) cp_async8(q, &Yg[(size_t)d * Ts + tbase + t]);
-                    else *q = make_float2(0.f, 0.f);
+            // The M phase reads the SAME resident complex64 tile as the E phase (planar rows: the 2x2
+            // blocks of consecutive lanes read consecutive 8 B chunks); float32 -> float64 happens on
+            // read.  Group m_g takes frames m_g, m_g + NG, ... of the super tile; operands of the next
+            // frame are loaded ahead of the FMAs of the current one.
+            if (m_active) {
+                const int tn = s1 - s0;
+                int t = m_g;
+                float2 fa0, fa1, fb0, fb1;
+                double wk[K];
+                if (t < tn) {
+                    const float2* yrow = yf + t * C::YLD;
+                    fa0 = yrow[bi]; fa1 = yrow[DP / 2 + bi]; fb0 = yrow[bj]; fb1 = yrow[DP / 2 + bj];
+                    const double* wr = wsm + t * C::KP;
+#pragma unroll
+                    for (int k = 0; k < K; ++k) wk[k] = wr[k];
                 }
-            };
-            stage_m(0, s0);
-            int mbuf = 0;
-            for (int t0 = s0; t0 < s1; t0 += TM, mbuf ^= 1) {
-                cp_async_commit_wait_all();
-                __syncthreads();                              // tile mbuf landed; everybody left tile mbuf^1
-                if (t0 + TM < s1) stage_m(mbuf ^ 1, t0 + TM); // next tile behind the FMAs
-                if (m_active) {
-                    const float2* ytile = ym + mbuf * (TM * C::YLD);
-                    const int tn = min(TM, s1 - t0);
-                    int t = m_g;
-                    float2 fa0, fa1, fb0, fb1;
-                    double wk[K];
-                    if (t < tn) {
-                        const float2* yrow = ytile + t * C::YLD;
+                while (t < tn) {
+                    const cd a0 = cmake((double)fa0.x, (double)fa0.y), a1 = cmake((double)fa1.x, (double)fa1.y);
+                    const cd b0 = cmake((double)fb0.x, (double)fb0.y), b1 = cmake((double)fb1.x, (double)fb1.y);
+                    double wc[K];
+#pragma unroll
+                    for (int k = 0; k < K; ++k) wc[k] = wk[k];
+                    const int tnext = t + C::NG;
+                    if (tnext < tn) {
+                        const float2* yrow = yf + tnext * C::YLD;
                         fa0 = yrow[bi]; fa1 = yrow[DP / 2 + bi]; fb0 = yrow[bj]; fb1 = yrow[DP / 2 + bj];
-                        const double* wr = wsm + (t0 - s0 + t) * C::KP;
+                        const double* wr = wsm + tnext * C::KP;
 #pragma unroll
                         for (int k = 0; k < K; ++k) wk[k] = wr[k];
                     }
-                    while (t < tn) {
-                        const cd a0 = cmake((double)fa0.x, (double)fa0.y), a1 = cmake((double)fa1.x, (double)fa1.y);
-                        const cd b0 = cmake((double)fb0.x, (double)fb0.y), b1 = cmake((double)fb1.x, (double)fb1.y);
-                        double wc[K];
+                    cd P[4];
+                    P[0] = cmulc(a0, b0); P[1] = cmulc(a0, b1);
+                    P[2] = cmulc(a1, b0); P[3] = cmulc(a1, b1);
 #pragma unroll
-                        for (int k = 0; k < K; ++k) wc[k] = wk[k];
-                        const int tnext = t + C::NG;
-                        if (tnext < tn) {                     // operands of the next frame, ahead of the FMAs
-                            const float2* yrow = ytile + tnext * C::YLD;
-                            fa0 = yrow[bi]; fa1 = yrow[DP / 2 + bi]; fb0 = yrow[bj]; fb1 = yrow[DP / 2 + bj];
-                            const double* wr = wsm + (t0 - s0 + tnext) * C::KP;
+                    for (int k = 0; k < K; ++k) {
 #pragma unroll
-                            for (int k = 0; k < K; ++k) wk[k] = wr[k];
+                        for (int a = 0; a < 4; ++a) {
+                            macc[a][k].x = fma(wc[k], P[a].x, macc[a][k].x);
+                            macc[a][k].y = fma(wc[k], P[a].y, macc[a][k].y);
                         }
-                        cd P[4];
-                        P[0] = cmulc(a0, b0); P[1] = cmulc(a0, b1);
-                        P[2] = cmulc(a1, b0); P[3] = cmulc(a1, b1);
-#pragma unroll
-                        for (int k = 0; k < K; ++k) {
-#pragma unroll
-                            for (int a = 0; a < 4; ++a) {
-                                macc[a][k].x = fma(wc[k], P[a].x, macc[a][k].x);
-                                macc[a][k].y = fma(wc[k], P[a].y, macc[a][k].y);
-                            }
-                        }
-                        t = tnext;
                     }
+                    t = tnext;
                 }
             }
             __syncthreads();
@@ -640,6 +643,13 @@ __global__ void __launch_bounds__(NT, MINB) cacgmm_em_kernel(const CacgmmParams 
             __syncthreads();
         }
 
+        // ---- per-pass class constants of the softmax: pi_k exp(min_j logdet_j - logdet_k) <= 1 ----
+        if (tid < K) {
+            double ldmin = logdet_s[0];
+#pragma unroll
+            for (int k = 1; k < K; ++k) ldmin = fmin(ldmin, logdet_s[k]);
+            apri_s[tid] = pi_s[tid] * exp(ldmin - logdet_s[tid]);
+        }
         // ---- optional model outputs after the last M-step ----
         if (pass == total_iters - 1) {
             if (p.weight_out && tid < K) p.weight_out[(size_t)bf * K + tid] = pi_s[tid];

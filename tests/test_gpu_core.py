@@ -286,16 +286,15 @@ def test_ragged_batch_equals_single_utterances():
 def test_gss_rank_deficient_class():
     """A speaker with fewer active frames than channels: its class covariance is (numerically)
     singular, the reference floors the eigenvalues at 1e-10 -> exact (Jacobi) path every pass.
-    The floored directions make the problem ill-conditioned in the reference itself, hence the
-    looser bound on the few affected frames and the tight one on the bulk."""
+    The oracle itself is well conditioned here (a 1 + 1e-12 rescale of its input moves its
+    posteriors by 8e-14), so the plain 1e-4 bar applies to every frame."""
     Obs, act = synth.make_utterance(31, D=8, T=200, F=6, K=3)
     act[1] = False
     act[1, 40:45] = True                      # 5 active frames < D = 8
     got, ref = _gss_both(Obs, act, 10)
     assert np.isfinite(got).all()
     err = np.abs(got - ref)
-    assert np.quantile(err, 0.99) < 1e-4, np.quantile(err, 0.99)
-    assert err.max() < 5e-2, err.max()
+    assert err.max() < 1e-4, err.max()
 
 
 def test_single_call_enhance_equals_blocks():
@@ -340,8 +339,10 @@ def test_reverberant_speech_like_stagewise():
     post = ops.cacgmm(Yw, torch.from_numpy(act.astype(np.uint8))[None].to(dev), 20)
     m_dev = ops.unpack_fkt_to_ktf(post)[0].cpu().numpy()
     ref = oracle.gss_posteriors(W64, act, 20)
+    # the EM on this data is well conditioned in the reference (1 + 1e-12 rescale of the float64
+    # oracle's input: 1e-11 in the posteriors), so the plain 1e-4 bar applies to every frame
     err = np.abs(m_dev - ref)
-    assert np.quantile(err, 0.999) < 1e-4 and err.max() < 2e-3, (np.quantile(err, 0.999), err.max())
+    assert err.max() < 1e-4, (np.quantile(err, 0.999), err.max())
     tm = m_dev[0].astype(np.float64); dm = m_dev[1:].sum(0).astype(np.float64)
     X = ops.beamform(Yw, post[:, :, 0].contiguous(), post[:, :, 1:].sum(dim=2))
     refX = oracle.beamform(W64, tm, dm)
