@@ -147,11 +147,29 @@ int gss_beamform_from_posterior_c64(const gss_c64* Y, const float* posterior,
  * The correlation build R = Yt L^-1 Yt^H, P = Yt L^-1 Y^H runs on the INT8 tensor cores
  * (tcgen05.mma kind::i8, exact digit-split integer arithmetic, float64 recombination) when
  * taps * D >= 48; bins whose normal equations are too ill conditioned for its 2^-38 truncation are
- * detected after the factorisation and re-done with the float64 (FP64 MMA) build inside the same
- * call, still asynchronously.  Environment: GSS_WPE_GRAM=f64|i8, GSS_WPE_I8_TAU (re-do threshold). */
+ * detected after the factorisation (a-posteriori check on the Cholesky pivots) and re-done with the
+ * float64 (FP64 MMA) build inside the same call, still asynchronously.  A bin that was flagged once
+ * stays on the float64 list for the remaining iterations of the call (no INT8 build for it). */
 int gss_wpe_c64(const gss_c64* Y, gss_c64* X, int taps, int delay, int iterations,
                 int psd_context, int B, int F, int D, int T, const int* T_per_utt,
                 int* info, void* ws, size_t ws_bytes, void* stream);
+
+/* Same with per-call options (no process-global switches; calls on different streams may differ):
+ * gram_mode  GSS_WPE_GRAM_AUTO (what gss_wpe_c64 does), _F64 (float64 build for every bin),
+ *            _I8 (INT8 build only, no re-do: diagnostics), _I8_REDO (INT8 + float64 re-do);
+ * i8_tau     threshold of the a-posteriori check (< 0: default 1e-3);
+ * stats      device int32[4] or NULL, ACCUMULATED (caller zeroes): [0] bins processed, [1] bins that
+ *            ended the call on the float64 list, [2] float64 re-do builds (bins x iterations).
+ * A caller that sees stats[1] / stats[0] > 1/2 (reverberant, low-noise recordings) should pass
+ * GSS_WPE_GRAM_F64 for the following batches: pb_chime5_b200.core.WPE does exactly that. */
+#define GSS_WPE_GRAM_AUTO    -1
+#define GSS_WPE_GRAM_F64      0
+#define GSS_WPE_GRAM_I8       1
+#define GSS_WPE_GRAM_I8_REDO  2
+int gss_wpe_c64_ex(const gss_c64* Y, gss_c64* X, int taps, int delay, int iterations,
+                   int psd_context, int B, int F, int D, int T, const int* T_per_utt,
+                   int gram_mode, double i8_tau, int* stats,
+                   int* info, void* ws, size_t ws_bytes, void* stream);
 
 /* ---- whole STFT-domain hot path in one call (Enhancer.enhance_observation without the
  * transforms, core.py:524-564), reference layouts on both sides ---------------------
@@ -177,28 +195,6 @@ int gss_stft_f32(const float* x, gss_c64* Y, int B, int D, int N,
 /* X (B,F,T) c64 -> x (B, T*shift + size - shift - 2*(size-shift)*fading) f32 */
 int gss_istft_f32(const gss_c64* X, float* x, int B, int T,
                   int size, int shift, int fading, void* ws, size_t ws_bytes, void* stream);
-
-/* ---- diagnostics (used by tests/ and tools/, not by the product path) -----------
- * WPE correlation-build selection: gram_mode -1 = default (environment GSS_WPE_GRAM=f64|i8, else
- * INT8 tensor cores with float64 re-do of ill-conditioned bins), 0 = float64 (DMMA), 1 = INT8
- * only, 2 = INT8 + re-do; tau < 0 = default threshold of the re-do test. */
-int gss_debug_wpe_config(int gram_mode, double tau);
-/* bins re-done in float64 since the last reset (synchronises the device) */
-int gss_debug_wpe_redo_count(int reset);
-/* one correlation build: Y (B,F,D,T) c64, inv (B,F,T) f64 -> Raug (B,F,taps*D+D,taps*D) c128,
- * lower trapezoid (rows [0,LD): R, rows [LD,LD+D): P^H); mode 0 = float64, 1 = INT8.
- * Workspace: gss_workspace_bytes(GSS_OP_WPE, ...). */
-int gss_debug_wpe_gram(const gss_c64* Y, const double* inv, double* Raug, int mode, int variant,
-                       int B, int F, int D, int T, int taps, int delay, const int* T_per_utt,
-                       void* ws, size_t ws_bytes, void* stream);
-
-/* EXPERIMENTAL building block of the tensor-core EM iteration, not used by
- * any other entry point: the CACGMM M-step covariance Phi[b,f,k] = sum_t w[b,f,k,t] y y^H
- * (complex_angular_central_gaussian.py:293-300) on the INT8 tensor cores with exact digit-split
- * arithmetic.  Y (B,F,D,T) c64, w (B,F,K,T) f64 >= 0, Phi (B,F,K,D,D) c128 (full Hermitian).
- * Built for D in {4, 8, 16, 24}, K * 2 D <= 256; workspace B F (ceil(T/32) 320 D + 4 (D + K)) + 1 KiB. */
-int gss_debug_mstep_i8(const gss_c64* Y, const double* w, double* Phi, int B, int F, int D, int T, int K,
-                       const int* T_per_utt, void* ws, size_t ws_bytes, void* stream);
 
 #ifdef __cplusplus
 }

@@ -11,6 +11,9 @@ from pathlib import Path
 
 _HERE = Path(__file__).resolve().parent
 LIB_PATH = Path(os.environ.get('GSS_LIB', _HERE / 'csrc' / 'libgss.so'))
+# developer / measurement API (include/gss_dev.h): a superset of the product library, loaded only by
+# tests/, tools/ and the side measurements of bench.py -- never by the product modules
+DEV_LIB_PATH = Path(os.environ.get('GSS_DEV_LIB', _HERE / 'csrc' / 'libgss_dev.so'))
 
 GSS_ERR_ARG = -1
 GSS_ERR_UNSUPPORTED = -2
@@ -50,16 +53,25 @@ _SIGNATURES = {
     'gss_beamform_from_posterior_c64': (_i, [_p, _p, _p, _p, _p, _p, _i, _i, _i,
                                              _i, _i, _i, _i, _i, _p, _p, _p, _p, _p, _sz, _p]),
     'gss_wpe_c64': (_i, [_p, _p, _i, _i, _i, _i, _i, _i, _i, _i, _p, _p, _p, _sz, _p]),
+    'gss_wpe_c64_ex': (_i, [_p, _p, _i, _i, _i, _i, _i, _i, _i, _i, _p, _i, _d, _p, _p, _p, _sz, _p]),
     'gss_enhance_c64': (_i, [_p] * 8 + [_i] * 15 + [_p, _p, _sz, _p]),
     'gss_stft_f32': (_i, [_p, _p, _i, _i, _i, _i, _i, _i, _p, _sz, _p]),
     'gss_istft_f32': (_i, [_p, _p, _i, _i, _i, _i, _i, _p, _sz, _p]),
-    'gss_debug_wpe_config': (_i, [_i, _d]),
-    'gss_debug_wpe_redo_count': (_i, [_i]),
-    'gss_debug_mstep_i8': (_i, [_p, _p, _p, _i, _i, _i, _i, _i, _p, _p, _sz, _p]),
-    'gss_debug_wpe_gram': (_i, [_p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _i, _p, _p, _sz, _p]),
 }
 
+_DEV_SIGNATURES = {
+    'gss_debug_mstep_i8': (_i, [_p, _p, _p, _i, _i, _i, _i, _i, _p, _p, _sz, _p]),
+    'gss_debug_wpe_gram': (_i, [_p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _i, _p, _p, _sz, _p]),
+    'gss_debug_fp64_peak_scratch_bytes': (_sz, []),
+    'gss_debug_fp64_peak': (_i, [_i, _i, _p, C.POINTER(_d), _p]),
+}
+
+WPE_GRAM_AUTO, WPE_GRAM_F64, WPE_GRAM_I8, WPE_GRAM_I8_REDO = -1, 0, 1, 2
+WPE_GRAM_MODES = {None: WPE_GRAM_AUTO, 'auto': WPE_GRAM_AUTO, 'f64': WPE_GRAM_F64, 'i8': WPE_GRAM_I8,
+                  'i8+redo': WPE_GRAM_I8_REDO}
+
 _lib = None
+_dev_lib = None
 
 
 def exported_symbols():
@@ -83,15 +95,36 @@ def lib():
     return _lib
 
 
-def last_error():
-    return lib().gss_last_error().decode('utf-8', 'replace')
+def dev_exported_symbols():
+    """Names include/gss_dev.h declares (libgss_dev.so only)."""
+    return sorted(_DEV_SIGNATURES)
 
 
-def check(rc):
-    """Map a C return code to the exception type the reference would raise."""
+def dev_lib():
+    """libgss_dev.so: the product ABI plus the gss_debug_* developer entry points."""
+    global _dev_lib
+    if _dev_lib is None:
+        if not DEV_LIB_PATH.exists():
+            raise RuntimeError(f'{DEV_LIB_PATH} not found: build it with pb_chime5_b200/csrc/build.sh')
+        handle = C.CDLL(str(DEV_LIB_PATH))
+        for name, (res, args) in {**_SIGNATURES, **_DEV_SIGNATURES}.items():
+            fn = getattr(handle, name)
+            fn.restype = res
+            fn.argtypes = args
+        _dev_lib = handle
+    return _dev_lib
+
+
+def last_error(handle=None):
+    return (handle or lib()).gss_last_error().decode('utf-8', 'replace')
+
+
+def check(rc, handle=None):
+    """Map a C return code to the exception type the reference would raise.
+    handle: the library the call went to (default: the product library)."""
     if rc == 0:
         return
-    msg = last_error()
+    msg = last_error(handle)
     if rc == GSS_ERR_ARG:
         raise AssertionError(msg)
     if rc == GSS_ERR_UNSUPPORTED:

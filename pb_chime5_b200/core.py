@@ -16,6 +16,7 @@ no host round trip).
 from __future__ import annotations
 
 import inspect
+import os
 from dataclasses import dataclass
 from functools import cached_property
 from pathlib import Path
@@ -92,15 +93,64 @@ def activity_time_to_frequency(time_activity, stft_window_length, stft_shift, st
 
 @dataclass
 class WPE:
-    """Dereverberation block.  Reference: pb_chime5/core.py:41-88."""
+    """Dereverberation block.  Reference: pb_chime5/core.py:41-88.
+
+    Correlation-build policy (device side, see include/gss.h `gss_wpe_c64_ex`): INT8 tensor cores
+    with a float64 re-do of the bins an a-posteriori check flags.  On reverberant, low-noise
+    recordings nearly every bin is flagged, so the INT8 attempt is wasted work: the block reads the
+    flag statistics of its earlier calls (asynchronously -- it never waits for them) and, once more
+    than half of the bins of a call ended on the float64 list, sends the following batches straight
+    to the float64 build, probing the INT8 path again every `REPROBE` calls.
+    `GSS_WPE_GRAM=f64|i8|i8+redo|auto` in the environment pins the policy."""
     taps: int
     delay: int
     iterations: int
     psd_context: int
 
-    def _run(self, Y, frames=None):
+    REPROBE = 32            # calls between two INT8 probes while the float64 policy is active
+
+    def _policy(self):
+        st = self.__dict__.setdefault('_gram_state', dict(mode=None, calls_in_f64=0, pending=[], last_fraction=None))
+        env = os.environ.get('GSS_WPE_GRAM')
+        if env:
+            return st, (None if env == 'auto' else env), False
+        # harvest finished statistics (event.query() does not block)
+        keep = []
+        for ev, host in st['pending']:
+            if ev.query():
+                bins, on_list = int(host[0]), int(host[1])
+                if bins > 0:
+                    st['last_fraction'] = on_list / bins
+                    st['mode'] = 'f64' if on_list * 2 > bins else None
+                    st['calls_in_f64'] = 0
+            else:
+                keep.append((ev, host))
+        st['pending'] = keep
+        if st['mode'] == 'f64':
+            st['calls_in_f64'] += 1
+            if st['calls_in_f64'] % self.REPROBE == 0:
+                return st, None, True                    # probe: INT8 + re-do, with statistics
+            return st, 'f64', False
+        return st, None, True
+
+    def _run(self, Y, frames=None, info=None):
         """Y (B,F,D,T) complex64 on the device -> same shape.  frames: valid frames per utterance."""
-        return ops.wpe(Y, self.taps, self.delay, self.iterations, self.psd_context, frames=frames)
+        st, mode, want_stats = self._policy()
+        stats = torch.zeros(4, dtype=torch.int32, device=Y.device) if want_stats else None
+        X = ops.wpe(Y, self.taps, self.delay, self.iterations, self.psd_context, frames=frames,
+                    gram_mode=mode, stats=stats, info=info)
+        if stats is not None:
+            host = torch.empty(4, dtype=torch.int32, pin_memory=True)
+            host.copy_(stats, non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record()
+            st['pending'] = st['pending'][-3:] + [(ev, host)]
+        return X
+
+    @property
+    def last_float64_fraction(self):
+        """fraction of bins that ended the last harvested call on the float64 list (None: unknown)"""
+        return self.__dict__.get('_gram_state', {}).get('last_fraction')
 
     def __call__(self, Obs, stack=None, debug=False):
         ndim = Obs.ndim
@@ -180,9 +230,9 @@ class GSS:
     iterations_post: int
     verbose: bool = True
 
-    def _run(self, Y, activity, frames=None):
+    def _run(self, Y, activity, frames=None, info=None):
         """Y (B,F,D,T) c64, activity (B,K,T_act) uint8/bool -> posterior (B,F,K,T) f32."""
-        return ops.cacgmm(Y, activity, self.iterations, self.iterations_post, frames=frames)
+        return ops.cacgmm(Y, activity, self.iterations, self.iterations_post, frames=frames, info=info)
 
     def __call__(self, Obs, acitivity_freq, debug=False):
         x, was_np = _to_device(Obs, torch.complex64)                     # (D,T,F)
@@ -247,11 +297,11 @@ class Beamformer:
         self._check_postfilter()
         return ops.beamform(Y, target_mask, distortion_mask, bf=bf, postfilter=self.postfilter, bf_arg=arg)
 
-    def _run_from_posterior(self, Y, posterior, target_index, start_ctx, end_ctx, frames=None):
+    def _run_from_posterior(self, Y, posterior, target_index, start_ctx, end_ctx, frames=None, info=None):
         bf, arg = self._bf_args()
         self._check_postfilter()
         return ops.beamform_from_posterior(Y, posterior, target_index, start_ctx, end_ctx, bf=bf,
-                                           postfilter=self.postfilter, bf_arg=arg, frames=frames)
+                                           postfilter=self.postfilter, bf_arg=arg, frames=frames, info=info)
 
     def __call__(self, Obs, target_mask, distortion_mask, debug=False):
         self._bf_args()
@@ -323,19 +373,30 @@ class Enhancer:
         return _from_device(out.reshape(*lead, out.shape[-1]), was_np, np.float64)
 
     # ---- the device-resident hot path ---------------------------------------
+    STAGES = ('wpe', 'cacgmm', 'beamform')
+
     def enhance_stft_batch(self, Y, activity_freq, target_index, start_ctx, end_ctx, return_masks=False,
-                           frames=None):
+                           frames=None, info=None):
         """Y (B,F,D,T) complex64 CUDA (bin-major), activity_freq (B,K,T_act) uint8,
         target_index / start_ctx / end_ctx (B) int32 -> X_hat (B,F,T) complex64
         [, posterior (B,F,K,T) float32].  core.py:524-564 without host round trips.
         frames: optional (B) valid frame counts for a ragged batch padded to T (each utterance
-        gives exactly the result it would give alone; padded frames come back as zeros)."""
+        gives exactly the result it would give alone; padded frames come back as zeros).
+        info: optional (3, B) int32 device tensor (`ops.new_info(B, dev, 3)`): the status words of
+        the three stages are left there and the call does not synchronise -- the caller checks them
+        with `ops.check_info(info, Enhancer.STAGES)` when it fetches the results.  Without it the
+        words are checked here (one device synchronisation at the end of the batch)."""
+        own = info is None
+        if own:
+            info = ops.new_info(Y.shape[0], Y.device, stages=3)
         if self.wpe_block is not None:
-            Y = self.wpe_block._run(Y, frames)
-        post = self.gss_block._run(Y, activity_freq, frames)
+            Y = self.wpe_block._run(Y, frames, info=info[0])
+        post = self.gss_block._run(Y, activity_freq, frames, info=info[1])
         if not self.bf_drop_context:
             start_ctx = end_ctx = None
-        X = self.bf_block._run_from_posterior(Y, post, target_index, start_ctx, end_ctx, frames)
+        X = self.bf_block._run_from_posterior(Y, post, target_index, start_ctx, end_ctx, frames, info=info[2])
+        if own:
+            ops.check_info(info, self.STAGES)
         return (X, post) if return_masks else X
 
     def enhance_stft_host(self, Obs, acitivity_freq, target_index, start_ctx=None, end_ctx=None,
@@ -355,8 +416,11 @@ class Enhancer:
         act = torch.as_tensor(acitivity_freq).to(torch.uint8).to(dev, non_blocking=True)
         ivec = lambda v: None if v is None else torch.as_tensor(v, dtype=torch.int32).to(dev, non_blocking=True)
         Y = ops.pack_dtf_to_fdt(x)
+        info = ops.new_info(B, dev, stages=3)
         X, post = self.enhance_stft_batch(Y, act, ivec(target_index), ivec(start_ctx), ivec(end_ctx),
-                                          return_masks=True)
+                                          return_masks=True, info=info)
+        info_h = torch.empty(info.shape, dtype=info.dtype, pin_memory=True)
+        info_h.copy_(info, non_blocking=True)
         X_tf = ops.unpack_ft_to_tf(X)
         if out is None:
             out = {}
@@ -373,6 +437,7 @@ class Enhancer:
             mh.copy_(m_ktf, non_blocking=True)
             res['masks'] = mh
         torch.cuda.current_stream().synchronize()
+        ops.check_info(info_h, self.STAGES)
         return res
 
     def enhance_stft_host_stream(self, batches, return_masks=True, reuse_outputs=False):
@@ -411,18 +476,19 @@ class Enhancer:
                 ring[key] = [torch.empty(like.shape, dtype=like.dtype, pin_memory=True) for _ in range(3)]
             return ring[key][ring_pos[0] % 3]
 
-        def download(X_tf, m_ktf, done):
+        def download(X_tf, m_ktf, info, done):
             with torch.cuda.stream(d2h):
                 d2h.wait_event(done)
-                res = {'X_hat': host_slot('X_hat', X_tf)}
+                res = {'X_hat': host_slot('X_hat', X_tf), 'info': host_slot('info', info)}
                 res['X_hat'].copy_(X_tf, non_blocking=True)
+                res['info'].copy_(info, non_blocking=True)
                 if m_ktf is not None:
                     res['masks'] = host_slot('masks', m_ktf)
                     res['masks'].copy_(m_ktf, non_blocking=True)
                 ring_pos[0] += 1
                 fin = torch.cuda.Event()
                 fin.record(d2h)
-            return res, fin, (X_tf, m_ktf)        # keep the device tensors alive until the copy is done
+            return res, fin, (X_tf, m_ktf, info)  # keep the device tensors alive until the copy is done
 
         it = iter(batches)
         try:
@@ -441,20 +507,24 @@ class Enhancer:
                 if t is not None:
                     t.record_stream(compute)
             Y = ops.pack_dtf_to_fdt(x)
-            X, post = self.enhance_stft_batch(Y, a, ti, sc, ec, return_masks=True)
+            info = ops.new_info(x.shape[0], dev, stages=3)
+            X, post = self.enhance_stft_batch(Y, a, ti, sc, ec, return_masks=True, info=info)
             X_tf = ops.unpack_ft_to_tf(X)
             m_ktf = ops.unpack_fkt_to_ktf(post) if return_masks else None
             done = torch.cuda.Event()
             done.record(compute)
             X_tf.record_stream(d2h)
+            info.record_stream(d2h)
             if m_ktf is not None:
                 m_ktf.record_stream(d2h)
-            cur = download(X_tf, m_ktf, done)
+            cur = download(X_tf, m_ktf, info, done)
             if pending is not None:
                 pending[1].synchronize()
+                ops.check_info(pending[0]['info'], self.STAGES)    # host words: no device synchronisation
                 yield pending[0]
             pending = cur
         pending[1].synchronize()
+        ops.check_info(pending[0]['info'], self.STAGES)
         yield pending[0]
 
     def enhance_observation(self, obs, ex_array_activity, speaker_id, ex=None, debug=False):
@@ -490,54 +560,83 @@ class Enhancer:
                 X_hat=ops.unpack_ft_to_tf(X)[0].cpu().numpy(), x_hat=x_hat.cpu().numpy())
         return _from_device(x_hat, was_np, np.float64)
 
-    def enhance_observation_batch(self, obs_list, ex_array_activities, speaker_ids, exs=None):
-        """B utterances of different lengths in ONE pass of the hot path (what
-        `enhance_observation` does per utterance, core.py:514-571): the samples are zero padded to
-        the longest utterance, the STFT frames beyond an utterance's own count are masked through
-        the ragged-batch interface (`frames`), the iSTFT output is cut back.  Each result is
-        bit-identical to the single-utterance call.  obs_list: B arrays (D, N_b) with the same
-        D; ex_array_activities: B dicts {speaker: (N_b,) bool} with the same number of classes;
-        exs: B example dicts (context frames) or None.  Returns a list of (N'_b,) arrays."""
-        B = len(obs_list)
-        assert B > 0 and len(ex_array_activities) == B and len(speaker_ids) == B
+    def prepare_observation(self, obs, ex_array_activity, speaker_id, ex=None, pin=True):
+        """Host-side half of `enhance_observation` for one utterance, safe to run in a loader
+        thread while the GPU works on the previous batch: float32 samples in page-locked memory
+        (so the later host->device copy is asynchronous), frame-level activity (a4: boolean
+        bookkeeping, database.py:409-472), target index and context frames.  core.py:514-547."""
+        on_device = isinstance(obs, torch.Tensor) and obs.is_cuda
+        if on_device:
+            x = obs.to(torch.float32)
+        else:
+            x = obs if isinstance(obs, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(obs))
+            x = x.to(torch.float32)
+            if pin and torch.cuda.is_available() and not x.is_pinned():
+                x = x.pin_memory()
+        assert x.ndim == 2, x.shape
+        N = int(x.shape[-1])
+        frames = ops.stft_frames(N, self.stft_size, self.stft_shift, self.stft_fading)
+        af = activity_time_to_frequency(
+            np.array([np.asarray(v) for v in ex_array_activity.values()]), stft_window_length=self.stft_size,
+            stft_shift=self.stft_shift, stft_fading=self.stft_fading, stft_pad=True)
+        sc = ec = 0
+        if self.bf_drop_context and ex is not None:
+            sc, ec = self._context_frames(ex)
+        return dict(obs=x, N=N, frames=frames, activity_freq=af.astype(np.uint8), K=len(ex_array_activity),
+                    target=tuple(ex_array_activity.keys()).index(speaker_id), start_ctx=sc, end_ctx=min(ec, frames),
+                    numpy=not isinstance(obs, torch.Tensor))
+
+    def enhance_prepared_batch(self, preps):
+        """B prepared utterances of different lengths in ONE pass of the hot path: zero padded to
+        the longest, frames beyond an utterance's own count masked through the ragged-batch
+        interface, iSTFT output cut back.  Copies: one asynchronous host->device copy per utterance
+        (pinned source), one device->host copy of the padded result."""
+        B = len(preps)
         dev = _device()
-        was_np = not isinstance(obs_list[0], torch.Tensor)
-        D = int(obs_list[0].shape[0])
-        Ns = [int(o.shape[-1]) for o in obs_list]
-        K = len(ex_array_activities[0])
+        D, K = int(preps[0]['obs'].shape[0]), preps[0]['K']
+        Ns = [p['N'] for p in preps]
+        frames = [p['frames'] for p in preps]
         pad = (self.stft_size - self.stft_shift) if self.stft_fading else 0
-        frames = [ops.stft_frames(n, self.stft_size, self.stft_shift, self.stft_fading) for n in Ns]
         x = torch.zeros((B, D, max(Ns)), dtype=torch.float32, device=dev)
-        for b, o in enumerate(obs_list):
-            assert o.ndim == 2 and o.shape[0] == D, (o.shape, D)
-            x[b, :, :Ns[b]] = _to_device(o, torch.float32)[0]
+        for b, p in enumerate(preps):
+            assert p['obs'].shape[0] == D and p['K'] == K, (p['obs'].shape, D, p['K'], K)
+            x[b, :, :Ns[b]].copy_(p['obs'], non_blocking=True)
         Y = ops.stft(x, self.stft_size, self.stft_shift, self.stft_fading)              # (B,F,D,Tmax)
         Tmax = Y.shape[3]
         act = np.zeros((B, K, Tmax), dtype=np.uint8)
-        ti, sc, ec = [], [], []
-        for b in range(B):
-            a = ex_array_activities[b]
-            assert len(a) == K, (len(a), K)
-            af = activity_time_to_frequency(
-                np.array([np.asarray(v) for v in a.values()]), stft_window_length=self.stft_size,
-                stft_shift=self.stft_shift, stft_fading=self.stft_fading, stft_pad=True)
-            n = min(af.shape[-1], Tmax)
-            act[b, :, :n] = af[:, :n]
-            ti.append(tuple(a.keys()).index(speaker_ids[b]))
-            s_ctx = e_ctx = 0
-            if self.bf_drop_context and exs is not None:
-                s_ctx, e_ctx = self._context_frames(exs[b])
-            sc.append(s_ctx)
-            ec.append(min(e_ctx, frames[b]))
-        ivec = lambda v: torch.tensor(v, dtype=torch.int32, device=dev)
-        fr = ivec(frames)
-        X = self.enhance_stft_batch(Y, torch.from_numpy(act).to(dev), ivec(ti), ivec(sc), ivec(ec), frames=fr)
+        for b, p in enumerate(preps):
+            n = min(p['activity_freq'].shape[-1], Tmax)
+            act[b, :, :n] = p['activity_freq'][:, :n]
+        ivec = lambda v: torch.tensor(v, dtype=torch.int32, device=dev)                 # noqa: E731
+        info = ops.new_info(B, dev, stages=3)
+        X = self.enhance_stft_batch(Y, torch.from_numpy(act).to(dev, non_blocking=True), ivec([p['target'] for p in preps]),
+                                    ivec([p['start_ctx'] for p in preps]), ivec([p['end_ctx'] for p in preps]),
+                                    frames=ivec(frames), info=info)
         x_hat = ops.istft(X, self.stft_size, self.stft_shift, self.stft_fading)        # (B, Nmax')
-        out = []
-        for b in range(B):
-            n_out = frames[b] * self.stft_shift + self.stft_size - self.stft_shift - 2 * pad
-            out.append(_from_device(x_hat[b, :n_out], was_np, np.float64))
-        return out
+        n_out = [f * self.stft_shift + self.stft_size - self.stft_shift - 2 * pad for f in frames]
+        if all(not p['numpy'] for p in preps):
+            ops.check_info(info, self.STAGES)
+            return [x_hat[b, :n_out[b]] for b in range(B)]
+        host = torch.empty(x_hat.shape, dtype=x_hat.dtype, pin_memory=True)
+        host.copy_(x_hat, non_blocking=True)
+        info_h = info.cpu()                                   # synchronises: results and status words landed
+        torch.cuda.current_stream().synchronize()
+        ops.check_info(info_h, self.STAGES)
+        hn = host.numpy()
+        return [hn[b, :n_out[b]].astype(np.float64) if p['numpy'] else x_hat[b, :n_out[b]]
+                for b, p in enumerate(preps)]
+
+    def enhance_observation_batch(self, obs_list, ex_array_activities, speaker_ids, exs=None):
+        """B utterances of different lengths in ONE pass of the hot path (what
+        `enhance_observation` does per utterance, core.py:514-571).  Each result is bit-identical
+        to the single-utterance call.  obs_list: B arrays (D, N_b) with the same D;
+        ex_array_activities: B dicts {speaker: (N_b,) bool} with the same number of classes;
+        exs: B example dicts (context frames) or None.  Returns a list of (N'_b,) arrays."""
+        B = len(obs_list)
+        assert B > 0 and len(ex_array_activities) == B and len(speaker_ids) == B
+        preps = [self.prepare_observation(obs_list[b], ex_array_activities[b], speaker_ids[b],
+                                          None if exs is None else exs[b]) for b in range(B)]
+        return self.enhance_prepared_batch(preps)
 
     # ---- data plumbing (out of the hot path; uses the reference's I/O code) --
     def get_iterator(self, session_id):
@@ -546,18 +645,18 @@ class Enhancer:
             context_samples=self.context_samples, equal_start_context=True)
 
     def enhance_session(self, session_ids, audio_dir, dataset_slice=False, audio_dir_exist_ok=False,
-                        batch_size=8, skip_existing=False, strict=True):
+                        batch_size=8, skip_existing=False, strict=True, schedule='auto'):
         """core.py:333-394.  Work distribution: one process per GPU; rank r of W takes a static
         shard of the examples (the task farm of dlp_mpi.split_managed, see sharding.py) and runs
         it through the batching session driver (session.py: length-bucketed batches, audio
         prefetch, asynchronous wav writing).  `strict` (default, like the reference): the first
         failing example raises; `skip_existing`: resume an interrupted run."""
         from . import sharding
-        from .session import SessionScheduler
+        from .session import SessionScheduler, run_distributed
 
         audio_dir = Path(audio_dir)
         it = self.get_iterator(session_ids)
-        rank, world = sharding.rank_world()
+        rank, world = sharding.init_process_group()      # binds the GPU of this rank (torchrun / mpiexec / srun)
         datasets = _session_to_dataset()
         if rank == 0:
             audio_dir.mkdir(exist_ok=audio_dir_exist_ok or skip_existing)
@@ -573,14 +672,14 @@ class Enhancer:
                 it = it[dataset_slice]
             else:
                 raise ValueError(dataset_slice)
-        mine = [it[i] for i in sharding.shard_indices(len(it), rank, world)]
+        examples = [it[i] for i in range(len(it))]
 
         def path_fn(ex):
             return audio_dir / datasets.get(ex['session_id'], 'unknown') / f'{ex["example_id"]}.wav'
 
         sched = SessionScheduler(self, self._load_example, path_fn, self._finish_example,
                                  batch_size=batch_size, skip_existing=skip_existing, strict=strict)
-        return sched.run(mine)
+        return run_distributed(sched, examples, schedule)
 
     def _reference_array(self, ex):
         reference_array = self.reference_array

@@ -215,13 +215,13 @@ class Enhancer(_c6.Enhancer):
         return obs, ex_array_activity, ex['speaker_id']
 
     def enhance_session(self, session_ids, audio_dir, dataset_slice=False, audio_dir_exist_ok=False,
-                        batch_size=8, skip_existing=False, strict=True):
+                        batch_size=8, skip_existing=False, strict=True, schedule='auto'):
         """core_chime6_rttm.py:137-185: one directory per session ('dataset' = session id)."""
         from . import sharding
-        from .session import SessionScheduler
+        from .session import SessionScheduler, run_distributed
         audio_dir = Path(audio_dir)
         it = self.get_iterator(session_ids)
-        rank, world = sharding.rank_world()
+        rank, world = sharding.init_process_group()      # binds the GPU of this rank (torchrun / mpiexec / srun)
         if rank == 0:
             audio_dir.mkdir(exist_ok=audio_dir_exist_ok or skip_existing)
         sharding.barrier()
@@ -232,12 +232,12 @@ class Enhancer(_c6.Enhancer):
                 it = it[:dataset_slice] if isinstance(dataset_slice, int) else it[dataset_slice]
             else:
                 raise ValueError(dataset_slice)
-        mine = [it[i] for i in sharding.shard_indices(len(it), rank, world)]
+        examples = [it[i] for i in range(len(it))]
         sched = SessionScheduler(self, self._load_example,
                                  lambda ex: audio_dir / ex['dataset'] / f'{ex["example_id"]}.wav',
                                  self._finish_example, batch_size=batch_size, skip_existing=skip_existing,
                                  strict=strict)
-        return sched.run(mine)
+        return run_distributed(sched, examples, schedule)
 
 
 def get_enhancer(

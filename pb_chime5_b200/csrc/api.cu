@@ -45,6 +45,13 @@ size_t weighted_cov_ws_bytes(int B, int F, int D, int K);
 size_t wpe_ws_bytes(int Bc, int F, int D, int T, int L);
 size_t istft_ws_bytes(int B, int T, int size);
 size_t enhance_ws_bytes(int B, int F, int D, int T, int K, int L);
+size_t cacgmm_generic_ws_bytes(int B, int F, int D, int K);
+bool cacgmm_fast_path(int D, int K);
+size_t cacgmm_ws_bytes(int B, int F, int D, int K) {
+    if (!cacgmm_fast_path(D, K)) return cacgmm_generic_ws_bytes(B, F, D, K);
+    // warm-start eigenvectors of the exact path + flags
+    return align_up(((size_t)B * F * K + 2) * sizeof(int)) + align_up((size_t)B * F * K * D * (D + 2) * 16);
+}
 }
 
 extern "C" {
@@ -56,8 +63,7 @@ int gss_workspace_bytes(int op, int B, int F, int D, int T, int K, int L, size_t
     size_t n = 256;
     switch (op) {
         case GSS_OP_WEIGHTED_COV: n = weighted_cov_ws_bytes(B, F, D, K); break;
-        case GSS_OP_CACGMM:   // warm-start eigenvectors of the exact path + flags
-            n = align_up(((size_t)B * F * K + 2) * sizeof(int)) + align_up((size_t)B * F * K * D * (D + 2) * 16); break;
+        case GSS_OP_CACGMM: n = cacgmm_ws_bytes(B, F, D, K); break;
         case GSS_OP_BEAMFORM: n = beamform_ws_bytes(B, F, D); break;
         case GSS_OP_WPE: n = wpe_ws_bytes(B < 4 ? B : 4, F, D, T, L); break;   // utterances are processed in chunks
         case GSS_OP_STFT: n = 256; break;

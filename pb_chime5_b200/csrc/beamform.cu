@@ -12,7 +12,7 @@
 #include "smallmat.cuh"
 
 #ifndef GSS_DP_LIST
-#define GSS_DP_LIST GSS_CASE(2) GSS_CASE(4) GSS_CASE(6) GSS_CASE(8) GSS_CASE(10) GSS_CASE(12) GSS_CASE(16) GSS_CASE(20) GSS_CASE(24)
+#define GSS_DP_LIST GSS_CASE(2) GSS_CASE(4) GSS_CASE(6) GSS_CASE(8) GSS_CASE(10) GSS_CASE(12) GSS_CASE(16) GSS_CASE(20) GSS_CASE(24) GSS_CASE(28) GSS_CASE(32)
 #endif
 
 namespace gss {
@@ -246,7 +246,7 @@ static int launch_weighted_cov_small(const float2* Y, const WeightSrc& src, cd* 
 template <int DP>
 static int launch_weighted_cov(const float2* Y, const WeightSrc& src, cd* Phi, double* wsum,
                                int B, int F, int D, int T, int Kout, int normalize, cudaStream_t st) {
-    constexpr int NT = 256, TM = 64;
+    constexpr int NT = 256, TM = DP > 28 ? 32 : 64;          // static shared memory stays below 48 KB
     dim3 grid(B * F, (Kout + 1) / 2);
     weighted_cov_kernel<DP, NT, TM><<<grid, NT, 0, st>>>(Y, src, Phi, wsum, F, D, T, Kout, normalize);
     GSS_LAUNCH_CHECK("weighted_cov_kernel");
@@ -269,13 +269,11 @@ int weighted_cov_dispatch(const float2* Y, const WeightSrc& src, cd* Phi, double
             case 8: return launch_weighted_cov_small<8, 1>(Y, src, Phi, B, F, T, Kout, normalize, st);
         }
     }
-    const int DP = (D + 1) & ~1;
-    switch (DP) {
-#define GSS_CASE(dp) case dp: return launch_weighted_cov<dp>(Y, src, Phi, wsum, B, F, D, T, Kout, normalize, st);
-        GSS_DP_LIST
+    // any channel count runs on the next built padded size (padded channels are zero rows of the tile)
+#define GSS_CASE(dp) if (D <= dp) return launch_weighted_cov<dp>(Y, src, Phi, wsum, B, F, D, T, Kout, normalize, st);
+    GSS_DP_LIST
 #undef GSS_CASE
-        default: return fail(GSS_ERR_UNSUPPORTED, "weighted covariance: D=%d not built", D);
-    }
+    return fail(GSS_ERR_UNSUPPORTED, "weighted covariance: D=%d not built", D);
 }
 
 __global__ void c128_to_c64_kernel(const cd* __restrict__ src, float2* __restrict__ dst, size_t n) {

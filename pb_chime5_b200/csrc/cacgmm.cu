@@ -56,6 +56,14 @@ struct CacgmmParams {
 
 constexpr size_t cmax(size_t a, size_t b) { return a > b ? a : b; }
 
+// cacgmm_generic.cu: any D < 35, K < 20 (runtime shapes)
+size_t cacgmm_generic_ws_bytes(int B, int F, int D, int K);
+int cacgmm_generic_launch(const float2* Y, const uint8_t* activity, const int* Tper, float* posterior,
+                          double* weight_out, double* logdet_out, double* cov_out, int* info,
+                          int B, int F, int D, int T, int K, int T_act, int iterations, int iterations_post,
+                          double eps, double floor_, void* ws, size_t ws_bytes, cudaStream_t st);
+bool cacgmm_fast_path(int D, int K);
+
 // E-phase sub-blocking of the packed lower triangle: SB x SB blocks so that only
 // 2*SB complex values of the frame are live in registers at a time.
 __host__ __device__ constexpr int sub_block(int DP) {
@@ -75,8 +83,14 @@ struct CacgmmCfg {
     static constexpr int SB = sub_block(DP);
     static constexpr int NS = DP / SB;
     static constexpr int NSB = NS * (NS + 1) / 2;
+    // sweep: a thread owns a chunk of up to CH consecutive columns of one row of one class (registers);
+    // CH = the smallest width for which the K * NCH chunks fit the block
+    static constexpr int chunks_per_class(int ch) { int n = 0; for (int i = 0; i < DP; ++i) n += (i + ch) / ch; return n; }
+    static constexpr int pick_ch() { int ch = 1; while (K * chunks_per_class(ch) > NT) ++ch; return ch; }
+    static constexpr int CH = pick_ch();
+    static constexpr int NCH = chunks_per_class(CH);
     static constexpr size_t E_BYTES = size_t(TE) * YLD * sizeof(float2);       // ONE resident super tile (E and M phase)
-    static constexpr size_t SWEEP_BYTES = size_t(K) * NP * sizeof(cd) + size_t(2) * K * DP * sizeof(cd) + 4 * K * 8 + 64;
+    static constexpr size_t SWEEP_BYTES = size_t(2) * K * DP * sizeof(cd) + 4 * K * 8 + size_t(K) * DP * 8 + 64;
     static constexpr size_t JAC_BYTES = size_t(3) * DP * JLD * sizeof(cd);
     static constexpr size_t YS_BYTES = cmax(E_BYTES, cmax(SWEEP_BYTES, JAC_BYTES));
     static constexpr size_t W_BYTES = size_t(TE) * KP * sizeof(double);
@@ -149,6 +163,93 @@ struct QuadAll<DP, K, NSB, NSB> {
     static __device__ __forceinline__ void run(const float2*, const cd*, double (&)[K], double (&)[K]) {}
 };
 
+// Symmetric sweep operator on the packed lower triangle of K class matrices at once (in place:
+// -Phi^-1; pivots = squared Cholesky pivots).  The chunk of a thread (up to CH consecutive columns of
+// one row of one class) stays in registers over all D sweep steps; per step only the pivot column
+// travels through shared memory (one barrier per step: the column of the next pivot is forwarded while
+// the current step is applied).  Not inlined: the fused kernel around it is at its register limit and
+// would keep the chunk in local memory.
+template <int DP, int K, int CH>
+__device__ __noinline__ void sweep_invert(cd (&sv_out)[CH], const cd* __restrict__ acc_k, const double* __restrict__ tr_s,
+                                          cd* __restrict__ colb, double* __restrict__ pivb, double* __restrict__ dinvb,
+                                          double* __restrict__ pivbuf, const bool sw_on, const int sw_k, const int sw_i,
+                                          const int sw_c0, const int sw_n, const int D) {
+    cd sv[CH];                                                          // registers for the whole function
+#pragma unroll
+    for (int n = 0; n < CH; ++n) sv[n] = cmake(0.0, 0.0);
+    if (sw_on) {
+        const double tr = tr_s[sw_k];
+        const double itr = (tr > 0.0 && isfinite(tr)) ? 1.0 / tr : 0.0;
+#pragma unroll
+        for (int n = 0; n < CH; ++n) {
+            const int c = sw_c0 + n;
+            cd v = cmake(0.0, 0.0);
+            if (n < sw_n) {
+                v = cscale(acc_k[tri(sw_i, c)], itr);
+                if (sw_i == c) v.y = 0.0;                               // force_hermitian (utils.py:323-334)
+                if (c == 0) {                                           // column of the first pivot
+                    colb[sw_k * DP + sw_i] = v;
+                    if (sw_i == 0) { pivb[sw_k] = v.x; dinvb[sw_k] = (v.x > 0.0 && isfinite(v.x)) ? 1.0 / v.x : 0.0; }
+                }
+            }
+            sv[n] = v;
+        }
+    }
+    __syncthreads();
+    for (int j = 0; j < D; ++j) {
+        const cd* col = colb + (j & 1) * K * DP;
+        cd* coln = colb + ((j + 1) & 1) * K * DP;
+        const double* piv = pivb + (j & 1) * K;
+        double* pivn = pivb + ((j + 1) & 1) * K;
+        const double* dinv = dinvb + (j & 1) * K;
+        double* dinvn = dinvb + ((j + 1) & 1) * K;
+        if (sw_on) {
+            const double d = dinv[sw_k];
+            const cd ui = col[sw_k * DP + sw_i];
+            const cd uid = cscale(ui, d);
+            const bool on_i = (sw_i == j);
+            const cd* colk = col + sw_k * DP + sw_c0;
+            cd vf = cmake(0.0, 0.0);                                // the entry of column j + 1, if this chunk has it
+#pragma unroll
+            for (int n = 0; n < CH; ++n) {
+                if (n >= sw_n) continue;
+                const int c = sw_c0 + n;
+                // branch-free: entries of row/column j are S*d (the stored value IS the column
+                // entry or its conjugate), the pivot becomes -d, everything else gets the
+                // rank-1 update  S - (u_i d) conj(u_c)
+                const cd s0v = sv[n];
+                const cd uc = colk[n];
+                const bool on_c = (c == j);
+                cd v = s0v;
+                cfmsc(v, uid, uc);
+                const cd vs = cscale(s0v, d);
+                v.x = (on_i | on_c) ? vs.x : v.x;
+                v.y = (on_i | on_c) ? vs.y : v.y;
+                v.x = (on_i & on_c) ? -d : v.x;
+                v.y = (on_i & on_c) ? 0.0 : v.y;
+                sv[n] = v;
+                vf.x = (c == j + 1) ? v.x : vf.x;
+                vf.y = (c == j + 1) ? v.y : vf.y;
+            }
+            if (on_i && j >= sw_c0 && j < sw_c0 + sw_n) pivbuf[sw_k * DP + j] = piv[sw_k];
+            // forward the column of the next pivot
+            if (j + 1 >= sw_c0 && j + 1 < sw_c0 + sw_n) {             // entry (i, j + 1): column part
+                coln[sw_k * DP + sw_i] = vf;
+                if (sw_i == j + 1) { pivn[sw_k] = vf.x; dinvn[sw_k] = (vf.x > 0.0 && isfinite(vf.x)) ? 1.0 / vf.x : 0.0; }
+            }
+            if (sw_i == j + 1) {                                       // entries (j + 1, c < j + 1): row part, conjugated
+#pragma unroll
+                for (int n = 0; n < CH; ++n)
+                    if (n < sw_n && sw_c0 + n != j + 1) coln[sw_k * DP + sw_c0 + n] = cconj(sv[n]);
+            }
+        }
+        __syncthreads();
+    }
+#pragma unroll
+    for (int n = 0; n < CH; ++n) sv_out[n] = sv[n];
+}
+
+
 template <int DP, int K, int NT, int MINB>
 __global__ void __launch_bounds__(NT, MINB) cacgmm_em_kernel(const CacgmmParams p) {
     using C = CacgmmCfg<DP, K, NT>;
@@ -192,6 +293,20 @@ __global__ void __launch_bounds__(NT, MINB) cacgmm_em_kernel(const CacgmmParams 
     while ((bi + 1) * (bi + 2) / 2 <= m_l) ++bi;
     const int bj = m_l - bi * (bi + 1) / 2;
     const int r0 = 2 * bi, c0 = 2 * bj;
+
+    // sweep role: chunk q = tid -> class sw_k, row sw_i, columns [sw_c0, sw_c0 + sw_n)
+    int sw_k = -1, sw_i = 0, sw_c0 = 0, sw_n = 0;
+    if (tid < K * C::NCH) {
+        sw_k = tid / C::NCH;
+        int r = tid - sw_k * C::NCH;
+        for (sw_i = 0; sw_i < DP; ++sw_i) {
+            const int nc = (sw_i + C::CH) / C::CH;
+            if (r < nc) break;
+            r -= nc;
+        }
+        sw_c0 = r * C::CH;
+        sw_n = min(C::CH, sw_i + 1 - sw_c0);
+    }
 
     const int total_iters = p.iterations + (p.iterations_post - 1);
     const int NPD = D * (D + 1) / 2;
@@ -329,42 +444,27 @@ __global__ void __launch_bounds__(NT, MINB) cacgmm_em_kernel(const CacgmmParams 
             // frame are loaded ahead of the FMAs of the current one.
             if (m_active) {
                 const int tn = s1 - s0;
-                int t = m_g;
-                float2 fa0, fa1, fb0, fb1;
-                double wk[K];
-                if (t < tn) {
-                    const float2* yrow = yf + t * C::YLD;
-                    fa0 = yrow[bi]; fa1 = yrow[DP / 2 + bi]; fb0 = yrow[bj]; fb1 = yrow[DP / 2 + bj];
-                    const double* wr = wsm + t * C::KP;
-#pragma unroll
-                    for (int k = 0; k < K; ++k) wk[k] = wr[k];
-                }
-                while (t < tn) {
+                const float2* yrow = yf + m_g * C::YLD;
+                const double* wr = wsm + m_g * C::KP;
+                // no software prefetch: with 40 accumulators live it only produced spills; the other
+                // warps of the two resident CTAs cover the shared-memory latency
+#pragma unroll 1
+                for (int t = m_g; t < tn; t += C::NG, yrow += C::NG * C::YLD, wr += C::NG * C::KP) {
+                    const float2 fa0 = yrow[bi], fa1 = yrow[DP / 2 + bi], fb0 = yrow[bj], fb1 = yrow[DP / 2 + bj];
                     const cd a0 = cmake((double)fa0.x, (double)fa0.y), a1 = cmake((double)fa1.x, (double)fa1.y);
                     const cd b0 = cmake((double)fb0.x, (double)fb0.y), b1 = cmake((double)fb1.x, (double)fb1.y);
-                    double wc[K];
-#pragma unroll
-                    for (int k = 0; k < K; ++k) wc[k] = wk[k];
-                    const int tnext = t + C::NG;
-                    if (tnext < tn) {
-                        const float2* yrow = yf + tnext * C::YLD;
-                        fa0 = yrow[bi]; fa1 = yrow[DP / 2 + bi]; fb0 = yrow[bj]; fb1 = yrow[DP / 2 + bj];
-                        const double* wr = wsm + tnext * C::KP;
-#pragma unroll
-                        for (int k = 0; k < K; ++k) wk[k] = wr[k];
-                    }
                     cd P[4];
                     P[0] = cmulc(a0, b0); P[1] = cmulc(a0, b1);
                     P[2] = cmulc(a1, b0); P[3] = cmulc(a1, b1);
 #pragma unroll
                     for (int k = 0; k < K; ++k) {
+                        const double w = wr[k];
 #pragma unroll
                         for (int a = 0; a < 4; ++a) {
-                            macc[a][k].x = fma(wc[k], P[a].x, macc[a][k].x);
-                            macc[a][k].y = fma(wc[k], P[a].y, macc[a][k].y);
+                            macc[a][k].x = fma(w, P[a].x, macc[a][k].x);
+                            macc[a][k].y = fma(w, P[a].y, macc[a][k].y);
                         }
                     }
-                    t = tnext;
                 }
             }
             __syncthreads();
@@ -461,76 +561,23 @@ __global__ void __launch_bounds__(NT, MINB) cacgmm_em_kernel(const CacgmmParams 
         //      operator (in place, packed lower; pivots = Cholesky pivots^2, logdet = sum log pivots).
         //      Thread-private entry metadata is decoded once per pass; one barrier per sweep step
         //      (the column of the next pivot is forwarded while the current step is applied).
-        cd* S = reinterpret_cast<cd*>(ys_raw);                                  // [K][NP]
-        cd* colb = S + K * C::NP;                                               // [2][K][DP] column of the pivot
+        cd* colb = reinterpret_cast<cd*>(ys_raw);                               // [2][K][DP] column of the pivot
         double* pivb = reinterpret_cast<double*>(colb + 2 * K * DP);            // [2][K] pivot
         double* dinvb = pivb + 2 * K;                                           // [2][K] 1 / pivot (0 if not positive): one division per class and step
+        double* diagb = dinvb + 2 * K;                                          // [K][DP] diagonal of the result
         const bool need_exact = flags_s[31] != 0;
         if (!need_exact) {
-            constexpr int EPT = (K * C::NP + NT - 1) / NT;                      // entries per thread
-            int ent_meta[EPT];                                                  // k << 16 | i << 8 | c ; -1 = none
+            constexpr int CH = C::CH;
+            cd sv[CH];
+            const bool sw_on = sw_k >= 0 && sw_i < D;
+            sweep_invert<DP, K, CH>(sv, acc_sm + (sw_on ? sw_k * C::NP : 0), tr_s, colb, pivb, dinvb, pivbuf,
+                                    sw_on, sw_k, sw_i, sw_c0, sw_n, D);
+            if (sw_on) {
 #pragma unroll
-            for (int n = 0; n < EPT; ++n) {
-                const int e = tid + n * NT;
-                int meta = -1;
-                if (e < K * C::NP) {
-                    const int k = e / C::NP, r = e - k * C::NP;
-                    if (r < NPD) {
-                        const unsigned ic = tri_tab[r];
-                        const int i = ic >> 8, c = ic & 255;
-                        meta = (k << 16) | (i << 8) | c;
-                        const double tr = tr_s[k];
-                        const double itr = (tr > 0.0 && isfinite(tr)) ? 1.0 / tr : 0.0;
-                        cd v = cscale(acc_sm[e], itr);
-                        if (i == c) v.y = 0.0;                                  // force_hermitian (utils.py:323-334)
-                        S[e] = v;
-                        if (c == 0) {                                           // column of the first pivot
-                            colb[k * DP + i] = v;
-                            if (i == 0) { pivb[k] = v.x; dinvb[k] = (v.x > 0.0 && isfinite(v.x)) ? 1.0 / v.x : 0.0; }
-                        }
-                    }
-                }
-                ent_meta[n] = meta;
+                for (int n = 0; n < CH; ++n)
+                    if (n < sw_n && sw_c0 + n == sw_i) diagb[sw_k * DP + sw_i] = -sv[n].x;
             }
             __syncthreads();
-            for (int j = 0; j < D; ++j) {
-                const cd* col = colb + (j & 1) * K * DP;
-                cd* coln = colb + ((j + 1) & 1) * K * DP;
-                const double* piv = pivb + (j & 1) * K;
-                double* pivn = pivb + ((j + 1) & 1) * K;
-                const double* dinv = dinvb + (j & 1) * K;
-                double* dinvn = dinvb + ((j + 1) & 1) * K;
-#pragma unroll
-                for (int n = 0; n < EPT; ++n) {
-                    const int meta = ent_meta[n];
-                    if (meta < 0) continue;
-                    const int k = meta >> 16, i = (meta >> 8) & 255, c = meta & 255;
-                    const int e = tid + n * NT;
-                    const double d = dinv[k];
-                    // branch-free: entries of row/column j are S*d (the stored value IS the column
-                    // entry or its conjugate), the pivot becomes -d, everything else gets the
-                    // rank-1 update  S - (u_i d) conj(u_c)
-                    const cd sv = S[e];
-                    const cd ui = col[k * DP + i], uc = col[k * DP + c];
-                    const bool on_i = (i == j), on_c = (c == j);
-                    cd v = sv;
-                    cfmsc(v, cscale(ui, d), uc);
-                    const cd vs = cscale(sv, d);
-                    v.x = (on_i | on_c) ? vs.x : v.x;
-                    v.y = (on_i | on_c) ? vs.y : v.y;
-                    v.x = (on_i & on_c) ? -d : v.x;
-                    v.y = (on_i & on_c) ? 0.0 : v.y;
-                    if (on_i & on_c) pivbuf[k * DP + j] = piv[k];
-                    S[e] = v;
-                    // forward the column of the next pivot
-                    if (c == j + 1) {
-                        coln[k * DP + i] = v;
-                        if (i == j + 1) { pivn[k] = v.x; dinvn[k] = (v.x > 0.0 && isfinite(v.x)) ? 1.0 / v.x : 0.0; }
-                    }
-                    else if (i == j + 1) coln[k * DP + c] = cconj(v);
-                }
-                __syncthreads();
-            }
             // logdet, trace of the inverse, validity of the fast path
             for (int k = warp; k < K; k += C::NW) {
                 double ld = 0.0, trb = 0.0;
@@ -539,7 +586,7 @@ __global__ void __launch_bounds__(NT, MINB) cacgmm_em_kernel(const CacgmmParams 
                     const double pv = pivbuf[k * DP + lane];
                     bad = !(pv > 0.0) || !isfinite(pv);
                     ld = bad ? 0.0 : log(pv);
-                    trb = -S[k * C::NP + tri(lane, lane)].x;
+                    trb = diagb[k * DP + lane];
                 }
                 ld = warp_sum(ld); trb = warp_sum(trb);
                 bad = __any_sync(0xffffffffu, bad);
@@ -549,14 +596,14 @@ __global__ void __launch_bounds__(NT, MINB) cacgmm_em_kernel(const CacgmmParams 
                 else if (lane == 0) logdet_s[k] = ld;
             }
             __syncthreads();
+            if (sw_on && !flags_s[sw_k]) {
 #pragma unroll
-            for (int n = 0; n < EPT; ++n) {
-                const int meta = ent_meta[n];
-                if (meta < 0) continue;
-                const int k = meta >> 16, i = (meta >> 8) & 255, c = meta & 255;
-                if (flags_s[k]) continue;
-                const cd v = S[tid + n * NT];
-                Bsm[tri(i, c) * K + k] = (i == c) ? cmake(-v.x, 0.0) : cmake(-2.0 * v.x, -2.0 * v.y);
+                for (int n = 0; n < CH; ++n) {
+                    if (n >= sw_n) continue;
+                    const int c = sw_c0 + n;
+                    const cd v = sv[n];
+                    Bsm[tri(sw_i, c) * K + sw_k] = (sw_i == c) ? cmake(-v.x, 0.0) : cmake(-2.0 * v.x, -2.0 * v.y);
+                }
             }
             __syncthreads();
         }
@@ -696,11 +743,13 @@ static int launch_cacgmm_dk(const CacgmmParams& p, cudaStream_t st) {
 template <int DP>
 int launch_cacgmm_d(const CacgmmParams& p, int K, cudaStream_t st) {
     switch (K) {
+#ifndef GSS_K_ONLY_5          // developer builds: -DGSS_K_ONLY_5 instantiates K = 5 only
         case 2: return launch_cacgmm_dk<DP, 2>(p, st);
         case 3: return launch_cacgmm_dk<DP, 3>(p, st);
         case 4: return launch_cacgmm_dk<DP, 4>(p, st);
-        case 5: return launch_cacgmm_dk<DP, 5>(p, st);
         case 6: return launch_cacgmm_dk<DP, 6>(p, st);
+#endif
+        case 5: return launch_cacgmm_dk<DP, 5>(p, st);
         default: return fail(GSS_ERR_UNSUPPORTED, "gss_cacgmm_c64: K=%d not built (built: 2..6)", K);
     }
 }
@@ -724,14 +773,21 @@ GSS_DP_PART2
 #endif
 
 #if GSS_EM_PART == 0
-int cacgmm_dispatch(const CacgmmParams& p, int K, cudaStream_t st) {
-    const int DP = (p.D + 1) & ~1;
-    switch (DP) {
-#define GSS_CASE(dp) case dp: return launch_cacgmm_d<dp>(p, K, st);
-        GSS_DP_LIST
+// the fused kernel is built for these padded channel counts and K = 2..6; any D runs on the next
+// built size (padded channels are zero rows; the matrix phase uses the true D)
+bool cacgmm_fast_path(int D, int K) {
+    if (K < 2 || K > 6) return false;
+#define GSS_CASE(dp) if (D <= dp) return true;
+    GSS_DP_LIST
 #undef GSS_CASE
-        default: return fail(GSS_ERR_UNSUPPORTED, "gss_cacgmm_c64: D=%d not built", p.D);
-    }
+    return false;
+}
+
+int cacgmm_dispatch(const CacgmmParams& p, int K, cudaStream_t st) {
+#define GSS_CASE(dp) if (p.D <= dp) return launch_cacgmm_d<dp>(p, K, st);
+    GSS_DP_LIST
+#undef GSS_CASE
+    return fail(GSS_ERR_UNSUPPORTED, "gss_cacgmm_c64: D=%d not built", p.D);
 }
 #endif
 
@@ -755,8 +811,11 @@ extern "C" int gss_cacgmm_c64(const gss_c64* Y, const uint8_t* activity, float* 
     GSS_REQUIRE(iterations_post >= 1, GSS_ERR_UNSUPPORTED,
                 "iterations_post=%d: the reference raises TypeError for 0 (core.py:198-202)", iterations_post);
     GSS_REQUIRE(T_act >= T, GSS_ERR_ARG, "activity has %d frames, observation %d (cacgmm.py:216-218)", T_act, T);
-    GSS_REQUIRE(D <= 32, GSS_ERR_UNSUPPORTED, "gss_cacgmm_c64: D=%d > 32 not built", D);
     if (B == 0 || F == 0) return GSS_OK;
+    if (!cacgmm_fast_path(D, K))          // K > 6 or D > 24: runtime-shape kernel (cacgmm_generic.cu), same results
+        return cacgmm_generic_launch((const float2*)Y, activity, T_per_utt, posterior, weight_out, logdet_out,
+                                     covariance_out, info, B, F, D, T, K, T_act, iterations, iterations_post,
+                                     affiliation_eps, eigenvalue_floor, ws, ws_bytes, (cudaStream_t)stream);
     CacgmmParams p;
     p.Y = (const float2*)Y; p.activity = activity; p.posterior = posterior; p.Tper = T_per_utt;
     p.weight_out = weight_out; p.logdet_out = logdet_out; p.cov_out = covariance_out;

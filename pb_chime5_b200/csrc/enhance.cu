@@ -9,11 +9,23 @@ namespace gss {
 size_t beamform_ws_bytes(int B, int F, int D);
 size_t wpe_ws_bytes(int Bc, int F, int D, int T, int L);
 
-struct EnhanceWs { float2* Yf; float2* Yw; float* post; float2* Xf; void* sub; size_t sub_bytes; size_t bytes; };
+struct EnhanceWs { float2* Yf; float2* Yw; float* post; float2* Xf; int* stage_info; void* sub; size_t sub_bytes; size_t bytes; };
 
-static size_t cacgmm_ws_bytes(int B, int F, int D, int K) {
-    return align_up(((size_t)B * F * K + 2) * sizeof(int)) + align_up((size_t)B * F * K * D * (D + 2) * 16);
+// One status word per stage and utterance inside the call; the caller's word gets the most severe
+// one (a failure code of any stage wins over the WPE's "singular, minimum-norm solution used").
+__global__ void enhance_merge_info_kernel(int* __restrict__ out, const int* __restrict__ st, int B) {
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= B) return;
+    int best = 0, rank = 0;
+    for (int s = 0; s < 3; ++s) {
+        const int v = st[s * B + b], code = v & 0xFF;
+        const int r = code == 0 ? 0 : (code == GSS_INFO_SINGULAR ? 1 : 2);
+        if (r > rank) { rank = r; best = v; }
+    }
+    if (best) atomicMax(&out[b], best);
 }
+
+size_t cacgmm_ws_bytes(int B, int F, int D, int K);
 
 static EnhanceWs enhance_layout(void* ws, int B, int F, int D, int T, int K, int L, bool wpe) {
     Arena a(ws, ~size_t(0));
@@ -22,6 +34,7 @@ static EnhanceWs enhance_layout(void* ws, int B, int F, int D, int T, int K, int
     w.Yw = wpe ? a.take<float2>((size_t)B * F * D * T) : nullptr;
     w.post = a.take<float>((size_t)B * F * K * T);
     w.Xf = a.take<float2>((size_t)B * F * T);
+    w.stage_info = a.take<int>((size_t)3 * B);
     size_t sub = std::max(cacgmm_ws_bytes(B, F, D, K), beamform_ws_bytes(B, F, D));
     if (wpe) sub = std::max(sub, wpe_ws_bytes(B < 4 ? B : 4, F, D, T, L));
     w.sub = a.take<char>(sub);
@@ -50,22 +63,28 @@ extern "C" int gss_enhance_c64(const gss_c64* Obs, const uint8_t* activity, cons
     const bool wpe = wpe_taps > 0 && wpe_iterations > 0;
     EnhanceWs w = enhance_layout(ws, B, F, D, T, K, wpe ? wpe_taps : 0, wpe);
     GSS_REQUIRE(ws && ws_bytes >= w.bytes, GSS_ERR_WORKSPACE, "gss_enhance_c64: workspace %zu < %zu", ws_bytes, w.bytes);
+    int* si = info ? w.stage_info : nullptr;           // [3][B]: WPE, EM, beamformer
+    if (si) GSS_CUDA(cudaMemsetAsync(si, 0, sizeof(int) * 3 * (size_t)B, (cudaStream_t)stream));
     int rc = gss_pack_dtf_to_fdt_c64(Obs, (gss_c64*)w.Yf, B, D, T, F, stream);
     if (rc) return rc;
     const gss_c64* Y = (const gss_c64*)w.Yf;
     if (wpe) {
         rc = gss_wpe_c64(Y, (gss_c64*)w.Yw, wpe_taps, wpe_delay, wpe_iterations, wpe_psd_context, B, F, D, T,
-                         T_per_utt, info, w.sub, w.sub_bytes, stream);
+                         T_per_utt, si, w.sub, w.sub_bytes, stream);
         if (rc) return rc;
         Y = (const gss_c64*)w.Yw;
     }
     rc = gss_cacgmm_c64(Y, activity, w.post, em_iterations, em_iterations_post, 1e-10, 1e-10, B, F, D, T, K, T_act,
-                        T_per_utt, nullptr, nullptr, nullptr, info, w.sub, w.sub_bytes, stream);
+                        T_per_utt, nullptr, nullptr, nullptr, si ? si + B : nullptr, w.sub, w.sub_bytes, stream);
     if (rc) return rc;
     rc = gss_beamform_from_posterior_c64(Y, w.post, target_index, start_ctx, end_ctx, (gss_c64*)w.Xf, bf_type, bf_arg,
-                                         postfilter, B, F, D, T, K, T_per_utt, nullptr, nullptr, info,
+                                         postfilter, B, F, D, T, K, T_per_utt, nullptr, nullptr, si ? si + 2 * B : nullptr,
                                          w.sub, w.sub_bytes, stream);
     if (rc) return rc;
+    if (si) {
+        enhance_merge_info_kernel<<<(B + 127) / 128, 128, 0, (cudaStream_t)stream>>>(info, si, B);
+        GSS_LAUNCH_CHECK("enhance_merge_info_kernel");
+    }
     rc = gss_unpack_ft_to_tf_c64((const gss_c64*)w.Xf, X_hat, B, T, F, stream);
     if (rc) return rc;
     if (posterior) rc = gss_unpack_fkt_to_ktf_f32(w.post, posterior, B, K, T, F, stream);

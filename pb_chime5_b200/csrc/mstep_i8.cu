@@ -1,4 +1,4 @@
-// EXPERIMENTAL (not on the product path yet; reached only through gss_debug_mstep_i8):
+// EXPERIMENTAL, libgss_dev.so only (not in the product library; reached only through gss_debug_mstep_i8):
 // the CACGMM M-step covariance  Phi_k = sum_t w_kt y_t y_t^H  (ComplexAngularCentralGaussianTrainer._fit,
 // pb_bss/distribution/complex_angular_central_gaussian.py:293-300) on the INT8 tensor cores with the
 // exact digit-split arithmetic of wpe_gram_i8.cu.  It is the building block of the tensor-core EM
@@ -16,6 +16,7 @@
 // rows x N = 2 D columns x 5 accumulators = 480 TMEM columns.  Row scales: one power of two per
 // class (max_t w_kt max_d |y_td|) and one per channel.
 #include "tc_i8.cuh"
+#include "../../include/gss_dev.h"
 #include <algorithm>
 
 namespace gss {

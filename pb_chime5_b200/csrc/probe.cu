@@ -1,0 +1,58 @@
+// Developer API (libgss_dev.so only): FP64 peak probe -- the denominator of the EM kernel's FP64
+// roofline view, measured on the box the bench runs on (bench.py `roofline.fp64`).
+#include "common.cuh"
+#include "../../include/gss_dev.h"
+
+namespace gss {
+
+__global__ void __launch_bounds__(512) fp64_dfma_probe_kernel(double* out, int iters) {
+    double a[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) a[i] = threadIdx.x * 1e-3 + i;
+    const double b = 1.0000001, c = 1e-9;
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) a[i] = fma(a[i], b, c);
+    }
+    double s = 0;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) s += a[i];
+    out[(size_t)blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+
+__global__ void __launch_bounds__(512) fp64_dmma_probe_kernel(double* out, int iters) {
+    double c[8][2];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { c[i][0] = 0; c[i][1] = 0; }
+    const double a = threadIdx.x * 1e-3, b = 1.0 + threadIdx.x * 1e-6;
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+            asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                         : "+d"(c[i][0]), "+d"(c[i][1]) : "d"(a), "d"(b));
+    }
+    double s = 0;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) s += c[i][0] + c[i][1];
+    out[(size_t)blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+
+}  // namespace gss
+
+extern "C" size_t gss_debug_fp64_peak_scratch_bytes(void) {
+    return (size_t)gss::num_sms() * 2 * 512 * sizeof(double);
+}
+
+extern "C" int gss_debug_fp64_peak(int mode, int iters, void* scratch, double* flops_out, void* stream) {
+    using namespace gss;
+    GSS_REQUIRE(scratch && iters > 0 && (mode == 0 || mode == 1), GSS_ERR_ARG, "gss_debug_fp64_peak: bad arguments");
+    const int grid = num_sms() * 2, block = 512;              // 32 warps per SM
+    cudaStream_t st = (cudaStream_t)stream;
+    if (mode == 0) fp64_dfma_probe_kernel<<<grid, block, 0, st>>>((double*)scratch, iters);
+    else fp64_dmma_probe_kernel<<<grid, block, 0, st>>>((double*)scratch, iters);
+    GSS_LAUNCH_CHECK("fp64_probe_kernel");
+    if (flops_out)
+        *flops_out = mode == 0 ? 2.0 * 8 * iters * (double)grid * block
+                               : 2.0 * 8 * 256 * iters * (double)grid * (block / 32);
+    return GSS_OK;
+}

@@ -193,17 +193,21 @@ __device__ __forceinline__ void wpe_corr_body(const size_t bf, const float2* __r
 // Kernel wrappers of the factorisation chain: one CTA (row) per bin in the first pass; in the
 // float64 re-do pass of the INT8 path (redo_list != null) a small grid walks the compacted list of
 // flagged bins, so an empty list costs a handful of CTAs instead of one per bin.
+// `skip` (direct mode only): per-bin flags, a bin whose flag is set belongs to the float64 list and
+// is left alone by the pass over the INT8 results.
 #define GSS_WPE_REDO_LOOP(CALL)                                                                           \
     {   const int n_bins = redo_list ? *redo_count : (int)gridDim.x;                                       \
         for (int li = blockIdx.x; li < n_bins; li += gridDim.x) {                                          \
             const size_t bf = redo_list ? (size_t)redo_list[li] : (size_t)li;                              \
+            if (!redo_list && skip && skip[bf]) continue;                                                  \
             CALL;                                                                                          \
             __syncthreads();                                                                               \
         } }
 
 __global__ void __launch_bounds__(CT_NT) wpe_corr_kernel(const float2* __restrict__ Y, const double* __restrict__ inv,
                                                          cd* __restrict__ Raug, WpeDims m,
-                                                         const int* __restrict__ redo_list, const int* __restrict__ redo_count) {
+                                                         const int* __restrict__ redo_list, const int* __restrict__ redo_count,
+                                                         const int* __restrict__ skip) {
     GSS_WPE_REDO_LOOP(wpe_corr_body(bf, Y, inv, Raug, m))
 }
 
@@ -288,7 +292,8 @@ __device__ __forceinline__ void wpe_diag_body(const size_t bf, cd* __restrict__ 
 
 __global__ void __launch_bounds__(32) wpe_diag_kernel(cd* __restrict__ Raug, cd* __restrict__ Minv,
                                                       int* __restrict__ info, WpeDims m, int j0, int jb,
-                                                      const int* __restrict__ redo_list, const int* __restrict__ redo_count) {
+                                                      const int* __restrict__ redo_list, const int* __restrict__ redo_count,
+                                                         const int* __restrict__ skip) {
     GSS_WPE_REDO_LOOP(wpe_diag_body(bf, Raug, Minv, info, m, j0, jb))
 }
 
@@ -329,7 +334,8 @@ __device__ __forceinline__ void wpe_panel_rows_body(const size_t bf, cd* __restr
 
 __global__ void __launch_bounds__(PR_NT) wpe_panel_rows_kernel(cd* __restrict__ Raug, const cd* __restrict__ Minv,
                                                                WpeDims m, int j0, int jb,
-                                                               const int* __restrict__ redo_list, const int* __restrict__ redo_count) {
+                                                               const int* __restrict__ redo_list, const int* __restrict__ redo_count,
+                                                         const int* __restrict__ skip) {
     GSS_WPE_REDO_LOOP(wpe_panel_rows_body(bf, Raug, Minv, m, j0, jb))
 }
 
@@ -411,7 +417,8 @@ __device__ __forceinline__ void wpe_trail_body(const size_t bf, cd* __restrict__
 }
 
 __global__ void __launch_bounds__(CT_NT, 4) wpe_trail_kernel(cd* __restrict__ Raug, WpeDims m, int j0,
-                                                          const int* __restrict__ redo_list, const int* __restrict__ redo_count) {
+                                                          const int* __restrict__ redo_list, const int* __restrict__ redo_count,
+                                                         const int* __restrict__ skip) {
     GSS_WPE_REDO_LOOP(wpe_trail_body(bf, Raug, m, j0))
 }
 
@@ -419,12 +426,13 @@ __global__ void __launch_bounds__(CT_NT, 4) wpe_trail_kernel(cd* __restrict__ Ra
 // 1 - (squared multiple correlation of row j with the rows before it), a scale-invariant
 // measure of how much of the pivot survived the elimination.  A bin whose smallest ratio is
 // below `tau` (or not finite: dead channels, failures) is put on the re-do list and re-done in float64.
-__device__ int g_wpe_redo_total = 0;
-
+// Flags are carried through the iterations of one call: a bin flagged once stays on the float64 list
+// (its INT8 Gram build and first factorisation are skipped from then on).
 __global__ void __launch_bounds__(32) wpe_flag_kernel(const cd* __restrict__ Raug, const double* __restrict__ rdiag,
-                                                      int* __restrict__ redo_list, int* __restrict__ redo_count,
-                                                      WpeDims m, double tau) {
+                                                      int* __restrict__ flag, int* __restrict__ redo_list,
+                                                      int* __restrict__ redo_count, WpeDims m, double tau) {
     const size_t bf = blockIdx.x;
+    if (flag[bf]) return;                                   // already on the float64 list
     const int n = m.LD, lane = threadIdx.x;
     const cd* A = Raug + bf * (size_t)(m.LD + m.D) * n;
     bool bad = false;
@@ -434,8 +442,18 @@ __global__ void __launch_bounds__(32) wpe_flag_kernel(const cd* __restrict__ Rau
     }
     bad = __any_sync(0xffffffffu, bad);
     if (lane == 0 && bad) {                                 // compacted list (order irrelevant: bins are independent)
+        flag[bf] = 1;
         redo_list[atomicAdd(redo_count, 1)] = (int)bf;
-        atomicAdd(&g_wpe_redo_total, 1);
+    }
+}
+
+// stats[0] += bins of the chunk, stats[1] += bins that ended on the float64 list,
+// stats[2] += float64 Gram builds done for listed bins (all iterations)
+__global__ void wpe_stats_kernel(int* __restrict__ stats, const int* __restrict__ redo_count, int BF, int mode) {
+    if (threadIdx.x == 0 && blockIdx.x == 0) {
+        if (mode == 0) atomicAdd(&stats[0], BF);
+        else if (mode == 1) atomicAdd(&stats[2], *redo_count);
+        else atomicAdd(&stats[1], *redo_count);
     }
 }
 
@@ -607,7 +625,7 @@ __global__ void __launch_bounds__(AP_NT) wpe_apply_kernel(const float2* __restri
         }
 }
 
-struct WpeWs { double* power; double* inv; cd* Raug; cd* G; cd* Minv; double* rdiag; int* redo_list; int* redo_count; WpeI8Ws i8; bool has_i8; size_t bytes; };
+struct WpeWs { double* power; double* inv; cd* Raug; cd* G; cd* Minv; double* rdiag; int* redo_list; int* redo_count; int* flag; WpeI8Ws i8; bool has_i8; size_t bytes; };
 
 static WpeWs wpe_ws_layout(void* ws, int Bc, int F, int D, int T, int L) {
     const int LD = L * D;
@@ -619,11 +637,12 @@ static WpeWs wpe_ws_layout(void* ws, int Bc, int F, int D, int T, int L) {
     w.G = a.take<cd>((size_t)Bc * F * LD * D);
     w.Minv = a.take<cd>((size_t)Bc * F * ((LD + WS_NB - 1) / WS_NB) * (WS_NB * (WS_NB + 1) / 2));
     w.has_i8 = wpe_i8_applicable(D, T, L);
-    w.rdiag = nullptr; w.redo_list = nullptr; w.redo_count = nullptr;
+    w.rdiag = nullptr; w.redo_list = nullptr; w.redo_count = nullptr; w.flag = nullptr;
     if (w.has_i8) {
         w.rdiag = a.take<double>((size_t)Bc * F * LD);
         w.redo_list = a.take<int>((size_t)Bc * F);
-        w.redo_count = a.take<int>(1);
+        w.flag = a.take<int>((size_t)Bc * F + 1);           // [BF] flags, then the list length
+        w.redo_count = w.flag + (size_t)Bc * F;
         const size_t used = wpe_i8_ws_layout(ws ? (char*)ws + a.off : nullptr, F, D, T, L, &w.i8);
         a.off += align_up(used);
     }
@@ -633,43 +652,25 @@ static WpeWs wpe_ws_layout(void* ws, int Bc, int F, int D, int T, int L) {
 
 size_t wpe_ws_bytes(int Bc, int F, int D, int T, int L) { return wpe_ws_layout(nullptr, Bc, F, D, T, L).bytes; }
 
-// Gram path selection: GSS_WPE_GRAM=f64 forces the FP64 tensor-core (DMMA) build, =i8 the INT8
-// build without the float64 re-do; default: INT8 where built, flagged bins re-done in float64.
-static int g_gram_mode_override = -1;
-static double g_tau_override = -1.0;
-static int wpe_gram_mode() {
-    if (g_gram_mode_override >= 0) return g_gram_mode_override;
-    static int mode = -1;
-    if (mode < 0) {
-        const char* e = getenv("GSS_WPE_GRAM");
-        mode = (e && e[0] == 'f') ? 0 : (e && e[0] == 'i') ? 1 : 2;
-    }
-    return mode;
-}
-static double wpe_i8_tau() {
-    if (g_tau_override >= 0.0) return g_tau_override;
-    static double tau = -1.0;
-    if (tau < 0.0) { const char* e = getenv("GSS_WPE_I8_TAU"); tau = e ? atof(e) : 1e-3; if (!(tau >= 0.0)) tau = 1e-3; }
-    return tau;
-}
-
-// blocked Cholesky of Raug with the P^H rows riding along (all bins, or the flagged ones)
-// redo == false: all BF bins; redo == true: the bins of w.redo_list (a grid of at most one CTA row per SM walks it)
-static int wpe_factor(const WpeWs& w, const WpeDims& m, int BF, int* infoc, bool redo, cudaStream_t st) {
+// blocked Cholesky of Raug with the P^H rows riding along.
+// redo == false: one CTA row per bin, bins whose `skip` flag is set are left alone;
+// redo == true : the bins of w.redo_list (a small grid walks the list, so an empty list costs a few CTAs)
+static int wpe_factor(const WpeWs& w, const WpeDims& m, int BF, int* infoc, bool redo, const int* skip, cudaStream_t st) {
     const int LD = m.LD, D = m.D;
     const int gx = redo ? std::min(BF, num_sms()) : BF;
+    const int gdiag = redo ? std::min(BF, 8 * num_sms()) : BF;        // one warp per bin: more rows in flight
     const int* rl = redo ? w.redo_list : nullptr;
     const int* rc = redo ? w.redo_count : nullptr;
     for (int j0 = 0, jb = 0; j0 < LD; j0 += WS_NB, ++jb) {
-        wpe_diag_kernel<<<gx, 32, 0, st>>>(w.Raug, w.Minv, infoc, m, j0, jb, rl, rc);
+        wpe_diag_kernel<<<gdiag, 32, 0, st>>>(w.Raug, w.Minv, infoc, m, j0, jb, rl, rc, skip);
         GSS_LAUNCH_CHECK("wpe_diag_kernel");
         const int j1 = std::min(j0 + WS_NB, LD);
         dim3 pg(gx, (LD + D - j1 + PR_NT - 1) / PR_NT);
-        wpe_panel_rows_kernel<<<pg, PR_NT, 0, st>>>(w.Raug, w.Minv, m, j0, jb, rl, rc);
+        wpe_panel_rows_kernel<<<pg, PR_NT, 0, st>>>(w.Raug, w.Minv, m, j0, jb, rl, rc, skip);
         GSS_LAUNCH_CHECK("wpe_panel_rows_kernel");
         if (j1 < LD) {
             dim3 tg(gx, (LD + D - j1 + CT_BM - 1) / CT_BM, (LD - j1 + CT_BM - 1) / CT_BM);
-            wpe_trail_kernel<<<tg, CT_NT, 0, st>>>(w.Raug, m, j0, rl, rc);
+            wpe_trail_kernel<<<tg, CT_NT, 0, st>>>(w.Raug, m, j0, rl, rc, skip);
             GSS_LAUNCH_CHECK("wpe_trail_kernel");
         }
     }
@@ -678,7 +679,7 @@ static int wpe_factor(const WpeWs& w, const WpeDims& m, int BF, int* infoc, bool
 
 static int wpe_corr_f64(const float2* Yc, const WpeWs& w, const WpeDims& m, int BF, bool redo, cudaStream_t st) {
     dim3 grid(redo ? std::min(BF, num_sms()) : BF, (m.LD + m.D + CT_BM - 1) / CT_BM, (m.LD + CT_BM - 1) / CT_BM);
-    wpe_corr_kernel<<<grid, CT_NT, 0, st>>>(Yc, w.inv, w.Raug, m, redo ? w.redo_list : nullptr, redo ? w.redo_count : nullptr);
+    wpe_corr_kernel<<<grid, CT_NT, 0, st>>>(Yc, w.inv, w.Raug, m, redo ? w.redo_list : nullptr, redo ? w.redo_count : nullptr, nullptr);
     GSS_LAUNCH_CHECK("wpe_corr_kernel");
     return GSS_OK;
 }
@@ -706,17 +707,22 @@ static int launch_apply(const float2* Y, const cd* G, float2* X, double* power, 
 
 }  // namespace gss
 
-extern "C" int gss_wpe_c64(const gss_c64* Y, gss_c64* X, int taps, int delay, int iterations, int psd_context,
-                           int B, int F, int D, int T, const int* T_per_utt, int* info, void* ws, size_t ws_bytes, void* stream) {
+extern "C" int gss_wpe_c64_ex(const gss_c64* Y, gss_c64* X, int taps, int delay, int iterations, int psd_context,
+                              int B, int F, int D, int T, const int* T_per_utt,
+                              int gram_mode, double i8_tau, int* stats,
+                              int* info, void* ws, size_t ws_bytes, void* stream) {
     using namespace gss;
     GSS_REQUIRE(Y && X && Y != X, GSS_ERR_ARG, "gss_wpe_c64: null or aliased pointers");
     GSS_REQUIRE(B >= 0 && F >= 0 && D > 0 && T > 0, GSS_ERR_ARG, "gss_wpe_c64: bad dims");
     GSS_REQUIRE(taps > 0 && delay >= 0 && iterations >= 0 && psd_context >= 0, GSS_ERR_ARG,
                 "gss_wpe_c64: taps=%d delay=%d iterations=%d psd_context=%d", taps, delay, iterations, psd_context);
+    GSS_REQUIRE(gram_mode >= GSS_WPE_GRAM_AUTO && gram_mode <= GSS_WPE_GRAM_I8_REDO, GSS_ERR_ARG,
+                "gss_wpe_c64_ex: gram_mode=%d", gram_mode);
     GSS_REQUIRE(D <= 32, GSS_ERR_UNSUPPORTED, "gss_wpe_c64: D=%d > 32 not built", D);
     const int LD = taps * D;
     GSS_REQUIRE(((size_t)LD * (D | 1) + 24 * D + 300) * sizeof(cd) <= 220 * 1024, GSS_ERR_UNSUPPORTED,
                 "gss_wpe_c64: taps*D*D=%d too large for the back-substitution tile", LD * D);
+    const double tau = i8_tau >= 0.0 ? i8_tau : 1e-3;
     cudaStream_t st = (cudaStream_t)stream;
     if (B == 0 || F == 0) return GSS_OK;
     if (iterations == 0) {
@@ -735,28 +741,34 @@ extern "C" int gss_wpe_c64(const gss_c64* Y, gss_c64* X, int taps, int delay, in
         float2* Xc = (float2*)X + (size_t)b0 * F * D * T;
         int* infoc = info ? info + b0 : nullptr;
         WpeWs w = wpe_ws_layout(ws, bn, F, D, T, taps);
-        const int gram_mode = w.has_i8 ? wpe_gram_mode() : 0;
+        // AUTO: INT8 tensor-core Gram where it is built, ill-conditioned bins re-done in float64
+        const int mode = !w.has_i8 ? GSS_WPE_GRAM_F64 : (gram_mode == GSS_WPE_GRAM_AUTO ? GSS_WPE_GRAM_I8_REDO : gram_mode);
+        if (mode == GSS_WPE_GRAM_I8_REDO)
+            GSS_CUDA(cudaMemsetAsync(w.flag, 0, ((size_t)BF + 1) * sizeof(int), st));
+        if (stats) { wpe_stats_kernel<<<1, 32, 0, st>>>(stats, nullptr, BF, 0); GSS_LAUNCH_CHECK("wpe_stats_kernel"); }
         wpe_power_kernel<<<BF, 256, 0, st>>>(Yc, w.power, m);
         GSS_LAUNCH_CHECK("wpe_power_kernel");
         for (int it = 0; it < iterations; ++it) {
             wpe_invpower_kernel<<<BF, 256, 0, st>>>(w.power, w.inv, m, psd_context);
             GSS_LAUNCH_CHECK("wpe_invpower_kernel");
             int rcf;
-            if (gram_mode == 0) {
+            if (mode == GSS_WPE_GRAM_F64) {
                 if ((rcf = wpe_corr_f64(Yc, w, m, BF, false, st))) return rcf;
-                if ((rcf = wpe_factor(w, m, BF, infoc, false, st))) return rcf;
+                if ((rcf = wpe_factor(w, m, BF, infoc, false, nullptr, st))) return rcf;
+            } else if (mode == GSS_WPE_GRAM_I8) {
+                if ((rcf = wpe_gram_i8_run(Yc, w.inv, w.Raug, w.rdiag, m, BF, w.i8, nullptr, st))) return rcf;
+                if ((rcf = wpe_factor(w, m, BF, infoc, false, nullptr, st))) return rcf;
             } else {
-                // INT8 tensor-core Gram matrix; ill-conditioned bins are flagged after the
-                // factorisation and re-done (Gram + factorisation) in float64
-                if ((rcf = wpe_gram_i8_run(Yc, w.inv, w.Raug, w.rdiag, m, BF, w.i8, 0, st))) return rcf;
-                if ((rcf = wpe_factor(w, m, BF, gram_mode == 2 ? nullptr : infoc, false, st))) return rcf;
-                if (gram_mode == 2) {
-                    GSS_CUDA(cudaMemsetAsync(w.redo_count, 0, sizeof(int), st));
-                    wpe_flag_kernel<<<BF, 32, 0, st>>>(w.Raug, w.rdiag, w.redo_list, w.redo_count, m, wpe_i8_tau());
-                    GSS_LAUNCH_CHECK("wpe_flag_kernel");
-                    if ((rcf = wpe_corr_f64(Yc, w, m, BF, true, st))) return rcf;
-                    if ((rcf = wpe_factor(w, m, BF, infoc, true, st))) return rcf;
-                }
+                // INT8 tensor-core Gram matrix for the bins that are not on the float64 list yet;
+                // after the factorisation the a-posteriori check moves ill-conditioned bins to the
+                // list, and the list (old and new members) is done in float64 (Gram + factorisation)
+                if ((rcf = wpe_gram_i8_run(Yc, w.inv, w.Raug, w.rdiag, m, BF, w.i8, w.flag, st))) return rcf;
+                if ((rcf = wpe_factor(w, m, BF, nullptr, false, w.flag, st))) return rcf;
+                wpe_flag_kernel<<<BF, 32, 0, st>>>(w.Raug, w.rdiag, w.flag, w.redo_list, w.redo_count, m, tau);
+                GSS_LAUNCH_CHECK("wpe_flag_kernel");
+                if ((rcf = wpe_corr_f64(Yc, w, m, BF, true, st))) return rcf;
+                if ((rcf = wpe_factor(w, m, BF, infoc, true, nullptr, st))) return rcf;
+                if (stats) { wpe_stats_kernel<<<1, 32, 0, st>>>(stats, w.redo_count, BF, 1); GSS_LAUNCH_CHECK("wpe_stats_kernel"); }
             }
             {
                 const size_t bs_smem = ((size_t)LD * (D | 1) + WS_NB * D + WS_NB * (WS_NB + 1) / 2) * sizeof(cd);
@@ -774,24 +786,20 @@ extern "C" int gss_wpe_c64(const gss_c64* Y, gss_c64* X, int taps, int delay, in
             else rc = launch_apply<4>(Yc, w.G, Xc, w.power, m, BF, st);
             if (rc) return rc;
         }
+        if (stats && mode == GSS_WPE_GRAM_I8_REDO) { wpe_stats_kernel<<<1, 32, 0, st>>>(stats, w.redo_count, BF, 2); GSS_LAUNCH_CHECK("wpe_stats_kernel"); }
     }
     return GSS_OK;
 }
 
-// ---- diagnostics (tests, tools/) ---------------------------------------------------------
-extern "C" int gss_debug_wpe_config(int gram_mode, double tau) {
-    gss::g_gram_mode_override = gram_mode;      // -1: environment / default, 0: f64, 1: i8 only, 2: i8 + f64 re-do
-    gss::g_tau_override = tau;                  // < 0: environment / default
-    return GSS_OK;
+extern "C" int gss_wpe_c64(const gss_c64* Y, gss_c64* X, int taps, int delay, int iterations, int psd_context,
+                           int B, int F, int D, int T, const int* T_per_utt, int* info, void* ws, size_t ws_bytes, void* stream) {
+    return gss_wpe_c64_ex(Y, X, taps, delay, iterations, psd_context, B, F, D, T, T_per_utt,
+                          GSS_WPE_GRAM_AUTO, -1.0, nullptr, info, ws, ws_bytes, stream);
 }
 
-extern "C" int gss_debug_wpe_redo_count(int reset) {
-    int v = 0;
-    if (cudaMemcpyFromSymbol(&v, gss::g_wpe_redo_total, sizeof(int)) != cudaSuccess) return -1;
-    if (reset) { const int z = 0; cudaMemcpyToSymbol(gss::g_wpe_redo_total, &z, sizeof(int)); }
-    return v;
-}
-
+// ---- developer API (libgss_dev.so only; include/gss_dev.h) ----------------------------------
+#ifdef GSS_DEV_API
+#include "../../include/gss_dev.h"
 extern "C" int gss_debug_wpe_gram(const gss_c64* Y, const double* inv, double* Raug, int mode, int variant,
                                   int B, int F, int D, int T, int taps, int delay, const int* T_per_utt,
                                   void* ws, size_t ws_bytes, void* stream) {
@@ -811,5 +819,6 @@ extern "C" int gss_debug_wpe_gram(const gss_c64* Y, const double* inv, double* R
     WpeI8Ws i8;
     const size_t need = wpe_i8_ws_layout(ws, F, D, T, taps, &i8);
     GSS_REQUIRE(ws && ws_bytes >= need, GSS_ERR_WORKSPACE, "gss_debug_wpe_gram: workspace %zu < %zu", ws_bytes, need);
-    return wpe_gram_i8_run((const float2*)Y, inv, reinterpret_cast<cd*>(Raug), nullptr, m, BF, i8, variant, st);
+    return wpe_gram_i8_run((const float2*)Y, inv, reinterpret_cast<cd*>(Raug), nullptr, m, BF, i8, nullptr, st);
 }
+#endif  // GSS_DEV_API

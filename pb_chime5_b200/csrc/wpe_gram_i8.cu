@@ -107,9 +107,10 @@ size_t wpe_i8_ws_bytes(int F, int D, int T, int L) {
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) wpe_i8_scale_kernel(const float2* __restrict__ Y, const double* __restrict__ inv,
                                                            double* __restrict__ mu, int* __restrict__ ex,
-                                                           WpeDims m, GiDims g, size_t bf0) {
+                                                           WpeDims m, GiDims g, size_t bf0, const int* __restrict__ skip) {
     extern __shared__ float mus[];                         // [T]
     const size_t bf = bf0 + blockIdx.x;
+    if (skip && skip[bf]) return;
     const int T = m.T, Tv = wpe_valid_frames(m, bf);
     const float2* __restrict__ Yg = Y + bf * (size_t)m.D * T;
     const double* __restrict__ iv = inv + bf * (size_t)T;
@@ -150,12 +151,13 @@ __global__ void __launch_bounds__(256) wpe_i8_scale_kernel(const float2* __restr
 
 __global__ void __launch_bounds__(256, 3) wpe_i8_slice_kernel(const float2* __restrict__ Y, const double* __restrict__ mu,
                                                            const int* __restrict__ ex, int8_t* __restrict__ slices,
-                                                           WpeDims m, GiDims g, size_t bf0) {
+                                                           WpeDims m, GiDims g, size_t bf0, const int* __restrict__ skip) {
     const int half = g.NRp >> 1;
     const int idx = blockIdx.x * 256 + threadIdx.x;
     if (idx >= half * g.KB) return;
     const int kb = idx / half, rc = idx - kb * half;
     const size_t bl = blockIdx.y, bf = bf0 + bl;
+    if (skip && skip[bf]) return;
     const int T = m.T, Tv = wpe_valid_frames(m, bf);
     int8_t* out = slices + bl * gi_slice_bytes_per_bin(g);
     unsigned lo_re[16], hi_re[16], lo_im[16], hi_im[16];
@@ -217,7 +219,8 @@ __global__ void __launch_bounds__(256, 3) wpe_i8_slice_kernel(const float2* __re
 
 __global__ void __launch_bounds__(GI_NT, 1) wpe_gram_i8_kernel(const int8_t* __restrict__ slices, const int* __restrict__ ex,
                                                                cd* __restrict__ Raug, double* __restrict__ rdiag,
-                                                               WpeDims m, GiDims g, GiPlan plan, size_t bf0, int nbins) {
+                                                               WpeDims m, GiDims g, GiPlan plan, size_t bf0, int nbins,
+                                                               const int* __restrict__ skip) {
     extern __shared__ __align__(128) unsigned char smem[];
     __shared__ __align__(8) unsigned long long bar_full[GI_STAGES], bar_empty[GI_STAGES], bar_acc, bar_drain;
     __shared__ uint32_t tmem_slot;
@@ -250,7 +253,7 @@ __global__ void __launch_bounds__(GI_NT, 1) wpe_gram_i8_kernel(const int8_t* __r
                 const int bl = w / plan.n_items;
                 const GiItem it = plan.items[w - bl * plan.n_items];
                 const int Tv = wpe_valid_frames(m, bf0 + bl);
-                const int nk = min(g.KB >> 1, (Tv + 31) >> 5);
+                const int nk = (skip && skip[bf0 + bl]) ? 0 : min(g.KB >> 1, (Tv + 31) >> 5);
                 const int8_t* __restrict__ sl = slices + (size_t)bl * bin_bytes;
                 const uint32_t stage_tx = (uint32_t)(GI_BLK_BYTES * (GI_BM / 8 + it.n / 8));
                 for (int ks = 0; ks < nk; ++ks, ++kg) {
@@ -280,7 +283,7 @@ __global__ void __launch_bounds__(GI_NT, 1) wpe_gram_i8_kernel(const int8_t* __r
                 const GiItem it = plan.items[w - bl * plan.n_items];
                 const int n = it.n;
                 const int Tv = wpe_valid_frames(m, bf0 + bl);
-                const int nk = min(g.KB >> 1, (Tv + 31) >> 5);
+                const int nk = (skip && skip[bf0 + bl]) ? 0 : min(g.KB >> 1, (Tv + 31) >> 5);
                 if (nk == 0) continue;
                 if (tile > 0) { mbar_wait(smem_u32(&bar_drain), (tile - 1) & 1); tc_fence_after(); }   // TMEM drained
                 const uint32_t idesc = umma_idesc_i8(n);
@@ -321,6 +324,7 @@ __global__ void __launch_bounds__(GI_NT, 1) wpe_gram_i8_kernel(const int8_t* __r
             const GiItem it = plan.items[w - bl * plan.n_items];
             const int n = it.n;
             const size_t bf = bf0 + bl;
+            if (skip && skip[bf]) continue;                // float64 list: nothing was produced, nothing to store
             const int Tv = wpe_valid_frames(m, bf);
             const int nk = min(g.KB >> 1, (Tv + 31) >> 5);
             const int a = it.r0 + 32 * q + lane;           // real row (digit-plane numbering)
@@ -420,7 +424,7 @@ static GiPlan gi_plan(int D, int LD) {
 }
 
 int wpe_gram_i8_run(const float2* Y, const double* inv, cd* Raug, double* rdiag, const WpeDims& m, int BF,
-                    const WpeI8Ws& ws, int /*variant*/, cudaStream_t st) {
+                    const WpeI8Ws& ws, const int* skip, cudaStream_t st) {
     const GiDims g = gi_dims(m.D, m.T, m.LD);
     const GiPlan plan = gi_plan(m.D, m.LD);
     GSS_CUDA(cudaFuncSetAttribute(wpe_gram_i8_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, GI_SMEM));   // per device
@@ -438,13 +442,13 @@ int wpe_gram_i8_run(const float2* Y, const double* inv, cd* Raug, double* rdiag,
     }
     for (int b0 = 0; b0 < BF; b0 += cbins) {
         const int nb = std::min(cbins, BF - b0);
-        wpe_i8_scale_kernel<<<dim3(nb, 8), 256, (size_t)m.T * sizeof(float), st>>>(Y, inv, ws.mu, ws.ex, m, g, (size_t)b0);
+        wpe_i8_scale_kernel<<<dim3(nb, 8), 256, (size_t)m.T * sizeof(float), st>>>(Y, inv, ws.mu, ws.ex, m, g, (size_t)b0, skip);
         GSS_LAUNCH_CHECK("wpe_i8_scale_kernel");
         dim3 sg((half * g.KB + 255) / 256, nb);
-        wpe_i8_slice_kernel<<<sg, 256, 0, st>>>(Y, ws.mu, ws.ex, ws.slices, m, g, (size_t)b0);
+        wpe_i8_slice_kernel<<<sg, 256, 0, st>>>(Y, ws.mu, ws.ex, ws.slices, m, g, (size_t)b0, skip);
         GSS_LAUNCH_CHECK("wpe_i8_slice_kernel");
         const int grid = std::min(plan.n_items * nb, num_sms());
-        wpe_gram_i8_kernel<<<grid, GI_NT, GI_SMEM, st>>>(ws.slices, ws.ex, Raug, rdiag, m, g, plan, (size_t)b0, nb);
+        wpe_gram_i8_kernel<<<grid, GI_NT, GI_SMEM, st>>>(ws.slices, ws.ex, Raug, rdiag, m, g, plan, (size_t)b0, nb, skip);
         GSS_LAUNCH_CHECK("wpe_gram_i8_kernel");
     }
     return GSS_OK;

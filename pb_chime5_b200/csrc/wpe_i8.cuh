@@ -26,8 +26,9 @@ size_t wpe_i8_ws_layout(void* p, int F, int D, int T, int L, WpeI8Ws* out);
 bool wpe_i8_applicable(int D, int T, int L);
 
 // Raug[bf] (lower trapezoid, same contract as wpe_corr_kernel) for bf in [0, BF);
-// rdiag[bf][i] = Re R_ii (may be null).  variant: reserved for debug switches (unused).
+// rdiag[bf][i] = Re R_ii (may be null).  skip (device, [BF], may be null): bins whose flag is set are
+// left untouched (they are on the float64 list of the a-posteriori check).
 int wpe_gram_i8_run(const float2* Y, const double* inv, cd* Raug, double* rdiag, const WpeDims& m, int BF,
-                    const WpeI8Ws& ws, int variant, cudaStream_t st);
+                    const WpeI8Ws& ws, const int* skip, cudaStream_t st);
 
 }  // namespace gss

@@ -41,22 +41,47 @@ def workspace(nbytes, device):
     return buf
 
 
+def new_info(B, device, stages=1):
+    """Zeroed device status words: one int32 per (stage, utterance).  Every stage of a pipeline gets its
+    own row, so a word of a later stage can never overwrite an earlier, more severe one."""
+    shape = (max(B, 1),) if stages == 1 else (stages, max(B, 1))
+    return torch.zeros(shape, dtype=torch.int32, device=device)
+
+
 def check_info(info, what):
-    """Translate the device-side status words into the reference's exceptions."""
+    """Translate device-side status words into the reference's exceptions.  `info`: a tensor (any
+    device) or a nested list of words (B,) / (stages, B); `what`: a name or one name per stage.
+    Reading a device tensor synchronises -- pipelines therefore pass their own `info` tensors to the
+    blocks below and call this once per batch, when the results are fetched."""
     if info is None:
         return
-    vals = info.tolist()
-    for b, v in enumerate(vals):
-        code, f = v & 0xFF, v >> 8
-        if code == _lib.INFO_NOT_POSDEF:
-            # zhegvd INFO > N (get_gev_vector.pyx:139-147)
-            raise ValueError(f'{what}: the noise PSD matrix is not positive definite '
-                             f'for utterance {b}, frequency {f}')
-        if code == _lib.INFO_NONFINITE:
-            raise AssertionError(f'{what}: non-finite SNR in the reference channel search '
-                                 f'(beamformer.py:542), utterance {b}')
-        if code == _lib.INFO_NO_CONVERGE:
-            raise RuntimeError(f'{what}: eigensolver did not converge, utterance {b}, frequency {f}')
+    rows = info.tolist() if isinstance(info, torch.Tensor) else info
+    if rows and not isinstance(rows[0], (list, tuple)):
+        rows = [rows]
+    names = [what] * len(rows) if isinstance(what, str) else list(what)
+    singular = []
+    for name, vals in zip(names, rows):
+        for b, v in enumerate(vals):
+            code, f = v & 0xFF, v >> 8
+            if code == _lib.INFO_NOT_POSDEF:
+                # zhegvd INFO > N (get_gev_vector.pyx:139-147)
+                raise ValueError(f'{name}: the noise PSD matrix is not positive definite '
+                                 f'for utterance {b}, frequency {f}')
+            if code == _lib.INFO_NONFINITE:
+                raise AssertionError(f'{name}: non-finite SNR in the reference channel search '
+                                     f'(beamformer.py:542), utterance {b}')
+            if code == _lib.INFO_NO_CONVERGE:
+                raise RuntimeError(f'{name}: eigensolver did not converge, utterance {b}, frequency {f}')
+            if code == _lib.INFO_SINGULAR:
+                singular.append((name, b, f))
+    if singular:
+        # nara_wpe falls back to a least-squares solve without telling anybody; the device returns the
+        # same minimum-norm solution (dead channels are deflated) -- say so once per batch
+        import warnings
+        name, b, f = singular[0]
+        warnings.warn(f'{name}: singular normal equations (dead channel?) in {len(singular)} utterance(s), '
+                      f'first: utterance {b}, frequency {f}; the minimum-norm solution was used',
+                      RuntimeWarning, stacklevel=2)
 
 
 # ---- layout glue ------------------------------------------------------------
@@ -134,9 +159,10 @@ def weighted_cov(Y, w, normalize=True, frames=None):
 
 
 def cacgmm(Y, activity, iterations, iterations_post=1, affiliation_eps=1e-10,
-           eigenvalue_floor=1e-10, return_model=False, frames=None):
+           eigenvalue_floor=1e-10, return_model=False, frames=None, info=None):
     """Guided CACGMM EM.  Y (B,F,D,T) c64, activity (B,K,T_act) bool/uint8 ->
-    posterior (B,F,K,T) f32 [, model dict]."""
+    posterior (B,F,K,T) f32 [, model dict].  info: optional (B,) int32 device tensor; when given the
+    status words are left for the caller to check (no host synchronisation here)."""
     Y = _need(Y, torch.complex64, 4, 'Y')
     B, F, D, T = Y.shape
     if activity.dtype == torch.bool:
@@ -145,7 +171,9 @@ def cacgmm(Y, activity, iterations, iterations_post=1, affiliation_eps=1e-10,
     assert activity.shape[0] == B, (activity.shape, Y.shape)
     K, T_act = activity.shape[1], activity.shape[2]
     post = torch.empty((B, F, K, T), dtype=torch.float32, device=Y.device)
-    info = torch.zeros((max(B, 1),), dtype=torch.int32, device=Y.device)
+    own_info = info is None
+    if own_info:
+        info = new_info(B, Y.device)
     weight = logdet = cov = None
     if return_model:
         weight = torch.empty((B, F, K), dtype=torch.float64, device=Y.device)
@@ -156,13 +184,14 @@ def cacgmm(Y, activity, iterations, iterations_post=1, affiliation_eps=1e-10,
         _ptr(Y), _ptr(activity), _ptr(post), int(iterations), int(iterations_post),
         float(affiliation_eps), float(eigenvalue_floor), B, F, D, T, K, T_act, _ptr(_tper(frames, B, Y.device)),
         _ptr(weight), _ptr(logdet), _ptr(cov), _ptr(info), _ptr(ws), ws.numel(), _stream()))
-    check_info(info, 'cacgmm')
+    if own_info:
+        check_info(info, 'cacgmm')
     if return_model:
         return post, dict(weight=weight, log_determinant=logdet, covariance=cov)
     return post
 
 
-def _bf_call(Y, fn, lead_args, bf, bf_arg, postfilter, K=None, return_aux=False, frames=None):
+def _bf_call(Y, fn, lead_args, bf, bf_arg, postfilter, K=None, return_aux=False, frames=None, info=None):
     B, F, D, T = Y.shape
     if bf not in _lib.BF_TYPES:
         raise NotImplementedError(bf)
@@ -170,7 +199,9 @@ def _bf_call(Y, fn, lead_args, bf, bf_arg, postfilter, K=None, return_aux=False,
         raise NotImplementedError(postfilter)
     X = torch.empty((B, F, T), dtype=torch.complex64, device=Y.device)
     ref = torch.full((max(B, 1),), -1, dtype=torch.int32, device=Y.device)
-    info = torch.zeros((max(B, 1),), dtype=torch.int32, device=Y.device)
+    own_info = info is None
+    if own_info:
+        info = new_info(B, Y.device)
     wts = torch.zeros((B, F, D), dtype=torch.complex128, device=Y.device) if return_aux else None
     n = _lib.workspace_bytes(_lib.OP_BEAMFORM, B, F, D, T, 2, 0)
     ws = workspace(n, Y.device)
@@ -178,14 +209,15 @@ def _bf_call(Y, fn, lead_args, bf, bf_arg, postfilter, K=None, return_aux=False,
     _lib.check(fn(_ptr(Y), *lead_args, _ptr(X), _lib.BF_TYPES[bf], int(bf_arg), _lib.POSTFILTERS[postfilter],
                   *dims, _ptr(_tper(frames, B, Y.device)), _ptr(ref), _ptr(wts), _ptr(info), _ptr(ws), ws.numel(),
                   _stream()))
-    check_info(info, 'beamform')
+    if own_info:
+        check_info(info, 'beamform')
     if return_aux:
         return X, dict(ref_channel=ref, weights=wts)
     return X
 
 
 def beamform(Y, target_mask, distortion_mask, bf='mvdrSouden_ban', postfilter=None, bf_arg=0,
-             return_aux=False, frames=None):
+             return_aux=False, frames=None, info=None):
     """Y (B,F,D,T) c64; masks (B,F,T) f32 -> X_hat (B,F,T) c64."""
     Y = _need(Y, torch.complex64, 4, 'Y')
     B, F, D, T = Y.shape
@@ -194,11 +226,12 @@ def beamform(Y, target_mask, distortion_mask, bf='mvdrSouden_ban', postfilter=No
     assert tm.shape == (B, F, T), (tm.shape, B, F, T)
     assert dm.shape == (B, F, T), (dm.shape, B, F, T)
     return _bf_call(Y, _lib.lib().gss_beamform_c64, (_ptr(tm), _ptr(dm)), bf, bf_arg, postfilter,
-                    return_aux=return_aux, frames=frames)
+                    return_aux=return_aux, frames=frames, info=info)
 
 
 def beamform_from_posterior(Y, posterior, target_index, start_ctx=None, end_ctx=None,
-                            bf='mvdrSouden_ban', postfilter=None, bf_arg=0, return_aux=False, frames=None):
+                            bf='mvdrSouden_ban', postfilter=None, bf_arg=0, return_aux=False, frames=None,
+                            info=None):
     """Fused core.py:537-564.  posterior (B,F,K,T) f32; target_index/start_ctx/end_ctx (B) int32."""
     Y = _need(Y, torch.complex64, 4, 'Y')
     B, F, D, T = Y.shape
@@ -216,20 +249,34 @@ def beamform_from_posterior(Y, posterior, target_index, start_ctx=None, end_ctx=
     ti, sc, ec = ivec(target_index), ivec(start_ctx), ivec(end_ctx)
     return _bf_call(Y, _lib.lib().gss_beamform_from_posterior_c64,
                     (_ptr(post), _ptr(ti), _ptr(sc), _ptr(ec)), bf, bf_arg, postfilter, K=K,
-                    return_aux=return_aux, frames=frames)
+                    return_aux=return_aux, frames=frames, info=info)
 
 
-def wpe(Y, taps=10, delay=3, iterations=3, psd_context=0, frames=None):
-    """Y (B,F,D,T) c64 -> dereverberated (B,F,D,T) c64."""
+def wpe(Y, taps=10, delay=3, iterations=3, psd_context=0, frames=None, gram_mode=None, i8_tau=None,
+        stats=None, info=None):
+    """Y (B,F,D,T) c64 -> dereverberated (B,F,D,T) c64.
+
+    gram_mode: None / 'auto' (INT8 tensor-core correlation build where it is built, ill-conditioned
+    bins re-done in float64), 'f64', 'i8' (diagnostics: no re-do), 'i8+redo'.  stats: optional int32[4]
+    device tensor, accumulated by the call ([0] bins, [1] bins that ended on the float64 list,
+    [2] float64 re-do builds).  info: optional (B,) int32 device tensor for GSS_INFO_SINGULAR words
+    (when omitted a fresh one is allocated and checked here, which synchronises)."""
     Y = _need(Y, torch.complex64, 4, 'Y')
     B, F, D, T = Y.shape
+    if gram_mode not in _lib.WPE_GRAM_MODES:
+        raise NotImplementedError(gram_mode)
     X = torch.empty_like(Y)
-    info = torch.zeros((max(B, 1),), dtype=torch.int32, device=Y.device)
+    own_info = info is None
+    if own_info:
+        info = new_info(B, Y.device)
     n = _lib.workspace_bytes(_lib.OP_WPE, B, F, D, T, 0, int(taps))
     ws = workspace(n, Y.device)
-    _lib.check(_lib.lib().gss_wpe_c64(_ptr(Y), _ptr(X), int(taps), int(delay), int(iterations),
-                                      int(psd_context), B, F, D, T, _ptr(_tper(frames, B, Y.device)), _ptr(info),
-                                      _ptr(ws), ws.numel(), _stream()))
+    _lib.check(_lib.lib().gss_wpe_c64_ex(_ptr(Y), _ptr(X), int(taps), int(delay), int(iterations),
+                                         int(psd_context), B, F, D, T, _ptr(_tper(frames, B, Y.device)),
+                                         _lib.WPE_GRAM_MODES[gram_mode], -1.0 if i8_tau is None else float(i8_tau),
+                                         _ptr(stats), _ptr(info), _ptr(ws), ws.numel(), _stream()))
+    if own_info:
+        check_info(info, 'wpe')
     return X
 
 

@@ -21,7 +21,7 @@ Nothing here computes: numerics are the libgss kernels behind ``Enhancer``.
 """
 from __future__ import annotations
 
-import queue
+import queue as queue_mod
 import threading
 import time
 from dataclasses import dataclass, field
@@ -71,6 +71,13 @@ class SessionReport:
     batches: int = 0
     seconds: float = 0.0
     audio_seconds: float = 0.0
+    busy_seconds: float = 0.0                       # time inside the enhancement calls (this rank)
+    padded_samples: int = 0                         # samples the batches occupied after padding ...
+    valid_samples: int = 0                          # ... and the samples that were real input
+
+    @property
+    def padding_efficiency(self):
+        return self.valid_samples / self.padded_samples if self.padded_samples else float('nan')
 
     def __str__(self):
         rtf = self.seconds / self.audio_seconds if self.audio_seconds else float('nan')
@@ -88,8 +95,11 @@ class SessionScheduler:
 
     def __init__(self, enhancer, load_fn, path_fn, finish_fn=None, *, batch_size=8, window=64,
                  max_batch_samples=8 * 60 * 16000, prefetch=2, skip_existing=True, strict=False,
-                 sample_rate=16000, verbose=False):
+                 sample_rate=16000, verbose=False, sink_fn=None):
+        """sink_fn(ex, x): where a finished utterance goes instead of a wav file (in-memory runs,
+        benchmarks); path_fn may then be None."""
         self.enhancer, self.load_fn, self.path_fn = enhancer, load_fn, path_fn
+        self.sink_fn = sink_fn
         self.finish_fn = finish_fn or (lambda ex, x: x)
         self.batch_size, self.window, self.max_batch_samples = batch_size, window, max_batch_samples
         self.prefetch, self.skip_existing, self.strict = prefetch, skip_existing, strict
@@ -113,7 +123,7 @@ class SessionScheduler:
     def plan(self, examples):
         todo, skipped = [], 0
         for i, ex in enumerate(examples):
-            if self.skip_existing and Path(self.path_fn(ex)).exists():
+            if self.skip_existing and self.path_fn is not None and Path(self.path_fn(ex)).exists():
                 skipped += 1
             else:
                 todo.append(i)
@@ -123,25 +133,62 @@ class SessionScheduler:
         return [[todo[j] for j in b] for b in batches], skipped
 
     # -- execution --------------------------------------------------------------------------
-    def run(self, examples):
+    def run(self, examples, queue=None):
+        """Enhance `examples`.  queue=None: all planned batches, in plan order (the list is this
+        rank's own shard).  queue = an iterable of batch indices, or a callable n_batches -> iterable
+        (`sharding.WorkQueue`): `examples`
+        is the WHOLE job on every rank, every rank makes the same plan (deterministic, longest
+        batches first) and takes the batches the queue hands it -- the task farm of
+        `dlp_mpi.split_managed` (pb_chime5/core.py:381)."""
         report = SessionReport()
         t0 = time.perf_counter()
         batches, report.skipped = self.plan(examples)
-        loaded = queue.Queue(maxsize=max(1, self.prefetch))
-        to_write = queue.Queue(maxsize=4 * self.batch_size)
+        if queue is not None:
+            order = sorted(range(len(batches)),
+                           key=lambda j: (-len(batches[j]) * max(self.example_length(examples[i]) for i in batches[j]), j))
+            batches = [batches[j] for j in order]
+            if callable(queue):
+                queue = queue(len(batches))
+            batch_iter = (batches[j] for j in queue)
+        else:
+            batch_iter = iter(batches)
+        loaded = queue_mod.Queue(maxsize=max(1, self.prefetch))
+        to_write = queue_mod.Queue(maxsize=4 * self.batch_size)
         errors = []
+        stop = threading.Event()
+        prepare = getattr(self.enhancer, 'prepare_observation', None)
+
+        def put(q, item):
+            """blocking put that gives up when the run was stopped (no thread left hanging on a full queue)"""
+            while not stop.is_set():
+                try:
+                    q.put(item, timeout=0.1)
+                    return True
+                except queue_mod.Full:
+                    continue
+            return False
 
         def loader():
-            for b in batches:
-                items = []
-                for i in b:
-                    ex = examples[i]
-                    try:
-                        items.append((ex, self.load_fn(ex), None))
-                    except Exception as e:  # noqa: BLE001  (isolated per example)
-                        items.append((ex, None, e))
-                loaded.put(items)
-            loaded.put(None)
+            try:
+                for b in batch_iter:
+                    if stop.is_set():
+                        return
+                    items = []
+                    for i in b:
+                        ex = examples[i]
+                        try:
+                            data = self.load_fn(ex)
+                            if prepare is not None:
+                                # host half of the hot path (pinned float32 samples, activity framing)
+                                # here, in the loader thread, while the GPU works on the previous batch
+                                data = data + (prepare(data[0], data[1], data[2], ex),)
+                            items.append((ex, data, None))
+                        except Exception as e:  # noqa: BLE001  (isolated per example)
+                            items.append((ex, None, e))
+                    if not put(loaded, items):
+                        return
+            finally:
+                put(loaded, None)
 
         def writer():
             while True:
@@ -150,9 +197,12 @@ class SessionScheduler:
                     return
                 ex, x = job
                 try:
-                    path = Path(self.path_fn(ex))
-                    path.parent.mkdir(parents=True, exist_ok=True)
-                    audio_io.dump_audio(x, path, sample_rate=self.sample_rate)
+                    if self.sink_fn is not None:
+                        self.sink_fn(ex, x)
+                    else:
+                        path = Path(self.path_fn(ex))
+                        path.parent.mkdir(parents=True, exist_ok=True)
+                        audio_io.dump_audio(x, path, sample_rate=self.sample_rate)
                 except Exception as e:  # noqa: BLE001
                     errors.append((ex.get('example_id'), repr(e)))
 
@@ -172,36 +222,23 @@ class SessionScheduler:
                         self._fail(report, ex, err)
                     else:
                         good.append((ex, data))
-                if not good:
-                    continue
-                try:
-                    outs = self._enhance([d for _, d in good], [e for e, _ in good])
-                except Exception as e:  # noqa: BLE001
-                    if self.strict or len(good) == 1:
-                        outs = None
-                        first_err = e
-                    else:
-                        outs, first_err = [], None          # retry one by one: isolate the bad example
-                        for ex, d in good:
-                            try:
-                                outs.append(self._enhance([d], [ex])[0])
-                            except Exception as e1:  # noqa: BLE001
-                                outs.append(e1)
-                    if outs is None:
-                        for ex, _ in good:
-                            self._fail(report, ex, first_err)
-                        continue
-                for (ex, d), x in zip(good, outs):
-                    if isinstance(x, Exception):
-                        self._fail(report, ex, x)
-                        continue
-                    x = self.finish_fn(ex, x)
-                    report.audio_seconds += x.shape[-1] / self.sample_rate
-                    to_write.put((ex, x))
-                    report.done += 1
+                # one pass of the hot path per (channels, classes) signature: a recording with a
+                # missing array or an extra speaker does not take its batch mates down
+                groups = {}
+                for ex, d in good:
+                    groups.setdefault((int(d[0].shape[0]), len(d[1])), []).append((ex, d))
+                for group in groups.values():
+                    self._run_group(report, group, to_write)
         finally:
+            stop.set()
+            while True:                                   # unblock and drop whatever the loader prefetched
+                try:
+                    loaded.get_nowait()
+                except queue_mod.Empty:
+                    break
             to_write.put(None)
             wt.join()
+            lt.join(timeout=5)
         for eid, msg in errors:
             report.failed.append((eid, msg))
         report.seconds = time.perf_counter() - t0
@@ -209,7 +246,38 @@ class SessionScheduler:
             raise RuntimeError(f'ERROR: Failed example: {report.failed[0][0]}: {report.failed[0][1]}')
         return report
 
+    def _run_group(self, report, good, to_write):
+        tb = time.perf_counter()
+        try:
+            outs = self._enhance([d for _, d in good], [e for e, _ in good])
+        except Exception as e:  # noqa: BLE001
+            if self.strict or len(good) == 1:
+                for ex, _ in good:
+                    self._fail(report, ex, e)
+                return
+            outs = []                                     # retry one by one: isolate the bad example
+            for ex, d in good:
+                try:
+                    outs.append(self._enhance([d], [ex])[0])
+                except Exception as e1:  # noqa: BLE001
+                    outs.append(e1)
+        finally:
+            report.busy_seconds += time.perf_counter() - tb
+        lens = [int(d[0].shape[-1]) for _, d in good]
+        report.padded_samples += len(lens) * max(lens)
+        report.valid_samples += sum(lens)
+        for (ex, d), x in zip(good, outs):
+            if isinstance(x, Exception):
+                self._fail(report, ex, x)
+                continue
+            x = self.finish_fn(ex, x)
+            report.audio_seconds += x.shape[-1] / self.sample_rate
+            to_write.put((ex, x))
+            report.done += 1
+
     def _enhance(self, datas, exs):
+        if len(datas[0]) == 4:                                # prepared by the loader thread
+            return self.enhancer.enhance_prepared_batch([d[3] for d in datas])
         obs = [d[0] for d in datas]
         acts = [d[1] for d in datas]
         spk = [d[2] for d in datas]
@@ -220,6 +288,29 @@ class SessionScheduler:
         report.failed.append((ex.get('example_id'), repr(err)))
         if self.strict:
             raise err
+
+
+def run_distributed(sched, examples, schedule='auto'):
+    """Run `examples` (the WHOLE job, identical on every rank) through `sched` on this rank's share.
+
+    schedule: 'dynamic' -- task farm (`sharding.WorkQueue`, the semantics of dlp_mpi.split_managed,
+              core.py:381): every rank plans the same length-sorted batches and pulls the next one
+              when it is free; 'lpt' -- static shards balanced by the known segment lengths;
+              'strided' -- i % world == rank (kaldi_run.py:73-76); 'auto' -- dynamic when a
+              process group with more than one rank is up, else lpt."""
+    from . import sharding
+    rank, world = sharding.init_process_group()
+    if schedule == 'auto':
+        schedule = 'dynamic' if world > 1 else 'lpt'
+    if world == 1:
+        return sched.run(examples)
+    if schedule == 'dynamic':
+        return sched.run(examples, queue=sharding.WorkQueue)
+    lengths = [sched.example_length(ex) for ex in examples] if schedule == 'lpt' else None
+    if schedule not in ('lpt', 'strided'):
+        raise ValueError(schedule)
+    mine = sharding.shard_indices(len(examples), rank, world, lengths=lengths)
+    return sched.run([examples[i] for i in mine])
 
 
 def stack_arrays(arrays, multiarray):

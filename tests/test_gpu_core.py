@@ -116,6 +116,33 @@ def test_gss_channel_and_class_counts(D, K):
     assert np.abs(got - ref).max() < 1e-4
 
 
+@pytest.mark.parametrize('D,K', [(13, 3), (14, 4), (18, 5), (22, 6),          # fused kernel on the next padded size
+                                 (26, 3), (29, 4), (33, 3), (34, 2),          # D > 24: runtime-shape kernel
+                                 (8, 7), (6, 12), (4, 19), (24, 8)])          # K > 6: runtime-shape kernel
+def test_gss_every_shape_the_reference_accepts(D, K):
+    """cacgmm.py:247-248 accepts K < 20 and D < 35: every such shape runs (fused kernel for K <= 6 and
+    D <= 24 on the next instantiated padded size, `cacgmm_generic.cu` otherwise) and meets the bar."""
+    Obs, act = synth.make_utterance(500 + 7 * D + K, D=D, T=300, F=2, K=K)
+    got, ref = _gss_both(Obs, act, 8)
+    assert np.abs(got - ref).max() < 1e-4
+    if K <= 6:                                   # unguided refinement passes on the same kernels
+        got2, ref2 = _gss_both(Obs[:, :, :1], act, 3, 3)
+        assert np.abs(got2 - ref2).max() < 1e-4
+
+
+@pytest.mark.parametrize('D', [13, 22, 26, 29])
+def test_beamformer_every_channel_count(D):
+    """beamforming_wrapper.py:44 accepts D < 30: PSD + MVDR-Souden + BAN and GEV on the next built size"""
+    Obs, act = synth.make_utterance(40 + D, D=D, T=200, F=3, K=3)
+    Obs = Obs.astype(np.complex128)
+    rng = np.random.default_rng(D)
+    tm, dm = rng.random((200, 3)), rng.random((200, 3))
+    X = core.Beamformer('mvdrSouden_ban', None)(Obs, tm, dm)
+    assert rel_err(X, oracle.beamform(Obs, tm, dm)) < 1e-4
+    Xg = core.Beamformer('gev_ban', None)(Obs, tm, dm)
+    assert rel_err(np.abs(Xg), np.abs(oracle.beamform(Obs, tm, dm, bf='gev_ban'))) < 1e-4
+
+
 def test_gss_edge_cases():
     Obs, act = synth.make_utterance(5, D=4, T=200, F=4, K=3)
     # digital silence frames stay zero vectors (utils.py:257-258) and must not produce NaN

@@ -23,7 +23,7 @@ def run_mstep(Y, w, frames=None):
     out = torch.full((B, F, K, D, D), float('nan'), dtype=torch.complex128, device=dev)
     ws = ops.workspace(B * F * (-(-T // 32) * 320 * D + 4 * (D + K)) + 4096, dev)
     fr = None if frames is None else torch.tensor(frames, dtype=torch.int32, device=dev)
-    _lib.check(_lib.lib().gss_debug_mstep_i8(ops._ptr(Yt), ops._ptr(wt), ops._ptr(out), B, F, D, T, K, ops._ptr(fr),
+    _lib.check(_lib.dev_lib().gss_debug_mstep_i8(ops._ptr(Yt), ops._ptr(wt), ops._ptr(out), B, F, D, T, K, ops._ptr(fr),
                                              ops._ptr(ws), ws.numel(), ops._stream()))
     torch.cuda.synchronize()
     return out.cpu().numpy()

@@ -26,6 +26,16 @@ def test_abi_exports_every_declared_symbol():
     for name in declared:
         getattr(handle, name)            # raises AttributeError if not exported
     assert _lib.lib().gss_version() >= 100
+    # the developer entry points live in libgss_dev.so only: the product library exports none of them
+    dev_header = (ROOT / 'include' / 'gss_dev.h').read_text()
+    dev_declared = set(re.findall(r'\b(gss_debug_[a-z0-9_]+)\s*\(', dev_header))
+    assert dev_declared == set(_lib.dev_exported_symbols()), dev_declared ^ set(_lib.dev_exported_symbols())
+    dev_handle = ctypes.CDLL(str(_lib.DEV_LIB_PATH))
+    for name in dev_declared:
+        getattr(dev_handle, name)
+        assert not hasattr(handle, name), f'{name} leaked into the product library'
+    for name in declared:
+        getattr(dev_handle, name)        # the developer library is a superset
 
 
 def test_abi_argument_errors_map_to_reference_exceptions():

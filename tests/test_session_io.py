@@ -9,6 +9,8 @@ import pytest
 from pb_chime5_b200 import audio_io
 from pb_chime5_b200.session import SessionScheduler, plan_batches, stack_arrays
 
+ROOT = Path(__file__).resolve().parent.parent
+
 
 def test_dump_audio_matches_reference_doctest(tmp_path):
     # pb_chime5/io/audiowrite.py:32-38: [1, 2, -4, 4] -> peak normalised 16-bit PCM
@@ -182,3 +184,109 @@ def test_rttm_front_door_plumbing(tmp_path):
     sig = r.signature_defaults()
     assert list(sig)[:5] == ['database_rttm', 'activity_rttm', 'chime6_dir', 'multiarray', 'context_samples']
     assert sig['multiarray'] == 'outer_array_mics' and sig['activity_garbage_class'] is True
+
+
+def test_two_rank_session_task_farm(tmp_path):
+    """world_size 2 on CPU (gloo), launched the way `mpiexec -np 2` launches the reference (OMPI_*
+    variables, no RANK / WORLD_SIZE): `run_distributed` binds the ranks, every rank plans the same
+    length-sorted batches and pulls them from the shared work queue (dlp_mpi.split_managed semantics,
+    core.py:381).  Every example is enhanced exactly once; a rank that is 20x slower per batch ends up
+    with far fewer batches instead of holding the job (it can hold at most prefetch + 1 claimed
+    batches at the end)."""
+    import json
+    import os
+    import subprocess
+    import sys
+    script = tmp_path / 'farm.py'
+    script.write_text('''
+import json, sys, time
+sys.path.insert(0, %r)
+import numpy as np
+from pb_chime5_b200 import sharding
+from pb_chime5_b200.session import SessionScheduler, run_distributed
+
+class Fake:
+    def __init__(self, delay): self.delay, self.calls = delay, []
+    def enhance_observation_batch(self, obs, acts, spk, exs=None):
+        time.sleep(self.delay)
+        self.calls.append([e['example_id'] for e in exs])
+        return [o[0] for o in obs]
+
+rank, world = sharding.init_process_group('gloo')
+exs = [{'example_id': f'ex{i}', 'session_id': 'S02', 'num_samples': 800 + 13 * i,
+        'start': {'observation': {'U01': 0}}, 'end': {'observation': {'U01': 800 + 13 * i}}} for i in range(120)]
+load = lambda ex: (np.zeros((2, ex['num_samples'])), {'P05': np.ones(ex['num_samples'], bool)}, 'P05')
+got = {}
+enh = Fake(0.2 if rank == 1 else 0.01)
+sched = SessionScheduler(enh, load, None, batch_size=4, window=64, prefetch=1, skip_existing=False, strict=True,
+                         sink_fn=lambda ex, x: got.__setitem__(ex['example_id'], x.shape[-1]))
+rep = run_distributed(sched, exs, sys.argv[1])
+sharding.barrier()
+print(json.dumps({'rank': rank, 'world': world, 'done': rep.done, 'batches': rep.batches, 'ids': sorted(got),
+                  'lens_ok': all(got[e['example_id']] == e['num_samples'] for e in exs if e['example_id'] in got)}), flush=True)
+sharding.shutdown()
+''' % str(ROOT))
+    for schedule, port in (('dynamic', '29541'), ('lpt', '29542')):
+        env = {k: v for k, v in os.environ.items() if k not in ('RANK', 'WORLD_SIZE', 'LOCAL_RANK')}
+        env.update(MASTER_ADDR='127.0.0.1', MASTER_PORT=port, OMPI_COMM_WORLD_SIZE='2')
+        procs = [subprocess.Popen([sys.executable, str(script), schedule],
+                                  env=dict(env, OMPI_COMM_WORLD_RANK=str(r), OMPI_COMM_WORLD_LOCAL_RANK=str(r)),
+                                  stdout=subprocess.PIPE, text=True) for r in range(2)]
+        outs = [json.loads(p.communicate(timeout=180)[0].strip().splitlines()[-1]) for p in procs]
+        assert all(p.returncode == 0 for p in procs)
+        outs.sort(key=lambda o: o['rank'])
+        assert [o['world'] for o in outs] == [2, 2] and all(o['lens_ok'] for o in outs)
+        assert sorted(outs[0]['ids'] + outs[1]['ids']) == sorted(f'ex{i}' for i in range(120))    # exactly once
+        assert outs[0]['done'] + outs[1]['done'] == 120
+        if schedule == 'dynamic':
+            assert outs[0]['batches'] >= 3 * outs[1]['batches'] > 0, outs       # the fast rank took most of the work
+        else:
+            assert abs(outs[0]['done'] - outs[1]['done']) <= 2                  # static balanced shards
+
+
+def test_session_scheduler_strict_failure_leaves_no_thread_behind(tmp_path):
+    """strict mode: the first failure raises and the loader thread ends (it used to stay blocked on
+    the full prefetch queue, holding the prefetched audio)."""
+    import threading
+    exs = _examples(tmp_path, 40)
+    exs[0]['missing'] = True
+
+    def load(ex):
+        if ex.get('missing'):
+            raise FileNotFoundError(ex['example_id'])
+        n = ex['num_samples']
+        return np.zeros((2, n)), {'P05': np.ones(n, bool)}, 'P05'
+
+    before = threading.active_count()
+    with pytest.raises(FileNotFoundError):
+        SessionScheduler(_FakeEnhancer(), load, None, batch_size=2, prefetch=1, skip_existing=False, strict=True,
+                         sink_fn=lambda ex, x: None).run(exs)
+    import time
+    time.sleep(0.5)
+    assert threading.active_count() <= before
+
+
+def test_session_batches_split_by_channel_and_class_count(tmp_path):
+    """examples of one session with a different channel count (a missing array) or class count are
+    enhanced in their own pass instead of tripping the batch (strict mode included)"""
+    exs = _examples(tmp_path, 6)
+
+    def load(ex):
+        n = ex['num_samples']
+        d = 3 if ex['example_id'] == 'ex2' else 2
+        acts = {'P05': np.ones(n, bool)}
+        if ex['example_id'] == 'ex4':
+            acts['P06'] = np.ones(n, bool)
+        return np.zeros((d, n)), acts, 'P05'
+
+    class Enh(_FakeEnhancer):
+        def enhance_observation_batch(self, obs_list, acts, spk, exs=None):
+            assert len({o.shape[0] for o in obs_list}) == 1 and len({len(a) for a in acts}) == 1
+            return super().enhance_observation_batch(obs_list, acts, spk, exs)
+
+    enh = Enh()
+    rep = SessionScheduler(enh, load, None, batch_size=8, skip_existing=False, strict=True,
+                           sink_fn=lambda ex, x: None).run(exs)
+    assert rep.done == 6 and not rep.failed
+    assert sorted(map(sorted, enh.calls)) == [['ex0', 'ex1', 'ex3', 'ex5'], ['ex2'], ['ex4']]
+    assert 0 < rep.padding_efficiency <= 1

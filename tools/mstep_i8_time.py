@@ -20,7 +20,7 @@ ws = ops.workspace(B * F * (-(-T // 32) * 320 * D + 4 * (D + K)) + 4096, dev)
 
 
 def i8():
-    _lib.check(_lib.lib().gss_debug_mstep_i8(ops._ptr(Y), ops._ptr(w), ops._ptr(out), B, F, D, T, K, None,
+    _lib.check(_lib.dev_lib().gss_debug_mstep_i8(ops._ptr(Y), ops._ptr(w), ops._ptr(out), B, F, D, T, K, None,
                                              ops._ptr(ws), ws.numel(), ops._stream()))
 
 

@@ -45,7 +45,7 @@ def gram(Yt, invt, mode, variant, taps, delay):
     out = torch.zeros((B, F, LD + D, LD), dtype=torch.complex128, device=Yt.device)
     n = _lib.workspace_bytes(_lib.OP_WPE, B, F, D, T, 0, taps)
     ws = ops.workspace(n, Yt.device)
-    _lib.check(_lib.lib().gss_debug_wpe_gram(ops._ptr(Yt), ops._ptr(invt), ops._ptr(out), mode, variant,
+    _lib.check(_lib.dev_lib().gss_debug_wpe_gram(ops._ptr(Yt), ops._ptr(invt), ops._ptr(out), mode, variant,
                                              B, F, D, T, taps, delay, None, ops._ptr(ws), ws.numel(), ops._stream()))
     torch.cuda.synchronize()
     return out
