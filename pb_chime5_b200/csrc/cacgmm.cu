@@ -165,10 +165,14 @@ struct QuadAll<DP, K, NSB, NSB> {
 
 // Symmetric sweep operator on the packed lower triangle of K class matrices at once (in place:
 // -Phi^-1; pivots = squared Cholesky pivots).  The chunk of a thread (up to CH consecutive columns of
-// one row of one class) stays in registers over all D sweep steps; per step only the pivot column
+// one row of one class) stays in registers over all D sweep steps; per step only the pivot column u
 // travels through shared memory (one barrier per step: the column of the next pivot is forwarded while
-// the current step is applied).  Not inlined: the fused kernel around it is at its register limit and
-// would keep the chunk in local memory.
+// the current step is applied).
+// Branch-free step: with d = 1 / pivot and the pivot entry of the published column replaced by
+// u_j := pivot - 1, the rank-1 update  S_ic - (u_i d) conj(u_c)  is ALSO right for the entries of row
+// and column j  (S_ij - u_i d (p - 1) = u_i d;  conj(u_c) - (p - 1) d conj(u_c) = conj(u_c) d);  only the
+// pivot entry itself is fixed up (the formula gives 2 - d, the sweep wants -d).
+// Not inlined: the fused kernel around it is at its register limit and would keep the chunk in local memory.
 template <int DP, int K, int CH>
 __device__ __noinline__ void sweep_invert(cd (&sv_out)[CH], const cd* __restrict__ acc_k, const double* __restrict__ tr_s,
                                           cd* __restrict__ colb, double* __restrict__ pivb, double* __restrict__ dinvb,
@@ -183,64 +187,67 @@ __device__ __noinline__ void sweep_invert(cd (&sv_out)[CH], const cd* __restrict
 #pragma unroll
         for (int n = 0; n < CH; ++n) {
             const int c = sw_c0 + n;
-            cd v = cmake(0.0, 0.0);
             if (n < sw_n) {
-                v = cscale(acc_k[tri(sw_i, c)], itr);
+                cd v = cscale(acc_k[tri(sw_i, c)], itr);
                 if (sw_i == c) v.y = 0.0;                               // force_hermitian (utils.py:323-334)
-                if (c == 0) {                                           // column of the first pivot
-                    colb[sw_k * DP + sw_i] = v;
-                    if (sw_i == 0) { pivb[sw_k] = v.x; dinvb[sw_k] = (v.x > 0.0 && isfinite(v.x)) ? 1.0 / v.x : 0.0; }
-                }
+                sv[n] = v;
             }
-            sv[n] = v;
+        }
+        if (sw_c0 == 0) {                                               // column of the first pivot
+            const cd v = sv[0];
+            if (sw_i == 0) {
+                pivb[sw_k] = v.x; dinvb[sw_k] = (v.x > 0.0 && isfinite(v.x)) ? 1.0 / v.x : 0.0;
+                colb[sw_k * DP] = cmake(v.x - 1.0, 0.0);
+            } else {
+                colb[sw_k * DP + sw_i] = v;
+            }
         }
     }
     __syncthreads();
     for (int j = 0; j < D; ++j) {
         const cd* col = colb + (j & 1) * K * DP;
         cd* coln = colb + ((j + 1) & 1) * K * DP;
-        const double* piv = pivb + (j & 1) * K;
-        double* pivn = pivb + ((j + 1) & 1) * K;
-        const double* dinv = dinvb + (j & 1) * K;
-        double* dinvn = dinvb + ((j + 1) & 1) * K;
         if (sw_on) {
-            const double d = dinv[sw_k];
-            const cd ui = col[sw_k * DP + sw_i];
-            const cd uid = cscale(ui, d);
-            const bool on_i = (sw_i == j);
+            const double d = dinvb[(j & 1) * K + sw_k];
+            const cd uid = cscale(col[sw_k * DP + sw_i], d);
             const cd* colk = col + sw_k * DP + sw_c0;
-            cd vf = cmake(0.0, 0.0);                                // the entry of column j + 1, if this chunk has it
 #pragma unroll
             for (int n = 0; n < CH; ++n) {
-                if (n >= sw_n) continue;
-                const int c = sw_c0 + n;
-                // branch-free: entries of row/column j are S*d (the stored value IS the column
-                // entry or its conjugate), the pivot becomes -d, everything else gets the
-                // rank-1 update  S - (u_i d) conj(u_c)
-                const cd s0v = sv[n];
-                const cd uc = colk[n];
-                const bool on_c = (c == j);
-                cd v = s0v;
-                cfmsc(v, uid, uc);
-                const cd vs = cscale(s0v, d);
-                v.x = (on_i | on_c) ? vs.x : v.x;
-                v.y = (on_i | on_c) ? vs.y : v.y;
-                v.x = (on_i & on_c) ? -d : v.x;
-                v.y = (on_i & on_c) ? 0.0 : v.y;
-                sv[n] = v;
-                vf.x = (c == j + 1) ? v.x : vf.x;
-                vf.y = (c == j + 1) ? v.y : vf.y;
+                if (n < sw_n) {
+                    cd v = sv[n];
+                    cfmsc(v, uid, colk[n]);
+                    sv[n] = v;
+                }
             }
-            if (on_i && j >= sw_c0 && j < sw_c0 + sw_n) pivbuf[sw_k * DP + j] = piv[sw_k];
-            // forward the column of the next pivot
-            if (j + 1 >= sw_c0 && j + 1 < sw_c0 + sw_n) {             // entry (i, j + 1): column part
-                coln[sw_k * DP + sw_i] = vf;
-                if (sw_i == j + 1) { pivn[sw_k] = vf.x; dinvn[sw_k] = (vf.x > 0.0 && isfinite(vf.x)) ? 1.0 / vf.x : 0.0; }
-            }
-            if (sw_i == j + 1) {                                       // entries (j + 1, c < j + 1): row part, conjugated
+            const int nj = j - sw_c0;                                   // position of column j in this chunk
+            if (sw_i == j && nj >= 0 && nj < sw_n) {                    // the pivot entry: 2 - d  ->  -d
+                pivbuf[sw_k * DP + j] = pivb[(j & 1) * K + sw_k];
 #pragma unroll
                 for (int n = 0; n < CH; ++n)
-                    if (n < sw_n && sw_c0 + n != j + 1) coln[sw_k * DP + sw_c0 + n] = cconj(sv[n]);
+                    if (n == nj) { sv[n].x -= 2.0; sv[n].y = 0.0; }
+            }
+            // forward the column of the next pivot: entry (i, j + 1) of this chunk, or, for row j + 1,
+            // the conjugates of its entries (j + 1, c < j + 1)
+            const int nf = nj + 1;
+            if (nf >= 0 && nf < sw_n) {
+#pragma unroll
+                for (int n = 0; n < CH; ++n) {
+                    if (n == nf) {
+                        if (sw_i == j + 1) {
+                            const double pv = sv[n].x;
+                            pivb[((j + 1) & 1) * K + sw_k] = pv;
+                            dinvb[((j + 1) & 1) * K + sw_k] = (pv > 0.0 && isfinite(pv)) ? 1.0 / pv : 0.0;
+                            coln[sw_k * DP + sw_i] = cmake(pv - 1.0, 0.0);
+                        } else {
+                            coln[sw_k * DP + sw_i] = sv[n];
+                        }
+                    }
+                }
+            }
+            if (sw_i == j + 1) {
+#pragma unroll
+                for (int n = 0; n < CH; ++n)
+                    if (n < sw_n && n != nf) coln[sw_k * DP + sw_c0 + n] = cconj(sv[n]);
             }
         }
         __syncthreads();
@@ -248,7 +255,6 @@ __device__ __noinline__ void sweep_invert(cd (&sv_out)[CH], const cd* __restrict
 #pragma unroll
     for (int n = 0; n < CH; ++n) sv_out[n] = sv[n];
 }
-
 
 template <int DP, int K, int NT, int MINB>
 __global__ void __launch_bounds__(NT, MINB) cacgmm_em_kernel(const CacgmmParams p) {

@@ -126,14 +126,14 @@ def make_reverberant_audio(seed, D=8, N=64000, K=3, rir_len=2048, t60_taps=900.0
 # dev-shaped work lists (BASELINE.json configs[2] / configs[3])
 # ---------------------------------------------------------------------------
 
-def make_work_list(seed, n, context_s=15.0, sample_rate=16000, n_bases=4, K=5, median_s=2.0, sigma=0.8):
+def make_work_list(seed, n, context_s=15.0, sample_rate=16000, n_bases=4, K=5, median_s=2.0, sigma=0.8, min_s=0.3):
     """n utterance descriptors with dev-shaped durations: LogNormal(median 2 s, sigma 0.8) clipped to
-    [0.3, 20] s, plus `context_s` seconds of context on both sides (the reference's default
+    [min_s = 0.3, 20] s, plus `context_s` seconds of context on both sides (the reference's default
     context_samples=240000, core.py:576).  Plain dicts of ints (cheap to broadcast): the audio itself
     is cut from one of `n_bases` long base recordings every rank synthesises locally
     (`make_base_recording`), starting at `offset`."""
     rng = np.random.default_rng(seed)
-    dur = np.clip(rng.lognormal(np.log(median_s), sigma, size=n), 0.3, 20.0)
+    dur = np.clip(rng.lognormal(np.log(median_s), sigma, size=n), min_s, 20.0)
     ctx = int(round(context_s * sample_rate))
     items = []
     for i in range(n):
