@@ -61,6 +61,7 @@ typedef struct { float re, im; } gss_c64;
 #define GSS_OP_STFT           4
 #define GSS_OP_ISTFT          5
 #define GSS_OP_ENHANCE        6
+#define GSS_OP_BF_VECTOR      7
 
 #define GSS_BF_MVDR_SOUDEN_BAN 0  /* core.py:249-258 */
 #define GSS_BF_GEV_BAN         1  /* beamforming_wrapper.py:192-208 */
@@ -140,6 +141,31 @@ int gss_beamform_from_posterior_c64(const gss_c64* Y, const float* posterior,
                      int B, int F, int D, int T, int K, const int* T_per_utt,
                      int* ref_channel_out, double* weights_out,
                      int* info, void* ws, size_t ws_bytes, void* stream);
+
+/* ---- beamforming vectors from PSD matrices: the `get_bf_vector` DSL of pb_bss
+ * (pb_bss/extraction/beamformer_wrapper.py:108-227): "[rank1_pca+|rank1_gev+]core[+ban]".
+ * Phi_X, Phi_N (B,F,D,D) complex128 (re,im interleaved doubles), Phi_N may be NULL for 'pca' / 'chN';
+ * w_out (B,F,D) complex128.  core = GSS_BFCORE_*; rank1: 0 none, 1 rank1_pca, 2 rank1_gev;
+ * ref_channel: -1 = SNR-optimal over the F bins of each utterance (mvdr_souden / wmwf,
+ * beamformer.py:524-543), else fixed; distortion_weight: wmwf mu (< 0: 'frequency_dependent');
+ * pca_scaling: 0 none, 1 'trace', 2 'eigenvalue'.  Eigenvector phases (pca, gev), which LAPACK leaves
+ * unspecified, are fixed deterministically (pca: largest component real positive; gev: (Phi_N w)[0] real
+ * non-negative).  Workspace: gss_workspace_bytes(GSS_OP_BF_VECTOR, B, F, D, ...). */
+#define GSS_BFCORE_MVDR_SOUDEN   0
+#define GSS_BFCORE_GEV           1
+#define GSS_BFCORE_WMWF          2
+#define GSS_BFCORE_PCA           3
+#define GSS_BFCORE_PCA_MVDR      4   /* 'pca+mvdr' */
+#define GSS_BFCORE_GEVATF_MVDR   5   /* 'scaled_gev_atf+mvdr' */
+#define GSS_BFCORE_CH            6   /* 'chN' */
+/* gss_beamform_c64 / gss_beamform_from_posterior_c64 also accept a DSL program as `bf_type` (the
+ * reference's default keyword arguments; `bf_arg` = N of 'chN'): */
+#define GSS_BF_PROGRAM_FLAG      0x100
+#define GSS_BF_PROGRAM(core, rank1, ban)  (GSS_BF_PROGRAM_FLAG | (core) | ((rank1) << 4) | ((ban) << 6))
+int gss_bf_vector_c128(const double* Phi_X, const double* Phi_N, double* w_out,
+                       int core, int rank1, int ban, int ref_channel, double distortion_weight,
+                       int pca_scaling, int channel, int B, int F, int D,
+                       int* ref_channel_out, int* info, void* ws, size_t ws_bytes, void* stream);
 
 /* ---- WPE dereverberation (WPE.__call__, core.py:48-88 -> nara_wpe.wpe.wpe_v8,
  * third party) ---------------------------------------------------------------

@@ -498,3 +498,98 @@ def enhance_observation(obs, sample_activity, target_index, *, stft_size=1024,
     out['x_hat'] = istft(out['X_hat'], stft_size, stft_shift, stft_fading)
     out['activity_freq'] = act
     return out
+
+
+# ---------------------------------------------------------------------------
+# get_bf_vector DSL  (pb_bss/pb_bss/extraction/beamformer_wrapper.py:108-227 and the
+# beamformer.py functions it dispatches to); SURVEY.md section 8 row f4
+# ---------------------------------------------------------------------------
+
+def pca_vector(psd, scaling=None):
+    """beamformer.py:148-202: principal eigenvector (np.linalg.eigh, largest eigenvalue)."""
+    psd = np.asarray(psd)
+    vals, vecs = np.linalg.eigh(psd)
+    v, lam = vecs[..., -1], vals[..., -1]
+    if scaling is None:
+        return v
+    if scaling == 'trace':
+        return v * (np.sqrt(np.trace(psd, axis1=-1, axis2=-2)) / np.linalg.norm(v, axis=-1))[..., None]
+    if scaling == 'eigenvalue':
+        return v * (lam / np.linalg.norm(v, axis=-1))[..., None]
+    raise ValueError(scaling)
+
+
+def mvdr_vector(atf, psd_n):
+    """beamformer.py:205-235: Phi_N^-1 a / (a^H Phi_N^-1 a), Phi_N hermitised first."""
+    psd_n = 0.5 * (psd_n + np.conj(np.swapaxes(psd_n, -1, -2)))
+    num = np.linalg.solve(psd_n, atf[..., None])[..., 0]
+    den = np.einsum('...d,...d->...', atf.conj(), num)
+    return num / den[..., None]
+
+
+def gev_atf_vector(psd_x, psd_n):
+    """beamformer_wrapper.py:24-44: Phi_N w_gev."""
+    return np.einsum('...dD,...D->...d', psd_n, gev_vector(psd_x, psd_n))
+
+
+def rank1_approximation(kind, psd_x, psd_n):
+    """beamformer_wrapper.py:11-21, 47-62, 88-101: trace-preserving rank-1 model of Phi_X."""
+    if kind == 'rank1_pca':
+        a = pca_vector(psd_x)
+    elif kind == 'rank1_gev':
+        a = gev_atf_vector(psd_x, psd_n)
+    else:
+        raise ValueError(kind, 'use either rank1_pca or rank1_gev')
+    r1 = np.einsum('...d,...D->...dD', a, a.conj())
+    scale = np.trace(psd_x, axis1=-1, axis2=-2) / np.trace(r1, axis1=-1, axis2=-2)
+    return scale[..., None, None] * r1
+
+
+def wmwf_vector(psd_x, psd_n, reference_channel=None, distortion_weight=1.0, return_ref_channel=False):
+    """beamformer.py:620-672 (no channel_selection_vector)."""
+    phi = _solve_with_fallback(psd_n, psd_x)
+    lam = np.trace(phi, axis1=-1, axis2=-2)[..., None, None]
+    if isinstance(distortion_weight, str):
+        assert distortion_weight == 'frequency_dependent', distortion_weight
+        filt = phi / np.sqrt(psd_x[..., 0:1, 0:1] * lam)
+    else:
+        filt = phi / (distortion_weight + lam)
+    if reference_channel is None:
+        # beamformer.py:524-543 with its default eps
+        reference_channel = optimal_reference_channel(filt, psd_x, psd_n, F64_TINY)
+    w = filt[..., reference_channel]
+    return (w, reference_channel) if return_ref_channel else w
+
+
+def get_bf_vector(beamformer, psd_x, psd_n=None, **bf_kwargs):
+    """beamformer_wrapper.py:108-227.  psd_* (F, D, D) -> (F, D)."""
+    assert isinstance(beamformer, str) and 'lcmv' not in beamformer, beamformer
+    psd_x = np.asarray(psd_x, dtype=np.complex128)
+    psd_n = None if psd_n is None else np.asarray(psd_n, dtype=np.complex128)
+    ban = beamformer.endswith('+ban')
+    core = beamformer[:-len('+ban')] if ban else beamformer
+    if core == 'pca':
+        w = pca_vector(psd_x, **bf_kwargs)
+    elif core in ('pca+mvdr', 'scaled_gev_atf+mvdr'):
+        atf = pca_vector(psd_x) if core.startswith('pca') else gev_atf_vector(psd_x, psd_n)
+        w = mvdr_vector(atf, psd_n)
+    elif core in ('mvdr_souden', 'rank1_pca+mvdr_souden', 'rank1_gev+mvdr_souden'):
+        if core != 'mvdr_souden':
+            psd_x = rank1_approximation(core.split('+')[0], psd_x, psd_n)
+        w = mvdr_souden(psd_x, psd_n, **bf_kwargs)
+    elif core in ('gev', 'rank1_pca+gev', 'rank1_gev+gev'):
+        if core != 'gev':
+            psd_x = rank1_approximation(core.split('+')[0], psd_x, psd_n)
+        w = gev_vector(psd_x, psd_n)
+    elif core in ('wmwf', 'rank1_pca+wmwf', 'rank1_gev+wmwf'):
+        if core != 'wmwf':
+            psd_x = rank1_approximation(core.split('+')[0], psd_x, psd_n)
+        w = wmwf_vector(psd_x, psd_n, **bf_kwargs)
+    elif core.startswith('ch') and core[2:].isdigit():
+        w = np.zeros(psd_x.shape[:-1], dtype=np.complex128)
+        w[..., int(core[2:])] = 1
+    else:
+        raise ValueError(f'Could not find implementation for {core}.\nOriginal call contained {beamformer}.')
+    if ban:
+        w = blind_analytic_normalization(w, psd_n)
+    return w

@@ -15,6 +15,12 @@ from oracle import refboot
 
 OUT = Path(__file__).resolve().parent.parent / 'tests' / 'golden'
 
+# DSL strings the reference evaluates under numpy 2 ('pca+mvdr' / 'scaled_gev_atf+mvdr' go through
+# get_mvdr_vector, whose np.linalg.solve(a, vector-stack) call breaks on numpy >= 2.0: SURVEY appendix B)
+BF_DSL_NAMES = ['mvdr_souden', 'mvdr_souden+ban', 'rank1_pca+mvdr_souden', 'rank1_gev+mvdr_souden',
+                'rank1_gev+mvdr_souden+ban', 'gev', 'gev+ban', 'rank1_pca+gev', 'rank1_pca+gev+ban',
+                'wmwf', 'wmwf+ban', 'rank1_pca+wmwf', 'rank1_gev+wmwf', 'pca', 'pca+ban', 'ch2', 'ch1+ban']
+
 
 def main():
     warnings.filterwarnings('ignore')
@@ -53,6 +59,19 @@ def main():
             w_mvdr_ban=bf._w_mvdr_souden_ban, X_mvdr_ban=X_mvdr,
             X_gev_ban_abs=np.abs(X_gev))
         print(name, post.shape, 'ref_channel', ref_ch)
+
+    # ---- get_bf_vector DSL (beamformer_wrapper.py:108-227) on the PSD matrices of a fixture ----
+    from pb_bss.extraction.beamformer_wrapper import get_bf_vector
+    g = np.load(OUT / 'gss_d8_k4.npz')
+    dsl = {}
+    for name in BF_DSL_NAMES:
+        dsl[name.replace('+', '__')] = get_bf_vector(name, g['cov_x'].copy(), g['cov_n'].copy())
+    dsl['wmwf_mu0p25'] = get_bf_vector('wmwf', g['cov_x'].copy(), g['cov_n'].copy(), distortion_weight=0.25)
+    dsl['wmwf_fd'] = get_bf_vector('wmwf', g['cov_x'].copy(), g['cov_n'].copy(), distortion_weight='frequency_dependent')
+    dsl['pca_trace'] = get_bf_vector('pca', g['cov_x'].copy(), g['cov_n'].copy(), scaling='trace')
+    dsl['pca_eigenvalue'] = get_bf_vector('pca', g['cov_x'].copy(), g['cov_n'].copy(), scaling='eigenvalue')
+    np.savez_compressed(OUT / 'bf_dsl_d8.npz', cov_x=g['cov_x'], cov_n=g['cov_n'], **dsl)
+    print('bf_dsl_d8', sorted(dsl))
 
     # ---- whole path on raw audio through Enhancer.enhance_observation ---
     for name, wpe in (('enh_nowpe', None), ('enh_wpe', dict(taps=4, delay=2, iterations=3, psd_context=0))):

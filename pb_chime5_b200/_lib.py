@@ -25,10 +25,13 @@ INFO_NONFINITE = 2
 INFO_NO_CONVERGE = 3
 INFO_SINGULAR = 4
 
-OP_WEIGHTED_COV, OP_CACGMM, OP_BEAMFORM, OP_WPE, OP_STFT, OP_ISTFT, OP_ENHANCE = range(7)
+OP_WEIGHTED_COV, OP_CACGMM, OP_BEAMFORM, OP_WPE, OP_STFT, OP_ISTFT, OP_ENHANCE, OP_BF_VECTOR = range(8)
 
 BF_TYPES = {'mvdrSouden_ban': 0, 'gev_ban': 1, 'ch': 2, 'sum': 3, 'mvdrSouden': 4, 'gev': 5}
 POSTFILTERS = {None: 0, 'mask_mul': 1}
+BF_CORES = {'mvdr_souden': 0, 'gev': 1, 'wmwf': 2, 'pca': 3, 'pca+mvdr': 4, 'scaled_gev_atf+mvdr': 5, 'ch': 6}
+BF_RANK1 = {None: 0, 'rank1_pca': 1, 'rank1_gev': 2}
+PCA_SCALING = {None: 0, 'trace': 1, 'eigenvalue': 2}
 
 _p = C.c_void_p
 _i = C.c_int
@@ -52,6 +55,7 @@ _SIGNATURES = {
                               _p, _p, _p, _p, _sz, _p]),
     'gss_beamform_from_posterior_c64': (_i, [_p, _p, _p, _p, _p, _p, _i, _i, _i,
                                              _i, _i, _i, _i, _i, _p, _p, _p, _p, _p, _sz, _p]),
+    'gss_bf_vector_c128': (_i, [_p, _p, _p, _i, _i, _i, _i, _d, _i, _i, _i, _i, _i, _p, _p, _p, _sz, _p]),
     'gss_wpe_c64': (_i, [_p, _p, _i, _i, _i, _i, _i, _i, _i, _i, _p, _p, _p, _sz, _p]),
     'gss_wpe_c64_ex': (_i, [_p, _p, _i, _i, _i, _i, _i, _i, _i, _i, _p, _i, _d, _p, _p, _p, _sz, _p]),
     'gss_enhance_c64': (_i, [_p] * 8 + [_i] * 15 + [_p, _p, _sz, _p]),

@@ -287,24 +287,42 @@ class Beamformer:
             return 'sum', 0
         raise NotImplementedError(bf)
 
+    def _dsl(self):
+        """Extension: any `get_bf_vector` string of pb_bss (beamformer_wrapper.py:114-227), e.g.
+        'rank1_gev+mvdr_souden+ban' or 'wmwf+ban', is accepted as `type` too -> parsed program, else None."""
+        if self.type in ('mvdrSouden_ban', 'gev_ban', 'mvdrSouden', 'gev', 'ch2', 'sum'):
+            return None
+        from .extraction import parse_beamformer
+        try:
+            return parse_beamformer(self.type)
+        except (ValueError, AssertionError):
+            raise NotImplementedError(self.type) from None
+
     def _check_postfilter(self):
         if self.postfilter not in (None, 'mask_mul'):
             raise NotImplementedError(self.postfilter)
 
     def _run(self, Y, target_mask, distortion_mask):
         """Y (B,F,D,T); masks (B,F,T) f32 -> X_hat (B,F,T) c64."""
-        bf, arg = self._bf_args()
         self._check_postfilter()
+        bf, arg = self._dsl_type() if self._dsl() is not None else self._bf_args()
         return ops.beamform(Y, target_mask, distortion_mask, bf=bf, postfilter=self.postfilter, bf_arg=arg)
 
+    def _dsl_type(self):
+        """`bf_type` word of a DSL program for the C ABI (GSS_BF_PROGRAM, include/gss.h) + N of 'chN'"""
+        from . import _lib
+        p = self._dsl()
+        return (0x100 | _lib.BF_CORES[p['core']] | (_lib.BF_RANK1[p['rank1']] << 4) | (int(p['ban']) << 6)), p['channel']
+
     def _run_from_posterior(self, Y, posterior, target_index, start_ctx, end_ctx, frames=None, info=None):
-        bf, arg = self._bf_args()
+        bf, arg = self._dsl_type() if self._dsl() is not None else self._bf_args()
         self._check_postfilter()
         return ops.beamform_from_posterior(Y, posterior, target_index, start_ctx, end_ctx, bf=bf,
                                            postfilter=self.postfilter, bf_arg=arg, frames=frames, info=info)
 
     def __call__(self, Obs, target_mask, distortion_mask, debug=False):
-        self._bf_args()
+        if self._dsl() is None:
+            self._bf_args()
         self._check_postfilter()
         x, was_np = _to_device(Obs, torch.complex64)
         if x.ndim == 4:                       # '1DTF' (beamforming_wrapper.py:21-22)

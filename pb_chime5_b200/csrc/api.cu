@@ -46,6 +46,7 @@ size_t wpe_ws_bytes(int Bc, int F, int D, int T, int L);
 size_t istft_ws_bytes(int B, int T, int size);
 size_t enhance_ws_bytes(int B, int F, int D, int T, int K, int L);
 size_t cacgmm_generic_ws_bytes(int B, int F, int D, int K);
+size_t bf_vector_ws_bytes(int B, int F, int D);
 bool cacgmm_fast_path(int D, int K);
 size_t cacgmm_ws_bytes(int B, int F, int D, int K) {
     if (!cacgmm_fast_path(D, K)) return cacgmm_generic_ws_bytes(B, F, D, K);
@@ -68,6 +69,7 @@ int gss_workspace_bytes(int op, int B, int F, int D, int T, int K, int L, size_t
         case GSS_OP_WPE: n = wpe_ws_bytes(B < 4 ? B : 4, F, D, T, L); break;   // utterances are processed in chunks
         case GSS_OP_STFT: n = 256; break;
         case GSS_OP_ISTFT: n = istft_ws_bytes(B, T, F > 1 ? 2 * (F - 1) : 2); break;   // F = size/2 + 1
+        case GSS_OP_BF_VECTOR: n = bf_vector_ws_bytes(B, F, D); break;
         case GSS_OP_ENHANCE: n = enhance_ws_bytes(B, F, D, T, K, L); break;   // L = WPE taps (0: no WPE)
         default: return fail(GSS_ERR_ARG, "gss_workspace_bytes: unknown op %d", op);
     }

@@ -292,194 +292,369 @@ constexpr int BFW_NT = 128;
 struct BfwSmem {
     static __host__ __device__ size_t bytes(int D) {
         const int ld = D + 1;
-        return size_t(4) * D * ld * sizeof(cd) + 64 * sizeof(double) + 16 * sizeof(JacobiRot) + 64 * sizeof(double) + 64;
+        return size_t(4) * D * ld * sizeof(cd) + 64 * sizeof(double) + 16 * sizeof(JacobiRot) + 64 * sizeof(double) + 64
+               + 32 * sizeof(cd);
     }
 };
 
-__global__ void __launch_bounds__(BFW_NT) bf_weights_kernel(const cd* __restrict__ Phi /*(B,F,2,D,D)*/,
+// What to compute per bin: the `get_bf_vector` DSL of pb_bss (beamformer_wrapper.py:108-227),
+// "[rank1_pca+|rank1_gev+]core[+ban]".  The reference's Beamformer block uses only
+// mvdr_souden(+ban) (core.py:263-268) and the wrapper-level gev(+ban) (beamforming_wrapper.py:192-208).
+struct BfProgram {
+    int rank1;          // 0 none, 1 rank1_pca, 2 rank1_gev  (trace-preserving rank-1 model of Phi_X first)
+    int core;           // GSS_BFCORE_*
+    int pca_scaling;    // pca: 0 none, 1 'trace', 2 'eigenvalue'   (beamformer.py:183-201)
+    int chan;           // chN
+    double mu;          // wmwf distortion_weight; < 0: 'frequency_dependent'   (beamformer.py:658-663)
+    double eps;         // mvdr_souden: floor of Re tr(phi) and of the SNR denominators
+};
+
+struct BfwCtx {
+    cd *PX, *PN, *A, *Bm;
+    double* red; JacobiRot* rot; double* lam; int* iscr;
+    int D, ld, tid, lane, warp;
+};
+
+// Bm <- solve(Phi_N, Phi_X) with LAPACK-like partial pivoting; exact-zero pivot -> lstsq fallback
+// (solve.py:108-113): minimum-norm solution through eigh of the Hermitian Phi_N, rcond = eps * D
+__device__ __forceinline__ void bfw_solve_phi(const BfwCtx& c) {
+    const int D = c.D, ld = c.ld, tid = c.tid;
+    cd *PX = c.PX, *PN = c.PN, *A = c.A, *Bm = c.Bm;
+    for (int i = tid; i < D * D; i += BFW_NT) {
+        const int r = i / D, cc = i - r * D;
+        A[r * ld + cc] = PN[r * ld + cc]; Bm[r * ld + cc] = PX[r * ld + cc];
+    }
+    __syncthreads();
+    const bool ok = block_lu_solve(A, ld, Bm, ld, D, D, c.iscr, tid, BFW_NT);
+    if (!ok) {
+        for (int i = tid; i < D * D; i += BFW_NT) {
+            const int r = i / D, cc = i - r * D;
+            A[r * ld + cc] = PN[r * ld + cc];
+        }
+        __syncthreads();
+        cd* V = Bm;
+        block_jacobi_eigh(A, V, D, ld, c.rot, c.red, tid, BFW_NT);
+        if (tid == 0) {
+            double mx = 0.0;
+            for (int i = 0; i < D; ++i) mx = fmax(mx, fabs(A[i * ld + i].x));
+            const double cut = mx * 2.220446049250313e-16 * D;
+            for (int i = 0; i < D; ++i) {
+                const double l = A[i * ld + i].x;
+                c.lam[i] = (fabs(l) > cut) ? 1.0 / l : 0.0;
+            }
+        }
+        __syncthreads();
+        // A <- V diag(lam) V^H  (pseudo inverse), then Bm <- A Phi_X
+        for (int i = tid; i < D * D; i += BFW_NT) {
+            const int r = i / D, cc = i - r * D;
+            cd sacc = cmake(0.0, 0.0);
+            for (int j = 0; j < D; ++j) cfmac(sacc, cscale(V[r * ld + j], c.lam[j]), V[cc * ld + j]);
+            A[r * ld + cc] = sacc;
+        }
+        __syncthreads();
+        for (int i = tid; i < D * D; i += BFW_NT) {
+            const int r = i / D, cc = i - r * D;
+            cd sacc = cmake(0.0, 0.0);
+            for (int j = 0; j < D; ++j) cfma(sacc, A[r * ld + j], PX[j * ld + cc]);
+            Bm[r * ld + cc] = sacc;
+        }
+        __syncthreads();
+    }
+}
+
+// per candidate reference r:  w_r^H Phi_X w_r  and  w_r^H Phi_N w_r   (beamformer.py:535-541); W = Bm
+__device__ __forceinline__ void bfw_snr_terms(const BfwCtx& c, double* __restrict__ numden_bf) {
+    const int D = c.D, ld = c.ld;
+    for (int i = c.tid; i < 2 * D; i += BFW_NT) {
+        const int which = i / D, r = i - which * D;
+        const cd* Pm = which ? c.PN : c.PX;
+        cd sacc = cmake(0.0, 0.0);
+        for (int d = 0; d < D; ++d) {
+            cd u = cmake(0.0, 0.0);
+            for (int e = 0; e < D; ++e) cfma(u, Pm[d * ld + e], c.Bm[e * ld + r]);
+            cfma(sacc, cconj(c.Bm[d * ld + r]), u);
+        }
+        numden_bf[which * D + r] = sacc.x;
+    }
+}
+
+// GEV: Cholesky Phi_N = L L^H ; C = L^-1 Phi_X L^-H ; eigh(C) ; v = L^-H u, canonical phase
+// ((Phi_N v)[0] real, non-negative) -> vv[0..D).  Destroys PX, A, Bm.  false: Phi_N not positive definite.
+__device__ __forceinline__ bool bfw_gev(const BfwCtx& c, cd* __restrict__ vv, int* __restrict__ info, int b, int f) {
+    const int D = c.D, ld = c.ld, tid = c.tid;
+    cd *PX = c.PX, *PN = c.PN, *Bm = c.Bm;
+    cd* Lp = c.A;                                  // packed lower
+    for (int i = tid; i < D * D; i += BFW_NT) {
+        const int r = i / D, cc = i - r * D;
+        if (cc <= r) Lp[tri(r, cc)] = (r == cc) ? cmake(PN[r * ld + r].x, 0.0) : PN[r * ld + cc];
+    }
+    __syncthreads();
+    if (c.warp == 0) {
+        const bool ok = warp_cholesky_packed(Lp, D, c.lane);
+        if (ok) warp_tri_inverse_inplace(Lp, D, c.lane);
+        if (c.lane == 0) c.iscr[1] = ok ? 1 : 0;
+    }
+    __syncthreads();
+    if (!c.iscr[1]) {
+        if (tid == 0 && info) atomicMax(&info[b], GSS_INFO_NOT_POSDEF | (f << 8));
+        return false;
+    }
+    // Bm <- M Phi_X  (M lower triangular packed in Lp)
+    for (int i = tid; i < D * D; i += BFW_NT) {
+        const int r = i / D, cc = i - r * D;
+        cd sacc = cmake(0.0, 0.0);
+        for (int j = 0; j <= r; ++j) cfma(sacc, Lp[tri(r, j)], PX[j * ld + cc]);
+        Bm[r * ld + cc] = sacc;
+    }
+    __syncthreads();
+    // PX <- Bm M^H  (Hermitian C), reuse PX storage after a barrier
+    cd cval[ (32 * 32 + BFW_NT - 1) / BFW_NT ];
+    {
+        int n = 0;
+        for (int i = tid; i < D * D; i += BFW_NT, ++n) {
+            const int r = i / D, cc = i - r * D;
+            cd sacc = cmake(0.0, 0.0);
+            for (int j = 0; j <= cc; ++j) cfmac(sacc, Bm[r * ld + j], Lp[tri(cc, j)]);
+            cval[n] = sacc;
+        }
+    }
+    __syncthreads();
+    {
+        int n = 0;
+        for (int i = tid; i < D * D; i += BFW_NT, ++n) {
+            const int r = i / D, cc = i - r * D;
+            PX[r * ld + cc] = cval[n];
+        }
+    }
+    __syncthreads();
+    // hermitise C exactly
+    for (int i = tid; i < D * D; i += BFW_NT) {
+        const int r = i / D, cc = i - r * D;
+        if (r == cc) Bm[r * ld + cc] = cmake(PX[r * ld + r].x, 0.0);
+        else {
+            const cd u = PX[r * ld + cc], v = PX[cc * ld + r];
+            Bm[r * ld + cc] = cmake(0.5 * (u.x + v.x), 0.5 * (u.y - v.y));
+        }
+    }
+    __syncthreads();
+    cd* V = PX;
+    const int sweeps = block_jacobi_eigh(Bm, V, D, ld, c.rot, c.red, tid, BFW_NT);
+    if (sweeps < 0 && tid == 0 && info) atomicMax(&info[b], GSS_INFO_NO_CONVERGE | (f << 8));
+    if (tid == 0) {
+        int best = 0; double bv = Bm[0].x;
+        for (int i = 1; i < D; ++i) if (Bm[i * ld + i].x > bv) { bv = Bm[i * ld + i].x; best = i; }
+        c.iscr[2] = best;
+    }
+    __syncthreads();
+    const int best = c.iscr[2];
+    // v = M^H u ; then canonical phase: (Phi_N v)[0] real, non-negative
+    if (tid < D) {
+        cd sacc = cmake(0.0, 0.0);
+        for (int j = tid; j < D; ++j) cfma(sacc, cconj(Lp[tri(j, tid)]), V[j * ld + best]);
+        vv[tid] = sacc;
+    }
+    __syncthreads();
+    if (tid == 0) {
+        cd z = cmake(0.0, 0.0);
+        for (int e = 0; e < D; ++e) cfma(z, PN[0 * ld + e], vv[e]);
+        const double az = sqrt(cabs2(z));
+        c.red[0] = az > 0.0 ? z.x / az : 1.0;
+        c.red[1] = az > 0.0 ? -z.y / az : 0.0;        // conj(phase)
+    }
+    __syncthreads();
+    const cd ph = cmake(c.red[0], c.red[1]);
+    __syncthreads();
+    if (tid < D) vv[tid] = cmul(vv[tid], ph);
+    __syncthreads();
+    return true;
+}
+
+// principal eigenvector (largest eigenvalue, np.linalg.eigh semantics up to the phase, which LAPACK
+// leaves unspecified: here the largest component is made real and positive) of the Hermitian PX.
+// Destroys A, Bm; PX stays.  vv[0..D) <- unit vector, returns the eigenvalue.
+__device__ __forceinline__ double bfw_principal(const BfwCtx& c, cd* __restrict__ vv) {
+    const int D = c.D, ld = c.ld, tid = c.tid;
+    for (int i = tid; i < D * D; i += BFW_NT) {
+        const int r = i / D, cc = i - r * D;
+        cd v;
+        if (r == cc) v = cmake(c.PX[r * ld + r].x, 0.0);
+        else if (r > cc) v = c.PX[r * ld + cc];
+        else v = cconj(c.PX[cc * ld + r]);             // eigh reads the lower triangle
+        c.A[r * ld + cc] = v;
+    }
+    __syncthreads();
+    block_jacobi_eigh(c.A, c.Bm, D, ld, c.rot, c.red, tid, BFW_NT);
+    if (tid == 0) {
+        int best = 0; double bv = c.A[0].x;
+        for (int i = 1; i < D; ++i) if (c.A[i * ld + i].x > bv) { bv = c.A[i * ld + i].x; best = i; }
+        int big = 0; double bm = 0.0;
+        for (int i = 0; i < D; ++i) { const double m = cabs2(c.Bm[i * ld + best]); if (m > bm) { bm = m; big = i; } }
+        const cd z = c.Bm[big * ld + best];
+        const double az = sqrt(cabs2(z));
+        c.iscr[2] = best;
+        c.red[0] = az > 0.0 ? z.x / az : 1.0; c.red[1] = az > 0.0 ? -z.y / az : 0.0; c.red[2] = bv;
+    }
+    __syncthreads();
+    const int best = c.iscr[2];
+    const cd ph = cmake(c.red[0], c.red[1]);
+    const double lam = c.red[2];
+    __syncthreads();
+    if (tid < D) vv[tid] = cmul(c.Bm[tid * ld + best], ph);
+    __syncthreads();
+    return lam;
+}
+
+__global__ void __launch_bounds__(BFW_NT) bf_weights_kernel(const cd* __restrict__ PhiX /*(B,F,[2,]D,D)*/,
+                                                            const cd* __restrict__ PhiN,
+                                                            size_t bin_stride /* elements between bins */,
                                                             cd* __restrict__ mat /*(B,F,D,D)*/,
                                                             double* __restrict__ numden /*(B,F,2,D)*/,
-                                                            int* __restrict__ info, int F, int D,
-                                                            int gev, double eps) {
+                                                            int* __restrict__ info, int F, int D, BfProgram prog) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int ld = D + 1;
-    cd* PX = reinterpret_cast<cd*>(smem_raw);         // Phi_X
-    cd* PN = PX + D * ld;                              // Phi_N
-    cd* A = PN + D * ld;                               // work
-    cd* Bm = A + D * ld;                               // work / result
-    double* red = reinterpret_cast<double*>(Bm + D * ld);     // [64]
-    JacobiRot* rot = reinterpret_cast<JacobiRot*>(red + 64);  // [16]
-    double* lam = reinterpret_cast<double*>(rot + 16);        // [64]
-    int* iscr = reinterpret_cast<int*>(lam + 64);             // [16]
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    BfwCtx c;
+    c.PX = reinterpret_cast<cd*>(smem_raw);         // Phi_X
+    c.PN = c.PX + D * ld;                            // Phi_N
+    c.A = c.PN + D * ld;                             // work
+    c.Bm = c.A + D * ld;                             // work / result
+    c.red = reinterpret_cast<double*>(c.Bm + D * ld);           // [64]
+    c.rot = reinterpret_cast<JacobiRot*>(c.red + 64);           // [16]
+    c.lam = reinterpret_cast<double*>(c.rot + 16);              // [64]
+    c.iscr = reinterpret_cast<int*>(c.lam + 64);                // [16]
+    cd* vv = reinterpret_cast<cd*>(c.iscr + 16);                // [32] vector scratch
+    c.D = D; c.ld = ld; c.tid = threadIdx.x; c.lane = c.tid & 31; c.warp = c.tid >> 5;
+    const int tid = c.tid;
+    cd *PX = c.PX, *PN = c.PN, *Bm = c.Bm;
     const size_t bf = blockIdx.x;
     const int b = (int)(bf / F), f = (int)(bf - (size_t)b * F);
-    const cd* gx = Phi + bf * 2 * D * D;
-    const cd* gn = gx + D * D;
+    const cd* gx = PhiX + bf * bin_stride;
+    const cd* gn = PhiN ? PhiN + bf * bin_stride : nullptr;
     for (int i = tid; i < D * D; i += BFW_NT) {
-        const int r = i / D, c = i - r * D;
-        PX[r * ld + c] = gx[i]; PN[r * ld + c] = gn[i];
+        const int r = i / D, cc = i - r * D;
+        PX[r * ld + cc] = gx[i]; PN[r * ld + cc] = gn ? gn[i] : cmake(r == cc ? 1.0 : 0.0, 0.0);
     }
     __syncthreads();
     cd* out = mat + bf * D * D;
+    double* nd = numden + bf * 2 * D;
 
-    if (!gev) {
-        // ---- phi = solve(Phi_N, Phi_X) with LAPACK-like partial pivoting ----
+    // ---- optional rank-1 model of Phi_X: scale a a^H with the trace of Phi_X (beamformer_wrapper.py:11-62) ----
+    if (prog.rank1 != 0) {
+        cd trx = cmake(0.0, 0.0);
+        if (tid < D) trx = PX[tid * ld + tid];
+        const double trr = block_sum(trx.x, c.red, tid, BFW_NT), tri_ = block_sum(trx.y, c.red, tid, BFW_NT);
+        bool ok = true;
+        if (prog.rank1 == 1) bfw_principal(c, vv);
+        else {
+            ok = bfw_gev(c, vv, info, b, f);           // w_gev; ATF estimate a = Phi_N w   (beamformer_wrapper.py:24-44)
+            if (ok) {
+                cd a = cmake(0.0, 0.0);
+                if (tid < D) for (int e = 0; e < D; ++e) cfma(a, PN[tid * ld + e], vv[e]);
+                __syncthreads();
+                if (tid < D) vv[tid] = a;
+                __syncthreads();
+            }
+        }
+        if (!ok) {
+            for (int i = tid; i < D * D; i += BFW_NT) out[i] = cmake(0.0, 0.0);
+            for (int i = tid; i < 2 * D; i += BFW_NT) nd[i] = 0.0;
+            return;
+        }
+        double n2 = tid < D ? cabs2(vv[tid]) : 0.0;
+        n2 = block_sum(n2, c.red, tid, BFW_NT);
+        const cd scale = cmake(trr / n2, tri_ / n2);
         for (int i = tid; i < D * D; i += BFW_NT) {
-            const int r = i / D, c = i - r * D;
-            A[r * ld + c] = PN[r * ld + c]; Bm[r * ld + c] = PX[r * ld + c];
+            const int r = i / D, cc = i - r * D;
+            PX[r * ld + cc] = cmul(scale, cmulc(vv[r], vv[cc]));
         }
         __syncthreads();
-        const bool ok = block_lu_solve(A, ld, Bm, ld, D, D, iscr, tid, BFW_NT);
-        if (!ok) {
-            // ---- lstsq fallback (solve.py:108-113): minimum-norm solution through the
-            //      eigendecomposition of the Hermitian Phi_N, rcond = eps * D (numpy default)
-            for (int i = tid; i < D * D; i += BFW_NT) {
-                const int r = i / D, c = i - r * D;
-                A[r * ld + c] = PN[r * ld + c];
+    }
+
+    if (prog.core == GSS_BFCORE_MVDR_SOUDEN || prog.core == GSS_BFCORE_WMWF) {
+        bfw_solve_phi(c);
+        cd tr = cmake(0.0, 0.0);
+        if (tid < D) tr = Bm[tid * ld + tid];
+        const double trr = block_sum(tr.x, c.red, tid, BFW_NT);
+        cd sc;
+        if (prog.core == GSS_BFCORE_MVDR_SOUDEN) {
+            sc = cmake(1.0 / fmax(trr, prog.eps), 0.0);            // mat = phi / max(Re tr(phi), eps)   (beamformer.py:604-607)
+        } else {
+            const double tri_ = block_sum(tr.y, c.red, tid, BFW_NT);
+            cd den;
+            if (prog.mu < 0.0) {                                   // 'frequency_dependent': sqrt(Phi_X[0,0] * lambda)
+                const cd z = cmul(PX[0], cmake(trr, tri_));
+                const double az = sqrt(cabs2(z));
+                const double re = sqrt(0.5 * (az + z.x)), im = sqrt(fmax(0.5 * (az - z.x), 0.0));
+                den = cmake(re, z.y < 0.0 ? -im : im);             // principal complex square root
+            } else {
+                den = cmake(prog.mu + trr, tri_);                  // distortion_weight + lambda   (beamformer.py:663)
             }
-            __syncthreads();
-            cd* V = Bm;
-            block_jacobi_eigh(A, V, D, ld, rot, red, tid, BFW_NT);
-            if (tid == 0) {
-                double mx = 0.0;
-                for (int i = 0; i < D; ++i) mx = fmax(mx, fabs(A[i * ld + i].x));
-                const double cut = mx * 2.220446049250313e-16 * D;
-                for (int i = 0; i < D; ++i) {
-                    const double l = A[i * ld + i].x;
-                    lam[i] = (fabs(l) > cut) ? 1.0 / l : 0.0;
-                }
-            }
-            __syncthreads();
-            // A <- V diag(lam) V^H  (pseudo inverse), then Bm <- A Phi_X
-            for (int i = tid; i < D * D; i += BFW_NT) {
-                const int r = i / D, c = i - r * D;
-                cd s = cmake(0.0, 0.0);
-                for (int j = 0; j < D; ++j) cfmac(s, cscale(V[r * ld + j], lam[j]), V[c * ld + j]);
-                A[r * ld + c] = s;
-            }
-            __syncthreads();
-            for (int i = tid; i < D * D; i += BFW_NT) {
-                const int r = i / D, c = i - r * D;
-                cd s = cmake(0.0, 0.0);
-                for (int j = 0; j < D; ++j) cfma(s, A[r * ld + j], PX[j * ld + c]);
-                Bm[r * ld + c] = s;
-            }
-            __syncthreads();
+            const double d2 = 1.0 / cabs2(den);
+            sc = cmake(den.x * d2, -den.y * d2);
         }
-        // ---- mat = phi / max(Re tr(phi), eps) ----
-        double tr = 0.0;
-        if (tid < D) tr = Bm[tid * ld + tid].x;
-        tr = block_sum(tr, red, tid, BFW_NT);
-        const double sc = 1.0 / fmax(tr, eps);
         for (int i = tid; i < D * D; i += BFW_NT) {
-            const int r = i / D, c = i - r * D;
-            const cd v = cscale(Bm[r * ld + c], sc);
-            Bm[r * ld + c] = v;
+            const int r = i / D, cc = i - r * D;
+            const cd v = cmul(Bm[r * ld + cc], sc);
+            Bm[r * ld + cc] = v;
             out[i] = v;
         }
         __syncthreads();
-        // ---- per candidate reference r:  w_r^H Phi_X w_r  and  w_r^H Phi_N w_r ----
-        for (int i = tid; i < 2 * D; i += BFW_NT) {
-            const int which = i / D, r = i - which * D;
-            const cd* Pm = which ? PN : PX;
-            cd s = cmake(0.0, 0.0);
-            for (int d = 0; d < D; ++d) {
-                cd u = cmake(0.0, 0.0);
-                for (int e = 0; e < D; ++e) cfma(u, Pm[d * ld + e], Bm[e * ld + r]);
-                cfma(s, cconj(Bm[d * ld + r]), u);
-            }
-            numden[(bf * 2 + which) * D + r] = s.x;
-        }
-    } else {
-        // ---- GEV: Cholesky Phi_N = L L^H ; C = L^-1 Phi_X L^-H ; eigh(C) ; v = L^-H u ----
-        cd* Lp = A;                                    // packed lower
-        for (int i = tid; i < D * D; i += BFW_NT) {
-            const int r = i / D, c = i - r * D;
-            if (c <= r) Lp[tri(r, c)] = (r == c) ? cmake(PN[r * ld + r].x, 0.0) : PN[r * ld + c];
-        }
-        __syncthreads();
-        if (warp == 0) {
-            const bool ok = warp_cholesky_packed(Lp, D, lane);
-            if (ok) warp_tri_inverse_inplace(Lp, D, lane);
-            if (lane == 0) iscr[1] = ok ? 1 : 0;
-        }
-        __syncthreads();
-        if (!iscr[1]) {
-            if (tid == 0 && info) atomicMax(&info[b], GSS_INFO_NOT_POSDEF | (f << 8));
-            for (int i = tid; i < D * D; i += BFW_NT) out[i] = cmake(0.0, 0.0);
-            return;
-        }
-        // Bm <- M Phi_X  (M lower triangular packed in Lp)
-        for (int i = tid; i < D * D; i += BFW_NT) {
-            const int r = i / D, c = i - r * D;
-            cd s = cmake(0.0, 0.0);
-            for (int j = 0; j <= r; ++j) cfma(s, Lp[tri(r, j)], PX[j * ld + c]);
-            Bm[r * ld + c] = s;
-        }
-        __syncthreads();
-        // PX <- Bm M^H  (Hermitian C), reuse PX storage after a barrier
-        cd cval[ (32 * 32 + BFW_NT - 1) / BFW_NT ];
-        {
-            int n = 0;
-            for (int i = tid; i < D * D; i += BFW_NT, ++n) {
-                const int r = i / D, c = i - r * D;
-                cd s = cmake(0.0, 0.0);
-                for (int j = 0; j <= c; ++j) cfmac(s, Bm[r * ld + j], Lp[tri(c, j)]);
-                cval[n] = s;
-            }
-        }
-        __syncthreads();
-        {
-            int n = 0;
-            for (int i = tid; i < D * D; i += BFW_NT, ++n) {
-                const int r = i / D, c = i - r * D;
-                PX[r * ld + c] = cval[n];
-            }
-        }
-        __syncthreads();
-        // hermitise C exactly
-        for (int i = tid; i < D * D; i += BFW_NT) {
-            const int r = i / D, c = i - r * D;
-            if (r == c) Bm[r * ld + c] = cmake(PX[r * ld + r].x, 0.0);
-            else {
-                const cd u = PX[r * ld + c], v = PX[c * ld + r];
-                Bm[r * ld + c] = cmake(0.5 * (u.x + v.x), 0.5 * (u.y - v.y));
-            }
-        }
-        __syncthreads();
-        cd* V = PX;
-        const int sweeps = block_jacobi_eigh(Bm, V, D, ld, rot, red, tid, BFW_NT);
-        if (sweeps < 0 && tid == 0 && info) atomicMax(&info[b], GSS_INFO_NO_CONVERGE | (f << 8));
-        if (tid == 0) {
-            int best = 0; double bv = Bm[0].x;
-            for (int i = 1; i < D; ++i) if (Bm[i * ld + i].x > bv) { bv = Bm[i * ld + i].x; best = i; }
-            iscr[2] = best;
-        }
-        __syncthreads();
-        const int best = iscr[2];
-        // v = M^H u ; then canonical phase: (Phi_N v)[0] real, non-negative
-        cd* vv = reinterpret_cast<cd*>(lam);           // needs D*16 bytes <= 64*8
-        if (tid < D) {
-            cd s = cmake(0.0, 0.0);
-            for (int j = tid; j < D; ++j) cfma(s, cconj(Lp[tri(j, tid)]), V[j * ld + best]);
-            vv[tid] = s;
-        }
-        __syncthreads();
-        if (tid == 0) {
-            cd z = cmake(0.0, 0.0);
-            for (int e = 0; e < D; ++e) cfma(z, PN[0 * ld + e], vv[e]);
-            const double az = sqrt(cabs2(z));
-            red[0] = az > 0.0 ? z.x / az : 1.0;
-            red[1] = az > 0.0 ? -z.y / az : 0.0;        // conj(phase)
-        }
-        __syncthreads();
-        const cd ph = cmake(red[0], red[1]);
-        for (int i = tid; i < D * D; i += BFW_NT) {
-            const int r = i / D, c = i - r * D;
-            out[i] = (c == 0) ? cmul(vv[r], ph) : cmake(0.0, 0.0);
-        }
+        bfw_snr_terms(c, nd);
+        return;
     }
+
+    // ---- cores that yield one vector: it goes to column 0 of `mat` ----
+    bool ok = true;
+    if (prog.core == GSS_BFCORE_GEV) {
+        ok = bfw_gev(c, vv, info, b, f);
+    } else if (prog.core == GSS_BFCORE_PCA) {
+        const double lam = bfw_principal(c, vv);
+        if (prog.pca_scaling != 0) {                               // beamformer.py:183-201 (the eigenvector has unit norm)
+            double trx = tid < D ? PX[tid * ld + tid].x : 0.0;
+            trx = block_sum(trx, c.red, tid, BFW_NT);
+            const double s = prog.pca_scaling == 1 ? sqrt(trx) : lam;
+            if (tid < D) vv[tid] = cscale(vv[tid], s);
+            __syncthreads();
+        }
+    } else if (prog.core == GSS_BFCORE_PCA_MVDR || prog.core == GSS_BFCORE_GEVATF_MVDR) {
+        // ATF estimate, then Phi_N^-1 a / (a^H Phi_N^-1 a) with Phi_N hermitised (beamformer.py:205-235)
+        if (prog.core == GSS_BFCORE_PCA_MVDR) bfw_principal(c, vv);
+        else {
+            ok = bfw_gev(c, vv, info, b, f);
+            if (ok) {
+                cd a = cmake(0.0, 0.0);
+                if (tid < D) for (int e = 0; e < D; ++e) cfma(a, PN[tid * ld + e], vv[e]);
+                __syncthreads();
+                if (tid < D) vv[tid] = a;
+                __syncthreads();
+            }
+        }
+        if (ok) {
+            for (int i = tid; i < D * D; i += BFW_NT) {
+                const int r = i / D, cc = i - r * D;
+                const cd u = PN[r * ld + cc], v = PN[cc * ld + r];
+                c.A[r * ld + cc] = cmake(0.5 * (u.x + v.x), 0.5 * (u.y - v.y));
+            }
+            if (tid < D) Bm[tid * ld] = vv[tid];                   // one right-hand side in column 0
+            __syncthreads();
+            block_lu_solve(c.A, ld, Bm, ld, D, 1, c.iscr, tid, BFW_NT);
+            cd den = cmake(0.0, 0.0);
+            if (tid < D) den = ccmul(vv[tid], Bm[tid * ld]);
+            const double dr = block_sum(den.x, c.red, tid, BFW_NT), di = block_sum(den.y, c.red, tid, BFW_NT);
+            const double d2 = 1.0 / (dr * dr + di * di);
+            const cd inv = cmake(dr * d2, -di * d2);
+            __syncthreads();
+            if (tid < D) vv[tid] = cmul(Bm[tid * ld], inv);
+            __syncthreads();
+        }
+    } else {                                                       // chN
+        if (tid < D) vv[tid] = cmake(tid == prog.chan ? 1.0 : 0.0, 0.0);
+        __syncthreads();
+    }
+    for (int i = tid; i < D * D; i += BFW_NT) {
+        const int r = i / D, cc = i - r * D;
+        out[i] = (ok && cc == 0) ? vv[r] : cmake(0.0, 0.0);
+    }
+    for (int i = tid; i < 2 * D; i += BFW_NT) nd[i] = 0.0;
 }
 
 // One CTA per utterance: SNR_r = sum_f num / max(sum_f den, eps); argmax (first max wins, np.argmax).
@@ -609,10 +784,22 @@ static int beamform_impl(const float2* Y, const WeightSrc& src, float2* Xhat, in
         GSS_LAUNCH_CHECK("bf_simple_kernel");
         return GSS_OK;
     }
-    const bool gev = bf_type == GSS_BF_GEV_BAN || bf_type == GSS_BF_GEV;
-    const bool mvdr = bf_type == GSS_BF_MVDR_SOUDEN_BAN || bf_type == GSS_BF_MVDR_SOUDEN;
-    GSS_REQUIRE(gev || mvdr, GSS_ERR_UNSUPPORTED, "beamformer type %d (core.py:263-264)", bf_type);
-    const bool ban = bf_type == GSS_BF_MVDR_SOUDEN_BAN || bf_type == GSS_BF_GEV_BAN;
+    BfProgram prog{0, GSS_BFCORE_MVDR_SOUDEN, 0, 0, 1.0, 1e-10};      // eps = 1e-10: beamforming_wrapper.py:75-83
+    bool ban;
+    if (bf_type & GSS_BF_PROGRAM_FLAG) {
+        // a `get_bf_vector` program (beamformer_wrapper.py:108-227) with the reference's default keyword arguments
+        prog.core = bf_type & 0xF; prog.rank1 = (bf_type >> 4) & 3; ban = (bf_type >> 6) & 1;
+        prog.chan = bf_arg; prog.eps = GSS_F64_TINY;
+        GSS_REQUIRE(prog.core <= GSS_BFCORE_CH && prog.rank1 <= 2, GSS_ERR_UNSUPPORTED, "beamformer program 0x%x", bf_type);
+        if (prog.core == GSS_BFCORE_CH) GSS_REQUIRE(bf_arg >= 0 && bf_arg < D, GSS_ERR_ARG, "channel %d out of range for D=%d", bf_arg, D);
+    } else {
+        const bool gev = bf_type == GSS_BF_GEV_BAN || bf_type == GSS_BF_GEV;
+        const bool mvdr = bf_type == GSS_BF_MVDR_SOUDEN_BAN || bf_type == GSS_BF_MVDR_SOUDEN;
+        GSS_REQUIRE(gev || mvdr, GSS_ERR_UNSUPPORTED, "beamformer type %d (core.py:263-264)", bf_type);
+        ban = bf_type == GSS_BF_MVDR_SOUDEN_BAN || bf_type == GSS_BF_GEV_BAN;
+        if (gev) prog.core = GSS_BFCORE_GEV;
+    }
+    const bool matrix_core = prog.core == GSS_BFCORE_MVDR_SOUDEN || prog.core == GSS_BFCORE_WMWF;
     GSS_REQUIRE(D < 30, GSS_ERR_ARG, "D=%d: beamformer needs D < 30 (beamforming_wrapper.py:44)", D);
     cd *Phi, *mat; double* numden; int* ref;
     const size_t need = bf_ws_layout(B, F, D, &Phi, &mat, &numden, &ref, ws);
@@ -621,22 +808,103 @@ static int beamform_impl(const float2* Y, const WeightSrc& src, float2* Xhat, in
     if (rc) return rc;
     const size_t smem = BfwSmem::bytes(D);
     GSS_CUDA(cudaFuncSetAttribute(bf_weights_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    bf_weights_kernel<<<B * F, BFW_NT, smem, st>>>(Phi, mat, numden, info, F, D, gev ? 1 : 0, 1e-10);
+    bf_weights_kernel<<<B * F, BFW_NT, smem, st>>>(Phi, Phi + (size_t)D * D, (size_t)2 * D * D, mat, numden, info, F, D, prog);
     GSS_LAUNCH_CHECK("bf_weights_kernel");
-    if (mvdr) {
-        bf_refchan_kernel<<<B, 256, 0, st>>>(numden, ref, info, F, D, 1e-10);
+    if (matrix_core) {
+        bf_refchan_kernel<<<B, 256, 0, st>>>(numden, ref, info, F, D, prog.eps);
         GSS_LAUNCH_CHECK("bf_refchan_kernel");
         if (ref_out) GSS_CUDA(cudaMemcpyAsync(ref_out, ref, sizeof(int) * B, cudaMemcpyDeviceToDevice, st));
     }
     bf_apply_kernel<<<B * F, 256, 0, st>>>(Y, Phi, mat, ref, src, Xhat, reinterpret_cast<cd*>(weights_out),
-                                           F, D, T, gev ? 0 : -1, ban ? 1 : 0, postfilter);
+                                           F, D, T, matrix_core ? -1 : 0, ban ? 1 : 0, postfilter);
     GSS_LAUNCH_CHECK("bf_apply_kernel");
     return GSS_OK;
+}
+
+// column `ref` of mat (or a fixed column), optional blind analytic normalisation -> w (B,F,D)
+__global__ void bf_vector_finish_kernel(const cd* __restrict__ mat, const cd* __restrict__ PhiN, const int* __restrict__ ref,
+                                        cd* __restrict__ w_out, int F, int D, int fixed_col, int ban) {
+    __shared__ cd w[32];
+    __shared__ cd pw[32];
+    __shared__ double scal;
+    const int tid = threadIdx.x;
+    const size_t bf = blockIdx.x;
+    const int b = (int)(bf / F);
+    const int col = fixed_col >= 0 ? fixed_col : ref[b];
+    if (tid < D) w[tid] = mat[bf * D * D + (size_t)tid * D + col];
+    __syncthreads();
+    if (ban) {
+        const cd* PN = PhiN + bf * D * D;
+        if (tid < D) {
+            cd s = cmake(0.0, 0.0);
+            for (int e = 0; e < D; ++e) cfma(s, PN[tid * D + e], w[e]);
+            pw[tid] = s;
+        }
+        __syncthreads();
+        if (tid == 0) {
+            double nom = 0.0; cd den = cmake(0.0, 0.0);
+            for (int d = 0; d < D; ++d) { nom += cabs2(pw[d]); cfma(den, cconj(w[d]), pw[d]); }
+            const double ad = sqrt(cabs2(den));
+            scal = ad != 0.0 ? sqrt(nom) / ad : 0.0;       // beamformer.py:406-417
+        }
+        __syncthreads();
+        if (tid < D) w[tid] = cscale(w[tid], scal);
+    }
+    if (tid < D) w_out[bf * D + tid] = w[tid];
+}
+
+size_t bf_vector_ws_bytes(int B, int F, int D) {
+    return align_up((size_t)B * F * D * D * sizeof(cd)) + align_up((size_t)B * F * 2 * D * sizeof(double)) + align_up((size_t)B * sizeof(int));
 }
 
 }  // namespace gss
 
 extern "C" {
+
+int gss_bf_vector_c128(const double* Phi_X, const double* Phi_N, double* w_out,
+                       int core, int rank1, int ban, int ref_channel, double distortion_weight,
+                       int pca_scaling, int channel, int B, int F, int D,
+                       int* ref_channel_out, int* info, void* ws, size_t ws_bytes, void* stream) {
+    using namespace gss;
+    GSS_REQUIRE(Phi_X && w_out, GSS_ERR_ARG, "gss_bf_vector_c128: null pointer");
+    GSS_REQUIRE(B >= 0 && F >= 0 && D > 0, GSS_ERR_ARG, "gss_bf_vector_c128: bad dims");
+    GSS_REQUIRE(D <= 32, GSS_ERR_UNSUPPORTED, "gss_bf_vector_c128: D=%d > 32 not built", D);
+    GSS_REQUIRE(core >= GSS_BFCORE_MVDR_SOUDEN && core <= GSS_BFCORE_CH, GSS_ERR_ARG, "gss_bf_vector_c128: core %d", core);
+    GSS_REQUIRE(rank1 >= 0 && rank1 <= 2 && pca_scaling >= 0 && pca_scaling <= 2, GSS_ERR_ARG, "gss_bf_vector_c128: rank1 / scaling");
+    const bool needs_noise = ban || rank1 == 2 || (core != GSS_BFCORE_PCA && core != GSS_BFCORE_CH);
+    GSS_REQUIRE(Phi_N || !needs_noise, GSS_ERR_ARG, "gss_bf_vector_c128: this beamformer needs the noise PSD matrix");
+    if (core == GSS_BFCORE_CH) GSS_REQUIRE(channel >= 0 && channel < D, GSS_ERR_ARG, "channel %d out of range for D=%d", channel, D);
+    GSS_REQUIRE(ref_channel < D, GSS_ERR_ARG, "ref_channel %d out of range for D=%d", ref_channel, D);
+    if (B == 0 || F == 0) return GSS_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    GSS_REQUIRE(ws && ws_bytes >= bf_vector_ws_bytes(B, F, D), GSS_ERR_WORKSPACE, "gss_bf_vector_c128: workspace %zu < %zu",
+                ws_bytes, bf_vector_ws_bytes(B, F, D));
+    Arena a(ws, ws_bytes);
+    cd* mat = a.take<cd>((size_t)B * F * D * D);
+    double* numden = a.take<double>((size_t)B * F * 2 * D);
+    int* ref = a.take<int>(B);
+    // reference defaults: eps = smallest positive float64 (beamformer.py:602-603, 524-526)
+    BfProgram prog{rank1, core, pca_scaling, channel, distortion_weight, GSS_F64_TINY};
+    const size_t smem = BfwSmem::bytes(D);
+    GSS_CUDA(cudaFuncSetAttribute(bf_weights_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    bf_weights_kernel<<<B * F, BFW_NT, smem, st>>>(reinterpret_cast<const cd*>(Phi_X), reinterpret_cast<const cd*>(Phi_N),
+                                                   (size_t)D * D, mat, numden, info, F, D, prog);
+    GSS_LAUNCH_CHECK("bf_weights_kernel");
+    const bool matrix_core = core == GSS_BFCORE_MVDR_SOUDEN || core == GSS_BFCORE_WMWF;
+    int fixed_col = 0;
+    if (matrix_core) {
+        fixed_col = ref_channel;                       // -1: SNR-optimal reference channel over all bins of the utterance
+        if (ref_channel < 0) {
+            bf_refchan_kernel<<<B, 256, 0, st>>>(numden, ref, info, F, D, GSS_F64_TINY);
+            GSS_LAUNCH_CHECK("bf_refchan_kernel");
+            if (ref_channel_out) GSS_CUDA(cudaMemcpyAsync(ref_channel_out, ref, sizeof(int) * B, cudaMemcpyDeviceToDevice, st));
+        }
+    }
+    bf_vector_finish_kernel<<<B * F, 32, 0, st>>>(mat, reinterpret_cast<const cd*>(Phi_N), ref, reinterpret_cast<cd*>(w_out),
+                                                  F, D, fixed_col, ban ? 1 : 0);
+    GSS_LAUNCH_CHECK("bf_vector_finish_kernel");
+    return GSS_OK;
+}
 
 int gss_weighted_cov_c64(const gss_c64* Y, const float* w, gss_c64* Phi, int normalize_mode,
                          int B, int F, int D, int T, int K, const int* T_per_utt, void* ws, size_t ws_bytes, void* stream) {

@@ -66,8 +66,11 @@ bool cacgmm_fast_path(int D, int K);
 
 // E-phase sub-blocking of the packed lower triangle: SB x SB blocks so that only
 // 2*SB complex values of the frame are live in registers at a time.
+#ifndef GSS_SB_LARGE
+#define GSS_SB_LARGE 6          // developer knob: sub-block edge for DP % 6 == 0 (A/B builds)
+#endif
 __host__ __device__ constexpr int sub_block(int DP) {
-    return DP < 12 ? DP : (DP % 6 == 0 ? 6 : 4);
+    return DP < 12 ? DP : (DP % GSS_SB_LARGE == 0 ? GSS_SB_LARGE : 4);
 }
 template <int DP, int K, int NT>
 struct CacgmmCfg {
@@ -80,6 +83,7 @@ struct CacgmmCfg {
     static constexpr int NW = NT / 32;
     static constexpr int JLD = DP + 1;                    // leading dim of Jacobi matrices
     static constexpr int TE = NT;                         // frames per E step = super tile (complex64 tile)
+    static constexpr bool SPLIT_E = DP >= 12 && (NT / 2) % 32 == 0;      // E phase with two frames per thread
     static constexpr int SB = sub_block(DP);
     static constexpr int NS = DP / SB;
     static constexpr int NSB = NS * (NS + 1) / 2;
@@ -141,8 +145,12 @@ __device__ __forceinline__ void quad_subblock(const float2* __restrict__ yrow, c
 #pragma unroll
             for (int k = 0; k < K; ++k) {
                 const cd bk = b[k];
+#ifdef GSS_E_ONEACC      // developer knob: one accumulator chain per class (10 registers less)
+                qa[k] = fma(pim[c], bk.y, fma(pre[c], bk.x, qa[k]));
+#else
                 qa[k] = fma(pre[c], bk.x, qa[k]);
                 qb[k] = fma(pim[c], bk.y, qb[k]);
+#endif
             }
         }
     }
@@ -162,6 +170,80 @@ template <int DP, int K, int NSB>
 struct QuadAll<DP, K, NSB, NSB> {
     static __device__ __forceinline__ void run(const float2*, const cd*, double (&)[K], double (&)[K]) {}
 };
+
+// ---- E phase, two frames per thread (DP >= 12) -------------------------------------------------
+// The thread-owns-a-frame E phase reads every B'_k entry once per warp as a warp-uniform LDS.128,
+// which costs two shared-memory wavefronts: 10 wavefronts per pair against 7 SM cycles of FP64 work
+// -- the phase ran at 91 % shared-memory pipe utilisation (ncu, profiles/r2_em_kernel_v7_*), not at
+// the FP64 roof.  Here a thread accumulates TWO frames (tid mod NT/2 and that + NT/2) per B' load,
+// and the two halves of the block (warp-uniform) split the sub-blocks of the packed triangle between
+// them; the partial sums of the frame a thread does not own travel through the weight tile.
+// Rolled loops over SB2 x SB2 sub-blocks (runtime sub-block coordinates): ~0.6 k instructions
+// instead of the 7 k of the fully unrolled single-frame form.
+__host__ __device__ constexpr int sub_block2(int DP) { return DP % 3 == 0 ? 3 : (DP % 4 == 0 ? 4 : 2); }
+
+template <int DP>
+__device__ __forceinline__ int ypos_rt(int d) { return (d & 1) * (DP / 2) + (d >> 1); }
+
+template <int DP, int K, int SB, bool DIAG>
+__device__ __forceinline__ void quad2_subblock(const float2* __restrict__ yA, const float2* __restrict__ yB,
+                                               const cd* __restrict__ Bsm, const int I, const int J,
+                                               double (&pA)[K], double (&pB)[K]) {
+    double rA[SB], iA[SB], rB[SB], iB[SB], crA[SB], ciA[SB], crB[SB], ciB[SB];
+#pragma unroll
+    for (int a = 0; a < SB; ++a) {
+        const int pos = ypos_rt<DP>(I * SB + a);
+        const float2 u = yA[pos], v = yB[pos];
+        rA[a] = (double)u.x; iA[a] = (double)u.y; rB[a] = (double)v.x; iB[a] = (double)v.y;
+    }
+#pragma unroll
+    for (int c = 0; c < SB; ++c) {
+        if (DIAG) { crA[c] = rA[c]; ciA[c] = iA[c]; crB[c] = rB[c]; ciB[c] = iB[c]; }
+        else {
+            const int pos = ypos_rt<DP>(J * SB + c);
+            const float2 u = yA[pos], v = yB[pos];
+            crA[c] = (double)u.x; ciA[c] = (double)u.y; crB[c] = (double)v.x; ciB[c] = (double)v.y;
+        }
+    }
+#pragma unroll
+    for (int a = 0; a < SB; ++a) {
+        const int row = I * SB + a;
+        const cd* __restrict__ brow = Bsm + (size_t)(row * (row + 1) / 2 + J * SB) * K;
+#pragma unroll
+        for (int c = 0; c < SB; ++c) {
+            if (DIAG && c > a) continue;
+            const double preA = fma(rA[a], crA[c], iA[a] * ciA[c]);
+            const double pimA = fma(iA[a], crA[c], -(rA[a] * ciA[c]));
+            const double preB = fma(rB[a], crB[c], iB[a] * ciB[c]);
+            const double pimB = fma(iB[a], crB[c], -(rB[a] * ciB[c]));
+            const cd* __restrict__ b = brow + c * K;
+#pragma unroll
+            for (int k = 0; k < K; ++k) {
+                const cd bk = b[k];
+                pA[k] = fma(pimA, bk.y, fma(preA, bk.x, pA[k]));
+                pB[k] = fma(pimB, bk.y, fma(preB, bk.x, pB[k]));
+            }
+        }
+    }
+}
+
+// sub-blocks of half `half` (0 / 1): every second diagonal block and every second off-diagonal block
+template <int DP, int K>
+__device__ __forceinline__ void quad2_half(const float2* __restrict__ yA, const float2* __restrict__ yB,
+                                           const cd* __restrict__ Bsm, const int half,
+                                           double (&pA)[K], double (&pB)[K]) {
+    constexpr int SB = sub_block2(DP), NS = DP / SB;
+#pragma unroll 1
+    for (int I = half; I < NS; I += 2) quad2_subblock<DP, K, SB, true>(yA, yB, Bsm, I, I, pA, pB);
+    int I = 1, J = 0;
+    if (half) { ++J; if (J == I) { ++I; J = 0; } }
+#pragma unroll 1
+    while (I < NS) {
+        quad2_subblock<DP, K, SB, false>(yA, yB, Bsm, I, J, pA, pB);
+#pragma unroll
+        for (int s2 = 0; s2 < 2; ++s2) { ++J; if (J == I) { ++I; J = 0; } }
+    }
+}
 
 // Symmetric sweep operator on the packed lower triangle of K class matrices at once (in place:
 // -Phi^-1; pivots = squared Cholesky pivots).  The chunk of a thread (up to CH consecutive columns of
@@ -352,7 +434,26 @@ __global__ void __launch_bounds__(NT, MINB) cacgmm_em_kernel(const CacgmmParams 
 #pragma unroll
                 for (int k = 0; k < K; ++k) { qa[k] = 0.0; qb[k] = 0.0; }
                 const float2* yrow = yf + tid * C::YLD;
-                if (pass > 0) QuadAll<DP, K, 0, C::NSB>::run(yrow, Bsm, qa, qb);
+                if constexpr (C::SPLIT_E) {
+                    if (pass > 0) {
+                        // two frames per thread, the halves of the block split the sub-blocks (see quad2_half)
+                        const int half = tid >= NT / 2 ? 1 : 0, lt = tid - half * (NT / 2);
+                        double pB[K];
+#pragma unroll
+                        for (int k = 0; k < K; ++k) pB[k] = 0.0;
+                        quad2_half<DP, K>(yf + lt * C::YLD, yf + (lt + NT / 2) * C::YLD, Bsm, half, qa, pB);
+                        // qa: frame lt, pB: frame lt + NT/2.  Hand the partial sums of the frame this thread
+                        // does not own to its owner (thread = frame) through the weight tile.
+                        const int other = half ? lt : lt + NT / 2;
+#pragma unroll
+                        for (int k = 0; k < K; ++k) wsm[other * C::KP + k] = half ? qa[k] : pB[k];
+                        __syncthreads();
+#pragma unroll
+                        for (int k = 0; k < K; ++k) qa[k] = (half ? pB[k] : qa[k]) + wsm[tid * C::KP + k];
+                    }
+                } else {
+                    if (pass > 0) QuadAll<DP, K, 0, C::NSB>::run(yrow, Bsm, qa, qb);
+                }
                 const int t = s0 + tid;
                 if (t < s1) {
                     double n2 = 0.0;

@@ -193,7 +193,11 @@ def cacgmm(Y, activity, iterations, iterations_post=1, affiliation_eps=1e-10,
 
 def _bf_call(Y, fn, lead_args, bf, bf_arg, postfilter, K=None, return_aux=False, frames=None, info=None):
     B, F, D, T = Y.shape
-    if bf not in _lib.BF_TYPES:
+    if isinstance(bf, int) and bf & 0x100:
+        bf_code = bf                                   # a get_bf_vector program (GSS_BF_PROGRAM, include/gss.h)
+    elif bf in _lib.BF_TYPES:
+        bf_code = _lib.BF_TYPES[bf]
+    else:
         raise NotImplementedError(bf)
     if postfilter not in _lib.POSTFILTERS:
         raise NotImplementedError(postfilter)
@@ -206,7 +210,7 @@ def _bf_call(Y, fn, lead_args, bf, bf_arg, postfilter, K=None, return_aux=False,
     n = _lib.workspace_bytes(_lib.OP_BEAMFORM, B, F, D, T, 2, 0)
     ws = workspace(n, Y.device)
     dims = (B, F, D, T) if K is None else (B, F, D, T, K)
-    _lib.check(fn(_ptr(Y), *lead_args, _ptr(X), _lib.BF_TYPES[bf], int(bf_arg), _lib.POSTFILTERS[postfilter],
+    _lib.check(fn(_ptr(Y), *lead_args, _ptr(X), bf_code, int(bf_arg), _lib.POSTFILTERS[postfilter],
                   *dims, _ptr(_tper(frames, B, Y.device)), _ptr(ref), _ptr(wts), _ptr(info), _ptr(ws), ws.numel(),
                   _stream()))
     if own_info:

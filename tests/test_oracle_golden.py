@@ -139,3 +139,30 @@ def test_wpe_normal_equations():
     # tap matrix layout: row k*D+d at frame t is Y[d, t-delay-k]
     assert np.array_equal(Yt[0, 1 * 4 + 2, 10], Y[0, 2, 10 - 2 - 1])
     assert np.all(Yt[:, :, 0] == 0)
+
+
+def test_bf_vector_dsl_oracle_matches_reference_fixture(golden_dir):
+    """get_bf_vector DSL (beamformer_wrapper.py:108-227): the oracle restatement against vectors the
+    unmodified reference produced (oracle/make_golden.py) -- same LAPACK calls, so bit for bit."""
+    g = np.load(golden_dir / 'bf_dsl_d8.npz')
+    cx, cn = g['cov_x'], g['cov_n']
+    for key in g.files:
+        if key in ('cov_x', 'cov_n'):
+            continue
+        kw = {}
+        name = key.replace('__', '+')
+        if key == 'wmwf_mu0p25':
+            name, kw = 'wmwf', dict(distortion_weight=0.25)
+        elif key == 'wmwf_fd':
+            name, kw = 'wmwf', dict(distortion_weight='frequency_dependent')
+        elif key in ('pca_trace', 'pca_eigenvalue'):
+            name, kw = 'pca', dict(scaling=key[4:])
+        w = oracle.get_bf_vector(name, cx, cn, **kw)
+        assert w.shape == g[key].shape and np.abs(w - g[key]).max() <= 1e-12 * np.abs(g[key]).max(), key
+    with pytest.raises(ValueError):
+        oracle.get_bf_vector('music', cx, cn)
+    # 'pca+mvdr' / 'scaled_gev_atf+mvdr' go through get_mvdr_vector, which does not run under numpy >= 2
+    # in the reference (SURVEY appendix B): restated from the formula, distortionless by construction
+    for name, atf in (('pca+mvdr', oracle.pca_vector(cx)), ('scaled_gev_atf+mvdr', oracle.gev_atf_vector(cx, cn))):
+        w = oracle.get_bf_vector(name, cx, cn)
+        assert np.abs(np.einsum('fd,fd->f', w.conj(), atf) - 1).max() < 1e-10
