@@ -214,7 +214,7 @@ def measure_fp64_peak(torch, _lib):
     scratch = torch.empty(int(dl.gss_debug_fp64_peak_scratch_bytes()), dtype=torch.uint8, device='cuda')
     stream = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
     out = {}
-    for name, mode in (('dfma', 0), ('dmma', 1)):
+    for name, mode in (('dfma', 0), ('dmma', 1), ('dfma_3operand', 2), ('dfma_3operand_16warps', 3)):
         fl = ctypes.c_double(0.0)
         _lib.check(dl.gss_debug_fp64_peak(mode, 2000, ctypes.c_void_p(scratch.data_ptr()), ctypes.byref(fl), stream), dl)
         best = 0.0
@@ -723,6 +723,8 @@ def run_gpu(args):
                               'executed_tflops': exe_flops / (em_ms * 1e-3) / 1e12,
                               'peak_tflops_measured': (fp64_peak or {}).get('dfma'),
                               'peak_tflops_measured_dmma': (fp64_peak or {}).get('dmma'),
+                              'peak_tflops_measured_dfma_3_register_operands': (fp64_peak or {}).get('dfma_3operand'),
+                              'peak_tflops_measured_dfma_3_register_operands_16_warps_per_sm': (fp64_peak or {}).get('dfma_3operand_16warps'),
                               'frac_of_measured_peak': (exe_flops / (em_ms * 1e-3) / 1e12 / fp64_peak['dfma'])
                               if fp64_peak and fp64_peak.get('dfma') else None,
                               'peak_source': 'measured in this run: gss_debug_fp64_peak (csrc/probe.cu, libgss_dev.so), '

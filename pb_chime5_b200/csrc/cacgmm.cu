@@ -83,7 +83,10 @@ struct CacgmmCfg {
     static constexpr int NW = NT / 32;
     static constexpr int JLD = DP + 1;                    // leading dim of Jacobi matrices
     static constexpr int TE = NT;                         // frames per E step = super tile (complex64 tile)
-    static constexpr bool SPLIT_E = DP >= 12 && (NT / 2) % 32 == 0;      // E phase with two frames per thread
+#ifndef GSS_SPLIT_E
+#define GSS_SPLIT_E 0           // measured alternative, see quad2_half: 44.8 vs 44.0 ms per utterance at cfg2
+#endif
+    static constexpr bool SPLIT_E = GSS_SPLIT_E && DP >= 12 && (NT / 2) % 32 == 0;   // E phase with two frames per thread
     static constexpr int SB = sub_block(DP);
     static constexpr int NS = DP / SB;
     static constexpr int NSB = NS * (NS + 1) / 2;
@@ -171,15 +174,18 @@ struct QuadAll<DP, K, NSB, NSB> {
     static __device__ __forceinline__ void run(const float2*, const cd*, double (&)[K], double (&)[K]) {}
 };
 
-// ---- E phase, two frames per thread (DP >= 12) -------------------------------------------------
+// ---- E phase, two frames per thread (DP >= 12): MEASURED ALTERNATIVE, off by default (-DGSS_SPLIT_E=1)
 // The thread-owns-a-frame E phase reads every B'_k entry once per warp as a warp-uniform LDS.128,
 // which costs two shared-memory wavefronts: 10 wavefronts per pair against 7 SM cycles of FP64 work
-// -- the phase ran at 91 % shared-memory pipe utilisation (ncu, profiles/r2_em_kernel_v7_*), not at
-// the FP64 roof.  Here a thread accumulates TWO frames (tid mod NT/2 and that + NT/2) per B' load,
-// and the two halves of the block (warp-uniform) split the sub-blocks of the packed triangle between
-// them; the partial sums of the frame a thread does not own travel through the weight tile.
-// Rolled loops over SB2 x SB2 sub-blocks (runtime sub-block coordinates): ~0.6 k instructions
-// instead of the 7 k of the fully unrolled single-frame form.
+// -- the phase runs at 91 % shared-memory pipe utilisation (ncu, profiles/r2_em_kernel_v7_*).  Here a
+// thread accumulates TWO frames (tid mod NT/2 and that + NT/2) per B' load, and the two halves of the
+// block (warp-uniform) split the sub-blocks of the packed triangle between them; the partial sums of
+// the frame a thread does not own travel through the weight tile.  Rolled loops over SB2 x SB2
+// sub-blocks (runtime sub-block coordinates): ~0.6 k instructions instead of 7 k.
+// Result (B200, cfg2, profiles/r2_em_kernel_v8_split_e_*): shared-memory wavefronts of the kernel -23 %,
+// E phase -8 %, but the extra barrier of the exchange and the per-sub-block conversions give it back:
+// 44.8 ms per utterance against 44.0 for the unrolled form.  The E phase is then throttled by the FP64
+// pipe itself (math_pipe_throttle is the top stall), which is where it should be.
 __host__ __device__ constexpr int sub_block2(int DP) { return DP % 3 == 0 ? 3 : (DP % 4 == 0 ? 4 : 2); }
 
 template <int DP>

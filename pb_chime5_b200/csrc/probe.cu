@@ -20,6 +20,34 @@ __global__ void __launch_bounds__(512) fp64_dfma_probe_kernel(double* out, int i
     out[(size_t)blockIdx.x * blockDim.x + threadIdx.x] = s;
 }
 
+// mode 2: the operand pattern of the EM kernel's inner loops -- every DFMA reads three DISTINCT
+// registers (accumulator, a per-frame product, a per-class coefficient), 40 independent chains
+__global__ void __launch_bounds__(512) fp64_dfma3_probe_kernel(double* out, int iters) {
+    double acc[8][5], p[8], w[5];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        p[i] = 1.0 + threadIdx.x * 1e-9 + i * 1e-3;
+#pragma unroll
+        for (int k = 0; k < 5; ++k) acc[i][k] = i + k;
+    }
+#pragma unroll
+    for (int k = 0; k < 5; ++k) w[k] = 1e-9 * (k + 1);
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int k = 0; k < 5; ++k)
+#pragma unroll
+            for (int i = 0; i < 8; ++i) acc[i][k] = fma(w[k], p[i], acc[i][k]);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) p[i] += 1e-12;          // 8 DADD per 40 DFMA keep the products live
+    }
+    double s = 0;
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int k = 0; k < 5; ++k) s += acc[i][k];
+    out[(size_t)blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+
 __global__ void __launch_bounds__(512) fp64_dmma_probe_kernel(double* out, int iters) {
     double c[8][2];
 #pragma unroll
@@ -45,14 +73,17 @@ extern "C" size_t gss_debug_fp64_peak_scratch_bytes(void) {
 
 extern "C" int gss_debug_fp64_peak(int mode, int iters, void* scratch, double* flops_out, void* stream) {
     using namespace gss;
-    GSS_REQUIRE(scratch && iters > 0 && (mode == 0 || mode == 1), GSS_ERR_ARG, "gss_debug_fp64_peak: bad arguments");
-    const int grid = num_sms() * 2, block = 512;              // 32 warps per SM
+    GSS_REQUIRE(scratch && iters > 0 && mode >= 0 && mode <= 3, GSS_ERR_ARG, "gss_debug_fp64_peak: bad arguments");
+    // 32 warps per SM (modes 0-2) or the EM kernel's 16 warps per SM (mode 3 = mode 2 at that occupancy)
+    const int block = mode == 3 ? 256 : 512, grid = num_sms() * 2;
     cudaStream_t st = (cudaStream_t)stream;
     if (mode == 0) fp64_dfma_probe_kernel<<<grid, block, 0, st>>>((double*)scratch, iters);
-    else fp64_dmma_probe_kernel<<<grid, block, 0, st>>>((double*)scratch, iters);
+    else if (mode == 1) fp64_dmma_probe_kernel<<<grid, block, 0, st>>>((double*)scratch, iters);
+    else fp64_dfma3_probe_kernel<<<grid, block, 0, st>>>((double*)scratch, iters);
     GSS_LAUNCH_CHECK("fp64_probe_kernel");
     if (flops_out)
         *flops_out = mode == 0 ? 2.0 * 8 * iters * (double)grid * block
-                               : 2.0 * 8 * 256 * iters * (double)grid * (block / 32);
+                   : mode == 1 ? 2.0 * 8 * 256 * iters * (double)grid * (block / 32)
+                               : (2.0 * 40 + 8) * iters * (double)grid * block;
     return GSS_OK;
 }
