@@ -578,12 +578,14 @@ class Enhancer:
                 X_hat=ops.unpack_ft_to_tf(X)[0].cpu().numpy(), x_hat=x_hat.cpu().numpy())
         return _from_device(x_hat, was_np, np.float64)
 
-    def prepare_observation(self, obs, ex_array_activity, speaker_id, ex=None, pin=True):
+    def prepare_observation(self, obs, ex_array_activity, speaker_id, ex=None, pin=True, upload=True):
         """Host-side half of `enhance_observation` for one utterance, safe to run in a loader
-        thread while the GPU works on the previous batch: float32 samples in page-locked memory
-        (so the later host->device copy is asynchronous), frame-level activity (a4: boolean
-        bookkeeping, database.py:409-472), target index and context frames.  core.py:514-547."""
+        thread while the GPU works on the previous batch: float32 samples in page-locked memory,
+        uploaded on a side stream (`upload`; the enhancement waits on the recorded event, so the
+        host->device copy overlaps the kernels of the previous batch), frame-level activity (a4:
+        boolean bookkeeping, database.py:409-472), target index and context frames.  core.py:514-547."""
         on_device = isinstance(obs, torch.Tensor) and obs.is_cuda
+        ready = host = None
         if on_device:
             x = obs.to(torch.float32)
         else:
@@ -591,6 +593,15 @@ class Enhancer:
             x = x.to(torch.float32)
             if pin and torch.cuda.is_available() and not x.is_pinned():
                 x = x.pin_memory()
+            if upload and x.is_pinned():
+                side = self.__dict__.get('_upload_stream')
+                if side is None or side.device.index != torch.cuda.current_device():
+                    side = self.__dict__['_upload_stream'] = torch.cuda.Stream()
+                with torch.cuda.stream(side):
+                    host = x                                    # keep the pinned source alive until the copy is done
+                    x = host.to(_device(), non_blocking=True)
+                    ready = torch.cuda.Event()
+                    ready.record(side)
         assert x.ndim == 2, x.shape
         N = int(x.shape[-1])
         frames = ops.stft_frames(N, self.stft_size, self.stft_shift, self.stft_fading)
@@ -600,7 +611,7 @@ class Enhancer:
         sc = ec = 0
         if self.bf_drop_context and ex is not None:
             sc, ec = self._context_frames(ex)
-        return dict(obs=x, N=N, frames=frames, activity_freq=af.astype(np.uint8), K=len(ex_array_activity),
+        return dict(obs=x, ready=ready, host_source=host, N=N, frames=frames, activity_freq=af.astype(np.uint8), K=len(ex_array_activity),
                     target=tuple(ex_array_activity.keys()).index(speaker_id), start_ctx=sc, end_ctx=min(ec, frames),
                     numpy=not isinstance(obs, torch.Tensor))
 
@@ -616,8 +627,12 @@ class Enhancer:
         frames = [p['frames'] for p in preps]
         pad = (self.stft_size - self.stft_shift) if self.stft_fading else 0
         x = torch.zeros((B, D, max(Ns)), dtype=torch.float32, device=dev)
+        cur = torch.cuda.current_stream()
         for b, p in enumerate(preps):
             assert p['obs'].shape[0] == D and p['K'] == K, (p['obs'].shape, D, p['K'], K)
+            if p.get('ready') is not None:                      # uploaded by the loader thread on its side stream
+                cur.wait_event(p['ready'])
+                p['obs'].record_stream(cur)
             x[b, :, :Ns[b]].copy_(p['obs'], non_blocking=True)
         Y = ops.stft(x, self.stft_size, self.stft_shift, self.stft_fading)              # (B,F,D,Tmax)
         Tmax = Y.shape[3]

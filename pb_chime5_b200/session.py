@@ -157,6 +157,14 @@ class SessionScheduler:
         errors = []
         stop = threading.Event()
         prepare = getattr(self.enhancer, 'prepare_observation', None)
+        cuda_device = None
+        if prepare is not None:
+            try:
+                import torch
+                if torch.cuda.is_available():
+                    cuda_device = torch.cuda.current_device()
+            except ImportError:
+                pass
 
         def put(q, item):
             """blocking put that gives up when the run was stopped (no thread left hanging on a full queue)"""
@@ -170,6 +178,9 @@ class SessionScheduler:
 
         def loader():
             try:
+                if cuda_device is not None:
+                    import torch
+                    torch.cuda.set_device(cuda_device)        # the current device is thread-local
                 for b in batch_iter:
                     if stop.is_set():
                         return
