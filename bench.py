@@ -214,7 +214,8 @@ def measure_fp64_peak(torch, _lib):
     scratch = torch.empty(int(dl.gss_debug_fp64_peak_scratch_bytes()), dtype=torch.uint8, device='cuda')
     stream = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
     out = {}
-    for name, mode in (('dfma', 0), ('dmma', 1), ('dfma_3operand', 2), ('dfma_3operand_16warps', 3)):
+    for name, mode in (('dfma', 0), ('dmma', 1), ('dfma_3operand', 2), ('dfma_3operand_16warps', 3),
+                       ('dfma_3operand_8warps', 4), ('dfma_3operand_4warps', 5)):
         fl = ctypes.c_double(0.0)
         _lib.check(dl.gss_debug_fp64_peak(mode, 2000, ctypes.c_void_p(scratch.data_ptr()), ctypes.byref(fl), stream), dl)
         best = 0.0

@@ -582,7 +582,37 @@ __global__ void __launch_bounds__(NT, MINB) cacgmm_em_kernel(const CacgmmParams 
             }
             __syncthreads();
             // ---- flush: reduce over the M-phase groups in fixed order (deterministic) ----
-            if constexpr (C::NG <= 4) {
+            if constexpr (C::NG >= 2 && C::NG <= 4 && size_t(C::NG - 1) * K * C::NP * sizeof(cd) <= C::YS_BYTES) {
+                // groups 1.. park their partial blocks in slabs inside the (now dead) frame tile, group 0
+                // goes straight to the accumulator; then every thread sums its entries in fixed order
+                cd* slab = reinterpret_cast<cd*>(ys_raw);
+                if (m_active) {
+#pragma unroll
+                    for (int a = 0; a < 4; ++a) {
+                        const int d = r0 + (a >> 1), e = c0 + (a & 1);
+                        if (e <= d) {
+#pragma unroll
+                            for (int k = 0; k < K; ++k) {
+                                if (m_g == 0) {
+                                    cd* dst = &acc_sm[k * C::NP + tri(d, e)];
+                                    if (s0 == 0) *dst = macc[a][k];
+                                    else { cd v = *dst; v.x += macc[a][k].x; v.y += macc[a][k].y; *dst = v; }
+                                } else {
+                                    slab[((m_g - 1) * K + k) * C::NP + tri(d, e)] = macc[a][k];
+                                }
+                            }
+                        }
+                    }
+                }
+                __syncthreads();
+                for (int e = tid; e < K * C::NP; e += NT) {
+                    cd v = acc_sm[e];
+#pragma unroll
+                    for (int g = 1; g < C::NG; ++g) { const cd u = slab[(g - 1) * K * C::NP + e]; v.x += u.x; v.y += u.y; }
+                    acc_sm[e] = v;
+                }
+                __syncthreads();
+            } else if constexpr (C::NG <= 4) {
                 for (int g = 0; g < C::NG; ++g) {
                     if (m_active && m_g == g) {
 #pragma unroll

@@ -73,9 +73,9 @@ extern "C" size_t gss_debug_fp64_peak_scratch_bytes(void) {
 
 extern "C" int gss_debug_fp64_peak(int mode, int iters, void* scratch, double* flops_out, void* stream) {
     using namespace gss;
-    GSS_REQUIRE(scratch && iters > 0 && mode >= 0 && mode <= 3, GSS_ERR_ARG, "gss_debug_fp64_peak: bad arguments");
-    // 32 warps per SM (modes 0-2) or the EM kernel's 16 warps per SM (mode 3 = mode 2 at that occupancy)
-    const int block = mode == 3 ? 256 : 512, grid = num_sms() * 2;
+    GSS_REQUIRE(scratch && iters > 0 && mode >= 0 && mode <= 5, GSS_ERR_ARG, "gss_debug_fp64_peak: bad arguments");
+    // 32 warps per SM (modes 0-2); mode 2 at 16 (mode 3: the EM kernel's occupancy), 8 (mode 4) and 4 (mode 5) warps per SM
+    const int block = mode == 3 ? 256 : mode == 4 ? 128 : mode == 5 ? 64 : 512, grid = num_sms() * 2;
     cudaStream_t st = (cudaStream_t)stream;
     if (mode == 0) fp64_dfma_probe_kernel<<<grid, block, 0, st>>>((double*)scratch, iters);
     else if (mode == 1) fp64_dmma_probe_kernel<<<grid, block, 0, st>>>((double*)scratch, iters);

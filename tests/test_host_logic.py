@@ -12,6 +12,8 @@ import numpy as np
 import pytest
 
 from oracle import gss_oracle as oracle
+import torch
+
 from pb_chime5_b200 import _lib, core, sharding, synth
 
 ROOT = Path(__file__).resolve().parent.parent
@@ -291,3 +293,68 @@ def test_cfg4_sized_work_list_shards_evenly():
     assert sorted(j for b in batches for j in b) == list(range(len(mine)))
     padded = sum(len(b) * lengths[mine[b[0]]] for b in batches)
     assert sum(lengths[i] for i in mine) / padded > 0.97        # length bucketing keeps the padding below 3 %
+
+
+def test_check_info_severity_and_stage_words():
+    """status words: one row per stage; failure codes raise the reference's exception types, the
+    WPE 'singular' word only warns (nara_wpe falls back to lstsq silently); host lists or tensors."""
+    import warnings
+    from pb_chime5_b200 import ops
+    ok = [[0, 0], [0, 0], [0, 0]]
+    ops.check_info(ok, ('wpe', 'cacgmm', 'beamform'))
+    with pytest.raises(ValueError, match='beamform.*utterance 1, frequency 7'):
+        ops.check_info([[0, 0], [0, 0], [0, _lib.INFO_NOT_POSDEF | (7 << 8)]], ('wpe', 'cacgmm', 'beamform'))
+    with pytest.raises(AssertionError, match='non-finite SNR'):
+        ops.check_info([0, _lib.INFO_NONFINITE], 'beamform')
+    with pytest.raises(RuntimeError, match='did not converge'):
+        ops.check_info(torch.tensor([_lib.INFO_NO_CONVERGE | (3 << 8)]), 'cacgmm')
+    # a singular WPE word in stage 0 does not hide the failure of stage 2, and alone it only warns
+    with pytest.raises(ValueError):
+        ops.check_info([[_lib.INFO_SINGULAR | (400 << 8)], [0], [_lib.INFO_NOT_POSDEF | (2 << 8)]], ('wpe', 'cacgmm', 'beamform'))
+    with warnings.catch_warnings(record=True) as w:
+        warnings.simplefilter('always')
+        ops.check_info([[_lib.INFO_SINGULAR | (5 << 8), 0], [0, 0]], ('wpe', 'cacgmm'))
+    assert len(w) == 1 and 'singular normal equations' in str(w[0].message) and 'frequency 5' in str(w[0].message)
+    ops.check_info(None, 'x')
+
+
+def test_parse_beamformer_dsl_strings():
+    """the string grammar of get_bf_vector (beamformer_wrapper.py:142-224) and its error behaviour"""
+    from pb_chime5_b200.extraction import parse_beamformer
+    assert parse_beamformer('mvdr_souden') == dict(rank1=None, core='mvdr_souden', ban=False, channel=0)
+    assert parse_beamformer('rank1_gev+mvdr_souden+ban') == dict(rank1='rank1_gev', core='mvdr_souden', ban=True, channel=0)
+    assert parse_beamformer('rank1_pca+wmwf')['rank1'] == 'rank1_pca'
+    assert parse_beamformer('scaled_gev_atf+mvdr+ban') == dict(rank1=None, core='scaled_gev_atf+mvdr', ban=True, channel=0)
+    assert parse_beamformer('ch13+ban') == dict(rank1=None, core='ch', ban=True, channel=13)
+    for bad in ('music', 'rank1_gev+pca', 'mvdr', 'ban'):
+        with pytest.raises(ValueError):
+            parse_beamformer(bad)
+    with pytest.raises(AssertionError):
+        parse_beamformer('lcmv_souden')
+    with pytest.raises(AssertionError):
+        parse_beamformer(3)
+    from pb_chime5_b200 import core
+    assert core.Beamformer('wmwf+ban', None)._dsl_type() == (0x100 | 2 | (1 << 6), 0)
+    assert core.Beamformer('mvdrSouden_ban', None)._dsl() is None
+    with pytest.raises(NotImplementedError):
+        core.Beamformer('nonsense', None)._dsl()
+
+
+def test_launcher_environment_detection(monkeypatch):
+    """rank / world / local rank from torchrun, mpiexec (Open MPI, MPICH) and srun variables"""
+    for v in ('RANK', 'WORLD_SIZE', 'LOCAL_RANK', 'OMPI_COMM_WORLD_RANK', 'OMPI_COMM_WORLD_SIZE',
+              'OMPI_COMM_WORLD_LOCAL_RANK', 'PMI_RANK', 'PMI_SIZE', 'MPI_LOCALRANKID', 'SLURM_PROCID',
+              'SLURM_NTASKS', 'SLURM_LOCALID', 'PMIX_RANK', 'OMPI_UNIVERSE_SIZE'):
+        monkeypatch.delenv(v, raising=False)
+    assert sharding.rank_world() == (0, 1) and sharding.local_rank() == 0
+    monkeypatch.setenv('OMPI_COMM_WORLD_RANK', '3'); monkeypatch.setenv('OMPI_COMM_WORLD_SIZE', '8')
+    monkeypatch.setenv('OMPI_COMM_WORLD_LOCAL_RANK', '3')
+    assert sharding.rank_world() == (3, 8) and sharding.local_rank() == 3
+    monkeypatch.setenv('RANK', '1'); monkeypatch.setenv('WORLD_SIZE', '2'); monkeypatch.setenv('LOCAL_RANK', '1')
+    assert sharding.rank_world() == (1, 2) and sharding.local_rank() == 1          # torchrun wins
+    for v in ('RANK', 'WORLD_SIZE', 'LOCAL_RANK', 'OMPI_COMM_WORLD_RANK', 'OMPI_COMM_WORLD_SIZE', 'OMPI_COMM_WORLD_LOCAL_RANK'):
+        monkeypatch.delenv(v)
+    monkeypatch.setenv('SLURM_PROCID', '5'); monkeypatch.setenv('SLURM_NTASKS', '6'); monkeypatch.setenv('SLURM_LOCALID', '1')
+    assert sharding.rank_world() == (5, 6) and sharding.local_rank() == 1
+    q = sharding.WorkQueue(4)
+    assert list(q) == [0, 1, 2, 3] and q.next() is None and q.taken == 4
