@@ -368,6 +368,15 @@ def parity_check(torch, ops, enh, obs_dtf, act, c, bins=(0, 256)):
     if wpe_kw:
         m32 = drop(oracle.gss_posteriors(ref['Obs'].astype(np.complex64).astype(np.complex128), a, c['em_iterations']))
         out['oracle_self_sensitivity_c64_handoff'] = float(np.abs(m32 - ref['masks']).max())
+        # the same bins with the float64 hand-off (gss_enhance_c64_ex, GSS_ENHANCE_F64_HANDOFF): end to end
+        # against the float64 oracle with no allowance (reference channel: each side's own arg-max on these bins)
+        ref2 = oracle.enhance_stft(O64, a, 0, wpe=wpe_kw, gss_iterations=c['em_iterations'], bf=c['bf'],
+                                   start_context_frames=ctx, end_context_frames=ctx)
+        Xf, pf = ops.enhance(obs_dtf[:, :, bins].contiguous()[None], act[None], iv(0), iv(ctx), iv(ctx),
+                             wpe=(c['taps'], c['delay'], c['wpe_iterations'], 0), em_iterations=c['em_iterations'],
+                             bf=c['bf'], handoff='f64')
+        out['float64_handoff'] = {'mask_max_abs': float(np.abs(drop(pf[0].cpu().numpy().astype(np.float64)) - ref2['masks']).max()),
+                                  'xhat_rel': rel(Xf[0].cpu().numpy(), ref2['X_hat'])}
     st = out['stagewise']
     out['ok'] = bool(st['wpe_rel'] < 1e-4 and st['mask_max_abs'] < 1e-4 and st['xhat_rel'] < 1e-4 and out['xhat_rel'] < 1e-4
                      and out['mask_max_abs'] < max(1e-4, 2 * out.get('oracle_self_sensitivity_c64_handoff', 0.0)))

@@ -62,6 +62,8 @@ typedef struct { float re, im; } gss_c64;
 #define GSS_OP_ISTFT          5
 #define GSS_OP_ENHANCE        6
 #define GSS_OP_BF_VECTOR      7
+#define GSS_OP_CACGMM_C128     8
+#define GSS_OP_ENHANCE_F64     9
 
 #define GSS_BF_MVDR_SOUDEN_BAN 0  /* core.py:249-258 */
 #define GSS_BF_GEV_BAN         1  /* beamforming_wrapper.py:192-208 */
@@ -187,15 +189,27 @@ int gss_wpe_c64(const gss_c64* Y, gss_c64* X, int taps, int delay, int iteration
  * stats      device int32[4] or NULL, ACCUMULATED (caller zeroes): [0] bins processed, [1] bins that
  *            ended the call on the float64 list, [2] float64 re-do builds (bins x iterations).
  * A caller that sees stats[1] / stats[0] > 1/2 (reverberant, low-noise recordings) should pass
- * GSS_WPE_GRAM_F64 for the following batches: pb_chime5_b200.core.WPE does exactly that. */
+ * GSS_WPE_GRAM_F64 for the following batches: pb_chime5_b200.core.WPE does exactly that.
+ * X_c128   optional (B,F,D,T) complex128 copy of the result before it is rounded to complex64: the
+ *            "float64 hand-off" to gss_cacgmm_c128 (the reference hands complex128 from block to block). */
 #define GSS_WPE_GRAM_AUTO    -1
 #define GSS_WPE_GRAM_F64      0
 #define GSS_WPE_GRAM_I8       1
 #define GSS_WPE_GRAM_I8_REDO  2
 int gss_wpe_c64_ex(const gss_c64* Y, gss_c64* X, int taps, int delay, int iterations,
                    int psd_context, int B, int F, int D, int T, const int* T_per_utt,
-                   int gram_mode, double i8_tau, int* stats,
+                   int gram_mode, double i8_tau, int* stats, double* X_c128,
                    int* info, void* ws, size_t ws_bytes, void* stream);
+
+/* gss_cacgmm_c64 on complex128 observations (B,F,D,T) -- the float64 hand-off from gss_wpe_c64_ex
+ * (X_c128).  Always the runtime-shape kernel (csrc/cacgmm_generic.cu); same results as gss_cacgmm_c64
+ * would give on unrounded input.  Workspace: gss_workspace_bytes(GSS_OP_CACGMM_C128, ...). */
+int gss_cacgmm_c128(const double* Y, const uint8_t* activity, float* posterior,
+                    int iterations, int iterations_post,
+                    double affiliation_eps, double eigenvalue_floor,
+                    int B, int F, int D, int T, int K, int T_act, const int* T_per_utt,
+                    double* weight_out, double* logdet_out, double* covariance_out,
+                    int* info, void* ws, size_t ws_bytes, void* stream);
 
 /* ---- whole STFT-domain hot path in one call (Enhancer.enhance_observation without the
  * transforms, core.py:524-564), reference layouts on both sides ---------------------
@@ -212,6 +226,20 @@ int gss_enhance_c64(const gss_c64* Obs, const uint8_t* activity, const int* targ
                     int bf_type, int bf_arg, int postfilter,
                     int B, int F, int D, int T, int K, int T_act,
                     int* info, void* ws, size_t ws_bytes, void* stream);
+
+/* The same with options.  flags: GSS_ENHANCE_F64_HANDOFF -- the dereverberated spectrum goes to the
+ * EM in complex128 (as in the reference) instead of complex64: removes the only end-to-end difference
+ * to the float64 chain that is not rounding of an output at the price of the
+ * slower runtime-shape EM kernel.  Workspace: gss_workspace_bytes(GSS_OP_ENHANCE_F64, ...). */
+#define GSS_ENHANCE_F64_HANDOFF  1
+int gss_enhance_c64_ex(const gss_c64* Obs, const uint8_t* activity, const int* target_index,
+                       const int* start_ctx, const int* end_ctx, const int* T_per_utt,
+                       gss_c64* X_hat, float* posterior,
+                       int wpe_taps, int wpe_delay, int wpe_iterations, int wpe_psd_context,
+                       int em_iterations, int em_iterations_post,
+                       int bf_type, int bf_arg, int postfilter, int flags,
+                       int B, int F, int D, int T, int K, int T_act,
+                       int* info, void* ws, size_t ws_bytes, void* stream);
 
 /* ---- STFT / iSTFT (Enhancer.stft / .istft, core.py:305-321 -> nara_wpe.utils)
  * x (B,D,N) f32 -> Y (B,F,D,T) c64 bin-major, F = size/2+1,

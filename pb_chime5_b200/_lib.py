@@ -25,7 +25,8 @@ INFO_NONFINITE = 2
 INFO_NO_CONVERGE = 3
 INFO_SINGULAR = 4
 
-OP_WEIGHTED_COV, OP_CACGMM, OP_BEAMFORM, OP_WPE, OP_STFT, OP_ISTFT, OP_ENHANCE, OP_BF_VECTOR = range(8)
+(OP_WEIGHTED_COV, OP_CACGMM, OP_BEAMFORM, OP_WPE, OP_STFT, OP_ISTFT, OP_ENHANCE, OP_BF_VECTOR,
+ OP_CACGMM_C128, OP_ENHANCE_F64) = range(10)
 
 BF_TYPES = {'mvdrSouden_ban': 0, 'gev_ban': 1, 'ch': 2, 'sum': 3, 'mvdrSouden': 4, 'gev': 5}
 POSTFILTERS = {None: 0, 'mask_mul': 1}
@@ -57,7 +58,10 @@ _SIGNATURES = {
                                              _i, _i, _i, _i, _i, _p, _p, _p, _p, _p, _sz, _p]),
     'gss_bf_vector_c128': (_i, [_p, _p, _p, _i, _i, _i, _i, _d, _i, _i, _i, _i, _i, _p, _p, _p, _sz, _p]),
     'gss_wpe_c64': (_i, [_p, _p, _i, _i, _i, _i, _i, _i, _i, _i, _p, _p, _p, _sz, _p]),
-    'gss_wpe_c64_ex': (_i, [_p, _p, _i, _i, _i, _i, _i, _i, _i, _i, _p, _i, _d, _p, _p, _p, _sz, _p]),
+    'gss_wpe_c64_ex': (_i, [_p, _p, _i, _i, _i, _i, _i, _i, _i, _i, _p, _i, _d, _p, _p, _p, _p, _sz, _p]),
+    'gss_cacgmm_c128': (_i, [_p, _p, _p, _i, _i, _d, _d, _i, _i, _i, _i, _i, _i, _p,
+                             _p, _p, _p, _p, _p, _sz, _p]),
+    'gss_enhance_c64_ex': (_i, [_p] * 8 + [_i] * 16 + [_p, _p, _sz, _p]),
     'gss_enhance_c64': (_i, [_p] * 8 + [_i] * 15 + [_p, _p, _sz, _p]),
     'gss_stft_f32': (_i, [_p, _p, _i, _i, _i, _i, _i, _i, _p, _sz, _p]),
     'gss_istft_f32': (_i, [_p, _p, _i, _i, _i, _i, _i, _p, _sz, _p]),

@@ -133,12 +133,13 @@ class WPE:
             return st, 'f64', False
         return st, None, True
 
-    def _run(self, Y, frames=None, info=None):
-        """Y (B,F,D,T) complex64 on the device -> same shape.  frames: valid frames per utterance."""
+    def _run(self, Y, frames=None, info=None, return_f64=False):
+        """Y (B,F,D,T) complex64 on the device -> same shape.  frames: valid frames per utterance.
+        return_f64: (X complex64, X complex128 before the rounding)."""
         st, mode, want_stats = self._policy()
         stats = torch.zeros(4, dtype=torch.int32, device=Y.device) if want_stats else None
         X = ops.wpe(Y, self.taps, self.delay, self.iterations, self.psd_context, frames=frames,
-                    gram_mode=mode, stats=stats, info=info)
+                    gram_mode=mode, stats=stats, info=info, return_f64=return_f64)
         if stats is not None:
             host = torch.empty(4, dtype=torch.int32, pin_memory=True)
             host.copy_(stats, non_blocking=True)
@@ -393,6 +394,13 @@ class Enhancer:
     # ---- the device-resident hot path ---------------------------------------
     STAGES = ('wpe', 'cacgmm', 'beamform')
 
+    # Hand-off between WPE and the EM: 'c64' (default; the blocks exchange complex64 tensors in HBM) or
+    # 'f64' (the EM sees the dereverberated spectrum unrounded, as in the float64 reference -- removes
+    # the one end-to-end difference that is not the rounding of an output, DESIGN.md section 3, at the
+    # price of the slower runtime-shape EM kernel).  Not a dataclass field: the constructor mirrors the
+    # reference's.  Set `enhancer.handoff = 'f64'` or GSS_HANDOFF=f64.
+    handoff = os.environ.get('GSS_HANDOFF', 'c64')
+
     def enhance_stft_batch(self, Y, activity_freq, target_index, start_ctx, end_ctx, return_masks=False,
                            frames=None, info=None):
         """Y (B,F,D,T) complex64 CUDA (bin-major), activity_freq (B,K,T_act) uint8,
@@ -407,9 +415,15 @@ class Enhancer:
         own = info is None
         if own:
             info = ops.new_info(Y.shape[0], Y.device, stages=3)
+        assert self.handoff in ('c64', 'f64'), self.handoff
+        Y_em = Y
         if self.wpe_block is not None:
-            Y = self.wpe_block._run(Y, frames, info=info[0])
-        post = self.gss_block._run(Y, activity_freq, frames, info=info[1])
+            if self.handoff == 'f64' and self.wpe_block.iterations > 0:
+                Y, Y_em = self.wpe_block._run(Y, frames, info=info[0], return_f64=True)
+            else:
+                Y = Y_em = self.wpe_block._run(Y, frames, info=info[0])
+        post = self.gss_block._run(Y_em, activity_freq, frames, info=info[1])
+        del Y_em
         if not self.bf_drop_context:
             start_ctx = end_ctx = None
         X = self.bf_block._run_from_posterior(Y, post, target_index, start_ctx, end_ctx, frames, info=info[2])

@@ -47,6 +47,7 @@ size_t istft_ws_bytes(int B, int T, int size);
 size_t enhance_ws_bytes(int B, int F, int D, int T, int K, int L);
 size_t cacgmm_generic_ws_bytes(int B, int F, int D, int K);
 size_t bf_vector_ws_bytes(int B, int F, int D);
+size_t enhance_f64_ws_bytes(int B, int F, int D, int T, int K, int L);
 bool cacgmm_fast_path(int D, int K);
 size_t cacgmm_ws_bytes(int B, int F, int D, int K) {
     if (!cacgmm_fast_path(D, K)) return cacgmm_generic_ws_bytes(B, F, D, K);
@@ -66,10 +67,12 @@ int gss_workspace_bytes(int op, int B, int F, int D, int T, int K, int L, size_t
         case GSS_OP_WEIGHTED_COV: n = weighted_cov_ws_bytes(B, F, D, K); break;
         case GSS_OP_CACGMM: n = cacgmm_ws_bytes(B, F, D, K); break;
         case GSS_OP_BEAMFORM: n = beamform_ws_bytes(B, F, D); break;
-        case GSS_OP_WPE: n = wpe_ws_bytes(B < 4 ? B : 4, F, D, T, L); break;   // utterances are processed in chunks
+        case GSS_OP_WPE: n = wpe_ws_bytes(B < 8 ? B : 8, F, D, T, L); break;   // utterances are processed in chunks of up to 8
         case GSS_OP_STFT: n = 256; break;
         case GSS_OP_ISTFT: n = istft_ws_bytes(B, T, F > 1 ? 2 * (F - 1) : 2); break;   // F = size/2 + 1
         case GSS_OP_BF_VECTOR: n = bf_vector_ws_bytes(B, F, D); break;
+        case GSS_OP_CACGMM_C128: n = cacgmm_generic_ws_bytes(B, F, D, K); break;
+        case GSS_OP_ENHANCE_F64: n = enhance_f64_ws_bytes(B, F, D, T, K, L); break;
         case GSS_OP_ENHANCE: n = enhance_ws_bytes(B, F, D, T, K, L); break;   // L = WPE taps (0: no WPE)
         default: return fail(GSS_ERR_ARG, "gss_workspace_bytes: unknown op %d", op);
     }

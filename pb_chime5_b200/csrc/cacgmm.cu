@@ -58,7 +58,7 @@ constexpr size_t cmax(size_t a, size_t b) { return a > b ? a : b; }
 
 // cacgmm_generic.cu: any D < 35, K < 20 (runtime shapes)
 size_t cacgmm_generic_ws_bytes(int B, int F, int D, int K);
-int cacgmm_generic_launch(const float2* Y, const uint8_t* activity, const int* Tper, float* posterior,
+int cacgmm_generic_launch(const void* Y, int y_is_c128, const uint8_t* activity, const int* Tper, float* posterior,
                           double* weight_out, double* logdet_out, double* cov_out, int* info,
                           int B, int F, int D, int T, int K, int T_act, int iterations, int iterations_post,
                           double eps, double floor_, void* ws, size_t ws_bytes, cudaStream_t st);
@@ -956,7 +956,7 @@ extern "C" int gss_cacgmm_c64(const gss_c64* Y, const uint8_t* activity, float* 
     GSS_REQUIRE(T_act >= T, GSS_ERR_ARG, "activity has %d frames, observation %d (cacgmm.py:216-218)", T_act, T);
     if (B == 0 || F == 0) return GSS_OK;
     if (!cacgmm_fast_path(D, K))          // K > 6 or D > 24: runtime-shape kernel (cacgmm_generic.cu), same results
-        return cacgmm_generic_launch((const float2*)Y, activity, T_per_utt, posterior, weight_out, logdet_out,
+        return cacgmm_generic_launch(Y, 0, activity, T_per_utt, posterior, weight_out, logdet_out,
                                      covariance_out, info, B, F, D, T, K, T_act, iterations, iterations_post,
                                      affiliation_eps, eigenvalue_floor, ws, ws_bytes, (cudaStream_t)stream);
     CacgmmParams p;
@@ -977,5 +977,27 @@ extern "C" int gss_cacgmm_c64(const gss_c64* Y, const uint8_t* activity, float* 
     p.iterations = iterations; p.iterations_post = iterations_post;
     p.eps = affiliation_eps; p.floor_ = eigenvalue_floor;
     return cacgmm_dispatch(p, K, (cudaStream_t)stream);
+}
+
+// complex128 observations (the float64 hand-off from WPE): always the runtime-shape kernel
+extern "C" int gss_cacgmm_c128(const double* Y, const uint8_t* activity, float* posterior,
+                               int iterations, int iterations_post,
+                               double affiliation_eps, double eigenvalue_floor,
+                               int B, int F, int D, int T, int K, int T_act, const int* T_per_utt,
+                               double* weight_out, double* logdet_out, double* covariance_out,
+                               int* info, void* ws, size_t ws_bytes, void* stream) {
+    using namespace gss;
+    GSS_REQUIRE(Y && activity && posterior, GSS_ERR_ARG, "gss_cacgmm_c128: null pointer");
+    GSS_REQUIRE(B >= 0 && F >= 0 && T > 0, GSS_ERR_ARG, "gss_cacgmm_c128: bad dims B=%d F=%d T=%d", B, F, T);
+    GSS_REQUIRE(D > 1 && D < 35, GSS_ERR_ARG, "Channels: %d, sure? (cacgmm.py:196,248)", D);
+    GSS_REQUIRE(K > 1 && K < 20, GSS_ERR_ARG, "num_classes: %d, sure? (cacgmm.py:212,247)", K);
+    GSS_REQUIRE(iterations > 0, GSS_ERR_ARG, "iterations=%d must be > 0 (cacgmm.py:199)", iterations);
+    GSS_REQUIRE(iterations_post >= 1, GSS_ERR_UNSUPPORTED,
+                "iterations_post=%d: the reference raises TypeError for 0 (core.py:198-202)", iterations_post);
+    GSS_REQUIRE(T_act >= T, GSS_ERR_ARG, "activity has %d frames, observation %d (cacgmm.py:216-218)", T_act, T);
+    if (B == 0 || F == 0) return GSS_OK;
+    return cacgmm_generic_launch(Y, 1, activity, T_per_utt, posterior, weight_out, logdet_out, covariance_out, info,
+                                 B, F, D, T, K, T_act, iterations, iterations_post, affiliation_eps, eigenvalue_floor,
+                                 ws, ws_bytes, (cudaStream_t)stream);
 }
 #endif  // GSS_EM_PART == 0

@@ -13,7 +13,7 @@
 namespace gss {
 
 struct CacgmmGenericParams {
-    const float2* Y;          // (B,F,D,T)
+    const void* Y;            // (B,F,D,T) complex64 or complex128 (template parameter of the kernel)
     const uint8_t* activity;  // (B,K,T_act)
     const int* Tper;
     float* posterior;         // (B,F,K,T)
@@ -34,23 +34,26 @@ constexpr int GEN_TT = 256;          // frames per tile = threads (E phase: thre
 constexpr int GEN_KC = 4;            // classes per E-phase sweep over the pairs
 constexpr int GEN_KMAX = 19;
 
-__host__ __device__ inline size_t gen_smem_bytes(int D, int K) {
-    const size_t tile = (size_t)D * (GEN_TT + 1) * sizeof(float2);            // y tile [D][TT+1]
+__host__ __device__ inline size_t gen_smem_bytes(int D, int K, size_t elem) {
+    const size_t tile = (size_t)D * (GEN_TT + 1) * elem;                      // y tile [D][TT+1]
     const size_t wt = (size_t)K * GEN_TT * sizeof(double);                    // w tile [K][TT]
     const size_t jac = (size_t)3 * D * (D + 1) * sizeof(cd);                  // A, V, T of the Jacobi phase
     const size_t a = tile + wt;
     return (a > jac ? a : jac) + (size_t)(4 * 32 + 8 + 8 * GEN_KMAX + 64) * sizeof(double) + 20 * sizeof(JacobiRot) + 64;
 }
 
-__global__ void __launch_bounds__(GEN_NT, 2) cacgmm_em_generic_kernel(const CacgmmGenericParams p) {
+// InT = float2 (complex64 observations, the normal hand-off between the blocks) or double2
+// (complex128: the float64 hand-off of gss_enhance_c64_ex / gss_cacgmm_c128)
+template <typename InT>
+__global__ void __launch_bounds__(GEN_NT, sizeof(InT) == 8 ? 2 : 1) cacgmm_em_generic_kernel(const CacgmmGenericParams p) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int D = p.D, K = p.K, Ts = p.T;
     const int NP = D * (D + 1) / 2;
     const int JLD = D + 1;
     const int YP = GEN_TT + 1;                                                 // tile row pitch (elements)
-    const size_t tile_b = (size_t)D * YP * sizeof(float2), wt_b = (size_t)K * GEN_TT * sizeof(double);
+    const size_t tile_b = (size_t)D * YP * sizeof(InT), wt_b = (size_t)K * GEN_TT * sizeof(double);
     const size_t jac_b = (size_t)3 * D * JLD * sizeof(cd);
-    float2* ytile = reinterpret_cast<float2*>(smem_raw);                      // [D][YP]
+    InT* ytile = reinterpret_cast<InT*>(smem_raw);                            // [D][YP]
     double* wtile = reinterpret_cast<double*>(smem_raw + tile_b);             // [K][TT]
     unsigned char* sp = smem_raw + (tile_b + wt_b > jac_b ? tile_b + wt_b : jac_b);
     double* logdet_s = reinterpret_cast<double*>(sp);                         // [32]
@@ -65,7 +68,7 @@ __global__ void __launch_bounds__(GEN_NT, 2) cacgmm_em_generic_kernel(const Cacg
     const int bf = blockIdx.x;
     const int b = bf / p.F, f = bf - b * p.F;
     const int T = p.Tper ? min(max(p.Tper[b], 0), Ts) : Ts;
-    const float2* __restrict__ Yg = p.Y + (size_t)bf * D * Ts;
+    const InT* __restrict__ Yg = reinterpret_cast<const InT*>(p.Y) + (size_t)bf * D * Ts;
     if (T <= 0) {
         for (int i = tid; i < K * Ts; i += GEN_NT) p.posterior[(size_t)bf * K * Ts + i] = 0.f;
         return;
@@ -87,7 +90,9 @@ __global__ void __launch_bounds__(GEN_NT, 2) cacgmm_em_generic_kernel(const Cacg
             const int tn = min(GEN_TT, T - s0);
             for (int i = tid; i < D * GEN_TT; i += GEN_NT) {
                 const int d = i / GEN_TT, t = i - d * GEN_TT;
-                ytile[d * YP + t] = t < tn ? __ldg(&Yg[(size_t)d * Ts + s0 + t]) : make_float2(0.f, 0.f);
+                InT v; v.x = 0; v.y = 0;
+                if (t < tn) v = __ldg(&Yg[(size_t)d * Ts + s0 + t]);
+                ytile[d * YP + t] = v;
             }
             __syncthreads();
             // ---------------- E step: thread owns frame s0 + tid ----------------
@@ -95,7 +100,7 @@ __global__ void __launch_bounds__(GEN_NT, 2) cacgmm_em_generic_kernel(const Cacg
                 const int t = s0 + tid;
                 double n2 = 0.0;
                 for (int d = 0; d < D; ++d) {
-                    const float2 v = ytile[d * YP + tid];
+                    const InT v = ytile[d * YP + tid];
                     n2 = fma((double)v.x, (double)v.x, fma((double)v.y, (double)v.y, n2));
                 }
                 const double s = n2 > 0.0 ? 1.0 / n2 : 0.0;
@@ -111,10 +116,10 @@ __global__ void __launch_bounds__(GEN_NT, 2) cacgmm_em_generic_kernel(const Cacg
                         for (int c = 0; c < GEN_KC; ++c) qa[c] = 0.0;
                         int pr = 0;
                         for (int d = 0; d < D; ++d) {
-                            const float2 yd = ytile[d * YP + tid];
+                            const InT yd = ytile[d * YP + tid];
                             const double dr = yd.x, di = yd.y;
                             for (int e = 0; e <= d; ++e, ++pr) {
-                                const float2 ye = ytile[e * YP + tid];
+                                const InT ye = ytile[e * YP + tid];
                                 const double pre = fma(dr, (double)ye.x, di * (double)ye.y);
                                 const double pim = fma(di, (double)ye.x, -(dr * (double)ye.y));
 #pragma unroll
@@ -163,13 +168,13 @@ __global__ void __launch_bounds__(GEN_NT, 2) cacgmm_em_generic_kernel(const Cacg
                     int d = 0;
                     while ((d + 1) * (d + 2) / 2 <= pr) ++d;
                     const int e = pr - d * (d + 1) / 2;
-                    const float2* yd = ytile + d * YP;
-                    const float2* ye = ytile + e * YP;
+                    const InT* yd = ytile + d * YP;
+                    const InT* ye = ytile + e * YP;
                     const double* wk = wtile + k * GEN_TT;
                     double ar = 0.0, ai = 0.0, br = 0.0, bi = 0.0;                        // two chains
                     int t = 0;
                     for (; t + 1 < tn; t += 2) {
-                        const float2 a0 = yd[t], c0 = ye[t], a1 = yd[t + 1], c1 = ye[t + 1];
+                        const InT a0 = yd[t], c0 = ye[t], a1 = yd[t + 1], c1 = ye[t + 1];
                         const double w0 = wk[t], w1 = wk[t + 1];
                         ar = fma(w0, fma((double)a0.x, (double)c0.x, (double)a0.y * (double)c0.y), ar);
                         ai = fma(w0, fma((double)a0.y, (double)c0.x, -((double)a0.x * (double)c0.y)), ai);
@@ -177,7 +182,7 @@ __global__ void __launch_bounds__(GEN_NT, 2) cacgmm_em_generic_kernel(const Cacg
                         bi = fma(w1, fma((double)a1.y, (double)c1.x, -((double)a1.x * (double)c1.y)), bi);
                     }
                     if (t < tn) {
-                        const float2 a0 = yd[t], c0 = ye[t];
+                        const InT a0 = yd[t], c0 = ye[t];
                         const double w0 = wk[t];
                         ar = fma(w0, fma((double)a0.x, (double)c0.x, (double)a0.y * (double)c0.y), ar);
                         ai = fma(w0, fma((double)a0.y, (double)c0.x, -((double)a0.x * (double)c0.y)), ai);
@@ -308,7 +313,7 @@ size_t cacgmm_generic_ws_bytes(int B, int F, int D, int K) {
     return 2 * align_up(BF * K * NP * sizeof(cd)) + align_up(BF * K * D * (D + 1) * sizeof(cd));
 }
 
-int cacgmm_generic_launch(const float2* Y, const uint8_t* activity, const int* Tper, float* posterior,
+int cacgmm_generic_launch(const void* Y, int y_is_c128, const uint8_t* activity, const int* Tper, float* posterior,
                           double* weight_out, double* logdet_out, double* cov_out, int* info,
                           int B, int F, int D, int T, int K, int T_act, int iterations, int iterations_post,
                           double eps, double floor_, void* ws, size_t ws_bytes, cudaStream_t st) {
@@ -327,9 +332,16 @@ int cacgmm_generic_launch(const float2* Y, const uint8_t* activity, const int* T
     p.Vwarm = a.take<cd>(BF * K * D * (D + 1));
     p.B = B; p.F = F; p.D = D; p.K = K; p.T = T; p.T_act = T_act;
     p.iterations = iterations; p.iterations_post = iterations_post; p.eps = eps; p.floor_ = floor_;
-    const size_t smem = gen_smem_bytes(D, K);
-    GSS_CUDA(cudaFuncSetAttribute(cacgmm_em_generic_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    cacgmm_em_generic_kernel<<<B * F, GEN_NT, smem, st>>>(p);
+    if (y_is_c128) {
+        const size_t smem = gen_smem_bytes(D, K, sizeof(double2));
+        GSS_REQUIRE(smem <= 227 * 1024, GSS_ERR_UNSUPPORTED, "gss_cacgmm_c128: D=%d K=%d need %zu bytes of shared memory", D, K, smem);
+        GSS_CUDA(cudaFuncSetAttribute(cacgmm_em_generic_kernel<double2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        cacgmm_em_generic_kernel<double2><<<B * F, GEN_NT, smem, st>>>(p);
+    } else {
+        const size_t smem = gen_smem_bytes(D, K, sizeof(float2));
+        GSS_CUDA(cudaFuncSetAttribute(cacgmm_em_generic_kernel<float2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        cacgmm_em_generic_kernel<float2><<<B * F, GEN_NT, smem, st>>>(p);
+    }
     GSS_LAUNCH_CHECK("cacgmm_em_generic_kernel");
     return GSS_OK;
 }

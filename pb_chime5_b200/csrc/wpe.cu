@@ -522,7 +522,8 @@ __host__ __device__ constexpr int ap_gld(int MT) { return MT <= 3 ? 26 : 34; }  
 
 template <int MT>
 __global__ void __launch_bounds__(AP_NT) wpe_apply_kernel(const float2* __restrict__ Y, const cd* __restrict__ G,
-                                                          float2* __restrict__ X, double* __restrict__ power, WpeDims m) {
+                                                          float2* __restrict__ X, cd* __restrict__ X64,
+                                                          double* __restrict__ power, WpeDims m) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int D = m.D, DP4 = (D + 3) & ~3, hist = m.delay + m.L - 1;
     const int YW = AP_TN + hist, YLD = YW | 1;                         // odd row stride (float2)
@@ -602,11 +603,15 @@ __global__ void __launch_bounds__(AP_NT) wpe_apply_kernel(const float2* __restri
 #pragma unroll
             for (int h = 0; h < 2; ++h) {
                 const int t = t0 + tl + h;
-                if (d < D && t < m.T && t >= Tv) X[bf * (size_t)D * m.T + (size_t)d * m.T + t] = make_float2(0.f, 0.f);
+                if (d < D && t < m.T && t >= Tv) {
+                    X[bf * (size_t)D * m.T + (size_t)d * m.T + t] = make_float2(0.f, 0.f);
+                    if (X64) X64[bf * (size_t)D * m.T + (size_t)d * m.T + t] = cmake(0.0, 0.0);
+                }
                 if (d < D && t < Tv) {
                     const float2 y = Ys[d * YLD + hist + tl + h];
                     const double xr = (double)y.x - cre[mi][ni][h], xi = (double)y.y - cim[mi][ni][h];
                     X[bf * (size_t)D * m.T + (size_t)d * m.T + t] = make_float2((float)xr, (float)xi);
+                    if (X64) X64[bf * (size_t)D * m.T + (size_t)d * m.T + t] = cmake(xr, xi);   // unrounded copy (float64 hand-off)
                     pw[ni][h] += xr * xr + xi * xi;
                 }
             }
@@ -694,13 +699,13 @@ static int launch_backsub(const cd* Raug, const cd* Minv, cd* G, const WpeDims& 
 }
 
 template <int MT>
-static int launch_apply(const float2* Y, const cd* G, float2* X, double* power, const WpeDims& m, int BF, cudaStream_t st) {
+static int launch_apply(const float2* Y, const cd* G, float2* X, cd* X64, double* power, const WpeDims& m, int BF, cudaStream_t st) {
     const int DP4 = (m.D + 3) & ~3, hist = m.delay + m.L - 1, YLD = (AP_TN + hist) | 1;
     const size_t smem = (size_t)2 * DP4 * ap_gld(MT) * sizeof(cd) + (size_t)DP4 * YLD * sizeof(float2);
     auto kern = wpe_apply_kernel<MT>;
     GSS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     dim3 grid(BF, (m.T + AP_TN - 1) / AP_TN);
-    kern<<<grid, AP_NT, smem, st>>>(Y, G, X, power, m);
+    kern<<<grid, AP_NT, smem, st>>>(Y, G, X, X64, power, m);
     GSS_LAUNCH_CHECK("wpe_apply_kernel");
     return GSS_OK;
 }
@@ -709,7 +714,7 @@ static int launch_apply(const float2* Y, const cd* G, float2* X, double* power, 
 
 extern "C" int gss_wpe_c64_ex(const gss_c64* Y, gss_c64* X, int taps, int delay, int iterations, int psd_context,
                               int B, int F, int D, int T, const int* T_per_utt,
-                              int gram_mode, double i8_tau, int* stats,
+                              int gram_mode, double i8_tau, int* stats, double* X_c128,
                               int* info, void* ws, size_t ws_bytes, void* stream) {
     using namespace gss;
     GSS_REQUIRE(Y && X && Y != X, GSS_ERR_ARG, "gss_wpe_c64: null or aliased pointers");
@@ -725,6 +730,7 @@ extern "C" int gss_wpe_c64_ex(const gss_c64* Y, gss_c64* X, int taps, int delay,
     const double tau = i8_tau >= 0.0 ? i8_tau : 1e-3;
     cudaStream_t st = (cudaStream_t)stream;
     if (B == 0 || F == 0) return GSS_OK;
+    GSS_REQUIRE(!(X_c128 && iterations == 0), GSS_ERR_ARG, "gss_wpe_c64_ex: X_c128 needs iterations > 0");
     if (iterations == 0) {
         GSS_CUDA(cudaMemcpyAsync(X, Y, sizeof(float2) * (size_t)B * F * D * T, cudaMemcpyDeviceToDevice, st));
         return GSS_OK;
@@ -739,6 +745,7 @@ extern "C" int gss_wpe_c64_ex(const gss_c64* Y, gss_c64* X, int taps, int delay,
         const int BF = bn * F;
         const float2* Yc = (const float2*)Y + (size_t)b0 * F * D * T;
         float2* Xc = (float2*)X + (size_t)b0 * F * D * T;
+        cd* X64c = X_c128 ? reinterpret_cast<cd*>(X_c128) + (size_t)b0 * F * D * T : nullptr;
         int* infoc = info ? info + b0 : nullptr;
         WpeWs w = wpe_ws_layout(ws, bn, F, D, T, taps);
         // AUTO: INT8 tensor-core Gram where it is built, ill-conditioned bins re-done in float64
@@ -780,10 +787,11 @@ extern "C" int gss_wpe_c64_ex(const gss_c64* Y, gss_c64* X, int taps, int delay,
                 if (rc2) return rc2;
             }
             int rc;
-            if (D <= 8) rc = launch_apply<1>(Yc, w.G, Xc, w.power, m, BF, st);
-            else if (D <= 16) rc = launch_apply<2>(Yc, w.G, Xc, w.power, m, BF, st);
-            else if (D <= 24) rc = launch_apply<3>(Yc, w.G, Xc, w.power, m, BF, st);
-            else rc = launch_apply<4>(Yc, w.G, Xc, w.power, m, BF, st);
+            cd* x64 = (it + 1 == iterations) ? X64c : nullptr;      // only the last iteration's result is needed unrounded
+            if (D <= 8) rc = launch_apply<1>(Yc, w.G, Xc, x64, w.power, m, BF, st);
+            else if (D <= 16) rc = launch_apply<2>(Yc, w.G, Xc, x64, w.power, m, BF, st);
+            else if (D <= 24) rc = launch_apply<3>(Yc, w.G, Xc, x64, w.power, m, BF, st);
+            else rc = launch_apply<4>(Yc, w.G, Xc, x64, w.power, m, BF, st);
             if (rc) return rc;
         }
         if (stats && mode == GSS_WPE_GRAM_I8_REDO) { wpe_stats_kernel<<<1, 32, 0, st>>>(stats, w.redo_count, BF, 2); GSS_LAUNCH_CHECK("wpe_stats_kernel"); }
@@ -794,7 +802,7 @@ extern "C" int gss_wpe_c64_ex(const gss_c64* Y, gss_c64* X, int taps, int delay,
 extern "C" int gss_wpe_c64(const gss_c64* Y, gss_c64* X, int taps, int delay, int iterations, int psd_context,
                            int B, int F, int D, int T, const int* T_per_utt, int* info, void* ws, size_t ws_bytes, void* stream) {
     return gss_wpe_c64_ex(Y, X, taps, delay, iterations, psd_context, B, F, D, T, T_per_utt,
-                          GSS_WPE_GRAM_AUTO, -1.0, nullptr, info, ws, ws_bytes, stream);
+                          GSS_WPE_GRAM_AUTO, -1.0, nullptr, nullptr, info, ws, ws_bytes, stream);
 }
 
 // ---- developer API (libgss_dev.so only; include/gss_dev.h) ----------------------------------

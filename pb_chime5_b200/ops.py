@@ -163,7 +163,8 @@ def cacgmm(Y, activity, iterations, iterations_post=1, affiliation_eps=1e-10,
     """Guided CACGMM EM.  Y (B,F,D,T) c64, activity (B,K,T_act) bool/uint8 ->
     posterior (B,F,K,T) f32 [, model dict].  info: optional (B,) int32 device tensor; when given the
     status words are left for the caller to check (no host synchronisation here)."""
-    Y = _need(Y, torch.complex64, 4, 'Y')
+    f64 = isinstance(Y, torch.Tensor) and Y.dtype == torch.complex128      # float64 hand-off (runtime-shape kernel)
+    Y = _need(Y, torch.complex128 if f64 else torch.complex64, 4, 'Y')
     B, F, D, T = Y.shape
     if activity.dtype == torch.bool:
         activity = activity.to(torch.uint8)
@@ -179,8 +180,8 @@ def cacgmm(Y, activity, iterations, iterations_post=1, affiliation_eps=1e-10,
         weight = torch.empty((B, F, K), dtype=torch.float64, device=Y.device)
         logdet = torch.empty((B, F, K), dtype=torch.float64, device=Y.device)
         cov = torch.empty((B, F, K, D, D), dtype=torch.complex128, device=Y.device)
-    ws = workspace(_lib.workspace_bytes(_lib.OP_CACGMM, B, F, D, T, K, 0), Y.device)
-    _lib.check(_lib.lib().gss_cacgmm_c64(
+    ws = workspace(_lib.workspace_bytes(_lib.OP_CACGMM_C128 if f64 else _lib.OP_CACGMM, B, F, D, T, K, 0), Y.device)
+    _lib.check((_lib.lib().gss_cacgmm_c128 if f64 else _lib.lib().gss_cacgmm_c64)(
         _ptr(Y), _ptr(activity), _ptr(post), int(iterations), int(iterations_post),
         float(affiliation_eps), float(eigenvalue_floor), B, F, D, T, K, T_act, _ptr(_tper(frames, B, Y.device)),
         _ptr(weight), _ptr(logdet), _ptr(cov), _ptr(info), _ptr(ws), ws.numel(), _stream()))
@@ -257,19 +258,22 @@ def beamform_from_posterior(Y, posterior, target_index, start_ctx=None, end_ctx=
 
 
 def wpe(Y, taps=10, delay=3, iterations=3, psd_context=0, frames=None, gram_mode=None, i8_tau=None,
-        stats=None, info=None):
+        stats=None, info=None, return_f64=False):
     """Y (B,F,D,T) c64 -> dereverberated (B,F,D,T) c64.
 
     gram_mode: None / 'auto' (INT8 tensor-core correlation build where it is built, ill-conditioned
     bins re-done in float64), 'f64', 'i8' (diagnostics: no re-do), 'i8+redo'.  stats: optional int32[4]
     device tensor, accumulated by the call ([0] bins, [1] bins that ended on the float64 list,
     [2] float64 re-do builds).  info: optional (B,) int32 device tensor for GSS_INFO_SINGULAR words
-    (when omitted a fresh one is allocated and checked here, which synchronises)."""
+    (when omitted a fresh one is allocated and checked here, which synchronises).
+    return_f64: also return the result before its rounding to complex64, (B,F,D,T) complex128 -- the
+    float64 hand-off to `cacgmm` (which accepts complex128 observations)."""
     Y = _need(Y, torch.complex64, 4, 'Y')
     B, F, D, T = Y.shape
     if gram_mode not in _lib.WPE_GRAM_MODES:
         raise NotImplementedError(gram_mode)
     X = torch.empty_like(Y)
+    X64 = torch.empty(Y.shape, dtype=torch.complex128, device=Y.device) if return_f64 else None
     own_info = info is None
     if own_info:
         info = new_info(B, Y.device)
@@ -278,10 +282,10 @@ def wpe(Y, taps=10, delay=3, iterations=3, psd_context=0, frames=None, gram_mode
     _lib.check(_lib.lib().gss_wpe_c64_ex(_ptr(Y), _ptr(X), int(taps), int(delay), int(iterations),
                                          int(psd_context), B, F, D, T, _ptr(_tper(frames, B, Y.device)),
                                          _lib.WPE_GRAM_MODES[gram_mode], -1.0 if i8_tau is None else float(i8_tau),
-                                         _ptr(stats), _ptr(info), _ptr(ws), ws.numel(), _stream()))
+                                         _ptr(stats), _ptr(X64), _ptr(info), _ptr(ws), ws.numel(), _stream()))
     if own_info:
         check_info(info, 'wpe')
-    return X
+    return (X, X64) if return_f64 else X
 
 
 def stft_frames(N, size, shift, fading):
@@ -319,10 +323,12 @@ def istft(X, size=1024, shift=256, fading=True):
 
 def enhance(Obs, activity, target_index, start_ctx=None, end_ctx=None, frames=None, *, wpe=None,
             em_iterations=20, em_iterations_post=1, bf='mvdrSouden_ban', postfilter=None, bf_arg=0,
-            return_posterior=True):
+            return_posterior=True, handoff='c64'):
     """Whole STFT-domain hot path in ONE library call (gss_enhance_c64), reference layouts:
     Obs (B,D,T,F) c64, activity (B,K,T_act) -> X_hat (B,T,F) c64 [, posterior (B,K,T,F) f32].
-    wpe: None or (taps, delay, iterations, psd_context)."""
+    wpe: None or (taps, delay, iterations, psd_context).  handoff: 'c64' (default: the blocks exchange
+    complex64 tensors) or 'f64' (gss_enhance_c64_ex with GSS_ENHANCE_F64_HANDOFF: the dereverberated spectrum
+    reaches the EM unrounded, as in the float64 reference; slower runtime-shape EM kernel)."""
     Obs = _need(Obs, torch.complex64, 4, 'Obs')
     B, D, T, F = Obs.shape
     if activity.dtype == torch.bool:
@@ -340,11 +346,13 @@ def enhance(Obs, activity, target_index, start_ctx=None, end_ctx=None, frames=No
     X = torch.empty((B, T, F), dtype=torch.complex64, device=Obs.device)
     post = torch.empty((B, K, T, F), dtype=torch.float32, device=Obs.device) if return_posterior else None
     info = torch.zeros((max(B, 1),), dtype=torch.int32, device=Obs.device)
-    ws = workspace(_lib.workspace_bytes(_lib.OP_ENHANCE, B, F, D, T, K, int(taps)), Obs.device)
-    _lib.check(_lib.lib().gss_enhance_c64(
+    assert handoff in ('c64', 'f64'), handoff
+    f64 = handoff == 'f64'
+    ws = workspace(_lib.workspace_bytes(_lib.OP_ENHANCE_F64 if f64 else _lib.OP_ENHANCE, B, F, D, T, K, int(taps)), Obs.device)
+    _lib.check(_lib.lib().gss_enhance_c64_ex(
         _ptr(Obs), _ptr(activity), _ptr(ti), _ptr(sc), _ptr(ec), _ptr(_tper(frames, B, Obs.device)),
         _ptr(X), _ptr(post), int(taps), int(delay), int(its), int(ctx), int(em_iterations), int(em_iterations_post),
-        _lib.BF_TYPES[bf], int(bf_arg), _lib.POSTFILTERS[postfilter], B, F, D, T, K, T_act,
+        _lib.BF_TYPES[bf], int(bf_arg), _lib.POSTFILTERS[postfilter], 1 if f64 else 0, B, F, D, T, K, T_act,
         _ptr(info), _ptr(ws), ws.numel(), _stream()))
     check_info(info, 'enhance')
     return (X, post) if return_posterior else X
