@@ -19,7 +19,7 @@ def built_library():
     """The C-ABI library is a build artefact (git-ignored): build it once if it is missing so
     that the CPU suite can check the exported surface on a fresh checkout."""
     lib = ROOT / 'pb_chime5_b200' / 'csrc' / 'libgss.so'
-    if not lib.exists():
+    if not lib.exists() or not (lib.parent / 'libgss_dev.so').exists():
         import subprocess
         subprocess.run(['bash', str(ROOT / 'pb_chime5_b200' / 'csrc' / 'build.sh')], check=True)
     return lib
