@@ -82,7 +82,7 @@ def activity_time_to_frequency(time_activity, stft_window_length, stft_shift, st
         n = a.shape[-1]
     count = (n - stft_window_length) // stft_shift + 1
     # any() over each frame through a cumulative count (no (T, size) gather)
-    c = np.concatenate([np.zeros(a.shape[:-1] + (1,), dtype=np.int64), np.cumsum(a, axis=-1)], axis=-1)
+    c = np.concatenate([np.zeros(a.shape[:-1] + (1,), dtype=np.int32), np.cumsum(a, axis=-1, dtype=np.int32)], axis=-1)
     starts = stft_shift * np.arange(count)
     return (c[..., starts + stft_window_length] - c[..., starts]) > 0
 
@@ -603,10 +603,15 @@ class Enhancer:
         if on_device:
             x = obs.to(torch.float32)
         else:
-            x = obs if isinstance(obs, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(obs))
-            x = x.to(torch.float32)
+            x = obs if isinstance(obs, torch.Tensor) else torch.from_numpy(np.asarray(obs))
             if pin and torch.cuda.is_available() and not x.is_pinned():
-                x = x.pin_memory()
+                # page-locked staging buffers are recycled (page-locking 50 MB per utterance costs more
+                # than the copy and serialises the ranks of a node in the kernel): a buffer is free again
+                # once the upload that read it has completed
+                src, x = x, self._pinned_buffer(tuple(x.shape))
+                x.copy_(src)                                    # also converts float64 -> float32
+            else:
+                x = x.to(torch.float32).contiguous()
             if upload and x.is_pinned():
                 side = self.__dict__.get('_upload_stream')
                 if side is None or side.device.index != torch.cuda.current_device():
@@ -625,9 +630,35 @@ class Enhancer:
         sc = ec = 0
         if self.bf_drop_context and ex is not None:
             sc, ec = self._context_frames(ex)
+        if host is not None:
+            self.__dict__['_pinned_busy'].append((ready, host))
         return dict(obs=x, ready=ready, host_source=host, N=N, frames=frames, activity_freq=af.astype(np.uint8), K=len(ex_array_activity),
                     target=tuple(ex_array_activity.keys()).index(speaker_id), start_ctx=sc, end_ctx=min(ec, frames),
                     numpy=not isinstance(obs, torch.Tensor))
+
+    def _pinned_buffer(self, shape):
+        """a float32 page-locked tensor of `shape` from the recycling pool (loader thread only)"""
+        n = int(np.prod(shape))
+        busy = self.__dict__.setdefault('_pinned_busy', [])     # (event, flat buffer) of uploads in flight
+        free = self.__dict__.setdefault('_pinned_free', [])
+        still = []
+        for ev, buf in busy:
+            if ev is None or ev.query():
+                free.append(buf._base if buf._base is not None else buf)
+            else:
+                still.append((ev, buf))
+        self.__dict__['_pinned_busy'] = still
+        best = None
+        for i, b in enumerate(free):
+            if b.numel() >= n and (best is None or b.numel() < free[best].numel()):
+                best = i
+        if best is None:
+            flat = torch.empty(max(n, 1), dtype=torch.float32, pin_memory=True)
+        else:
+            flat = free.pop(best)
+        while len(free) > 32:                                   # bound the pool
+            free.pop(0)
+        return flat[:n].view(shape)
 
     def enhance_prepared_batch(self, preps):
         """B prepared utterances of different lengths in ONE pass of the hot path: zero padded to
