@@ -435,7 +435,8 @@ def session_summary(reports, counts, n_items, items, sec, world):
             'segment_audio_s_per_s': seg_s / sec, 'utterance_audio_s_per_s': utt_s / sec,
             'real_time_factor_segments': sec / seg_s,
             'per_rank': {'done': [r.done for r in reports], 'batches': [r.batches for r in reports],
-                         'busy_s': busy, 'wall_s': [r.seconds for r in reports]},
+                         'busy_s': busy, 'wall_s': [r.seconds for r in reports],
+                         'starved_s': [r.wait_seconds for r in reports], 'loader_s': [r.load_seconds for r in reports]},
             'busy_imbalance_max_over_min': (max(busy) / min(busy)) if min(busy) > 0 else None,
             'padding_efficiency': valid / padded if padded else None,
             'h2d_bytes': sum(cn['h2d'] for cn in counts), 'd2h_bytes': sum(cn['d2h'] for cn in counts),

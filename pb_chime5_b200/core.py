@@ -613,9 +613,10 @@ class Enhancer:
             else:
                 x = x.to(torch.float32).contiguous()
             if upload and x.is_pinned():
-                side = self.__dict__.get('_upload_stream')
-                if side is None or side.device.index != torch.cuda.current_device():
-                    side = self.__dict__['_upload_stream'] = torch.cuda.Stream()
+                with self._pool_lock():
+                    side = self.__dict__.get('_upload_stream')
+                    if side is None or side.device.index != torch.cuda.current_device():
+                        side = self.__dict__['_upload_stream'] = torch.cuda.Stream()
                 with torch.cuda.stream(side):
                     host = x                                    # keep the pinned source alive until the copy is done
                     x = host.to(_device(), non_blocking=True)
@@ -631,33 +632,43 @@ class Enhancer:
         if self.bf_drop_context and ex is not None:
             sc, ec = self._context_frames(ex)
         if host is not None:
-            self.__dict__['_pinned_busy'].append((ready, host))
+            with self._pool_lock():
+                self.__dict__.setdefault('_pinned_busy', []).append((ready, host))
         return dict(obs=x, ready=ready, host_source=host, N=N, frames=frames, activity_freq=af.astype(np.uint8), K=len(ex_array_activity),
                     target=tuple(ex_array_activity.keys()).index(speaker_id), start_ctx=sc, end_ctx=min(ec, frames),
                     numpy=not isinstance(obs, torch.Tensor))
 
+    def _pool_lock(self):
+        lock = self.__dict__.get('_pinned_lock')
+        if lock is None:
+            import threading
+            lock = self.__dict__.setdefault('_pinned_lock', threading.Lock())
+        return lock
+
     def _pinned_buffer(self, shape):
-        """a float32 page-locked tensor of `shape` from the recycling pool (loader thread only)"""
+        """a float32 page-locked tensor of `shape` from the recycling pool (loader threads)"""
         n = int(np.prod(shape))
-        busy = self.__dict__.setdefault('_pinned_busy', [])     # (event, flat buffer) of uploads in flight
-        free = self.__dict__.setdefault('_pinned_free', [])
-        still = []
-        for ev, buf in busy:
-            if ev is None or ev.query():
-                free.append(buf._base if buf._base is not None else buf)
-            else:
-                still.append((ev, buf))
-        self.__dict__['_pinned_busy'] = still
-        best = None
-        for i, b in enumerate(free):
-            if b.numel() >= n and (best is None or b.numel() < free[best].numel()):
-                best = i
-        if best is None:
+        flat = None
+        with self._pool_lock():
+            busy = self.__dict__.setdefault('_pinned_busy', [])     # (event, buffer) of uploads in flight
+            free = self.__dict__.setdefault('_pinned_free', [])
+            still = []
+            for ev, buf in busy:
+                if ev is None or ev.query():
+                    free.append(buf._base if buf._base is not None else buf)
+                else:
+                    still.append((ev, buf))
+            busy[:] = still
+            best = None
+            for i, b in enumerate(free):
+                if b.numel() >= n and (best is None or b.numel() < free[best].numel()):
+                    best = i
+            if best is not None:
+                flat = free.pop(best)
+            while len(free) > 48:                                   # bound the pool
+                free.pop(0)
+        if flat is None:
             flat = torch.empty(max(n, 1), dtype=torch.float32, pin_memory=True)
-        else:
-            flat = free.pop(best)
-        while len(free) > 32:                                   # bound the pool
-            free.pop(0)
         return flat[:n].view(shape)
 
     def enhance_prepared_batch(self, preps):

@@ -876,7 +876,10 @@ static int launch_cacgmm_dk(const CacgmmParams& p, cudaStream_t st) {
 #endif
     constexpr int NT = GSS_EM_NT;
     using C = CacgmmCfg<DP, K, NT>;
-    auto kern = cacgmm_em_kernel<DP, K, NT, GSS_EM_MINB>;
+    // two CTAs per SM (128 registers) while two of them fit the shared memory; the K = 7, 8 variants of the
+    // large channel counts need one CTA per SM (and get its 255 registers)
+    constexpr int MINB = (2 * (C::SMEM + 1024) <= 228 * 1024) ? GSS_EM_MINB : 1;      // 228 KB per SM, 1 KB reserved per CTA
+    auto kern = cacgmm_em_kernel<DP, K, NT, MINB>;
     GSS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM));
     kern<<<p.B * p.F, NT, C::SMEM, st>>>(p);
     GSS_LAUNCH_CHECK("cacgmm_em_kernel");
@@ -891,9 +894,11 @@ int launch_cacgmm_d(const CacgmmParams& p, int K, cudaStream_t st) {
         case 3: return launch_cacgmm_dk<DP, 3>(p, st);
         case 4: return launch_cacgmm_dk<DP, 4>(p, st);
         case 6: return launch_cacgmm_dk<DP, 6>(p, st);
+        case 7: return launch_cacgmm_dk<DP, 7>(p, st);
+        case 8: return launch_cacgmm_dk<DP, 8>(p, st);
 #endif
         case 5: return launch_cacgmm_dk<DP, 5>(p, st);
-        default: return fail(GSS_ERR_UNSUPPORTED, "gss_cacgmm_c64: K=%d not built (built: 2..6)", K);
+        default: return fail(GSS_ERR_UNSUPPORTED, "gss_cacgmm_c64: K=%d not built (built: 2..8)", K);
     }
 }
 
@@ -916,10 +921,10 @@ GSS_DP_PART2
 #endif
 
 #if GSS_EM_PART == 0
-// the fused kernel is built for these padded channel counts and K = 2..6; any D runs on the next
+// the fused kernel is built for these padded channel counts and K = 2..8; any D runs on the next
 // built size (padded channels are zero rows; the matrix phase uses the true D)
 bool cacgmm_fast_path(int D, int K) {
-    if (K < 2 || K > 6) return false;
+    if (K < 2 || K > 8) return false;
 #define GSS_CASE(dp) if (D <= dp) return true;
     GSS_DP_LIST
 #undef GSS_CASE

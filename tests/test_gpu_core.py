@@ -118,9 +118,10 @@ def test_gss_channel_and_class_counts(D, K):
 
 @pytest.mark.parametrize('D,K', [(13, 3), (14, 4), (18, 5), (22, 6),          # fused kernel on the next padded size
                                  (26, 3), (29, 4), (33, 3), (34, 2),          # D > 24: runtime-shape kernel
-                                 (8, 7), (6, 12), (4, 19), (24, 8)])          # K > 6: runtime-shape kernel
+                                 (8, 7), (24, 8),                             # K = 7, 8: fused kernel, one CTA per SM at D = 24
+                                 (6, 12), (4, 19), (24, 9)])                  # K > 8: runtime-shape kernel
 def test_gss_every_shape_the_reference_accepts(D, K):
-    """cacgmm.py:247-248 accepts K < 20 and D < 35: every such shape runs (fused kernel for K <= 6 and
+    """cacgmm.py:247-248 accepts K < 20 and D < 35: every such shape runs (fused kernel for K <= 8 and
     D <= 24 on the next instantiated padded size, `cacgmm_generic.cu` otherwise) and meets the bar."""
     Obs, act = synth.make_utterance(500 + 7 * D + K, D=D, T=300, F=2, K=K)
     got, ref = _gss_both(Obs, act, 8)
