@@ -406,15 +406,15 @@ def run_session_job(torch, enh, items, c, rank, world, schedule, device_resident
         a, b = it['offset'], it['offset'] + it['total']
         acts = {spk: act[k, a:b] for k, spk in enumerate(speakers)}
         acts['Noise'] = act[-1, a:b]
-        counts['h2d'] += obs.shape[0] * it['total'] * 4
         return obs[:, a:b], acts, ex['speaker_id']
 
     def finish(ex, x):
         it = ex['item']
         return x[..., it['context']:it['context'] + it['num_samples_orig']]
 
-    def sink(ex, x):
-        counts['d2h'] += (ex['item']['total'] - 0) * 4
+    def sink(ex, x):                                   # writer thread (single): byte counts per finished utterance
+        counts['h2d'] += c['D'] * ex['item']['total'] * 4      # float32 samples of the segment, all channels
+        counts['d2h'] += ex['item']['total'] * 4               # enhanced float32 samples of the segment (before the context cut)
         counts['utt_samples'] += x.shape[-1]
 
     sched = SessionScheduler(enh, load, None, finish, batch_size=c['batch_size'], window=64,

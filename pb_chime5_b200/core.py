@@ -706,7 +706,10 @@ class Enhancer:
         if all(not p['numpy'] for p in preps):
             ops.check_info(info, self.STAGES)
             return [x_hat[b, :n_out[b]] for b in range(B)]
-        host = torch.empty(x_hat.shape, dtype=x_hat.dtype, pin_memory=True)
+        flat = self.__dict__.get('_out_host')                    # grow-only page-locked result buffer; the returned
+        if flat is None or flat.numel() < x_hat.numel():         # arrays are float64 copies, so it can be reused
+            flat = self.__dict__['_out_host'] = torch.empty(x_hat.numel(), dtype=x_hat.dtype, pin_memory=True)
+        host = flat[:x_hat.numel()].view(x_hat.shape)
         host.copy_(x_hat, non_blocking=True)
         info_h = info.cpu()                                   # synchronises: results and status words landed
         torch.cuda.current_stream().synchronize()
