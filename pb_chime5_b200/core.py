@@ -81,6 +81,15 @@ def activity_time_to_frequency(time_activity, stft_window_length, stft_shift, st
             a = np.pad(a, [(0, 0)] * (a.ndim - 1) + [(0, extra)], mode='constant')
         n = a.shape[-1]
     count = (n - stft_window_length) // stft_shift + 1
+    if stft_window_length % stft_shift == 0 and n % stft_shift == 0:
+        # a frame is size / shift consecutive hops: any() per hop (one pass over the samples), then the OR
+        # of the hops of each frame -- ~4x faster than the cumulative count below on 30 s segments
+        hops = a.reshape(a.shape[:-1] + (n // stft_shift, stft_shift)).any(axis=-1)
+        r = stft_window_length // stft_shift
+        out = hops[..., 0:count].copy()
+        for j in range(1, r):
+            out |= hops[..., j:j + count]
+        return out
     # any() over each frame through a cumulative count (no (T, size) gather)
     c = np.concatenate([np.zeros(a.shape[:-1] + (1,), dtype=np.int32), np.cumsum(a, axis=-1, dtype=np.int32)], axis=-1)
     starts = stft_shift * np.arange(count)
@@ -609,7 +618,9 @@ class Enhancer:
                 # than the copy and serialises the ranks of a node in the kernel): a buffer is free again
                 # once the upload that read it has completed
                 src, x = x, self._pinned_buffer(tuple(x.shape))
-                x.copy_(src)                                    # also converts float64 -> float32
+                # NumPy copies a strided (D, N) cut row by row with memcpy (4x faster than torch's
+                # strided copy_) and converts float64 -> float32 on the way
+                np.copyto(x.numpy(), src.numpy(), casting='same_kind')
             else:
                 x = x.to(torch.float32).contiguous()
             if upload and x.is_pinned():
