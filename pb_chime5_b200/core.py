@@ -679,7 +679,10 @@ class Enhancer:
             while len(free) > 48:                                   # bound the pool
                 free.pop(0)
         if flat is None:
-            flat = torch.empty(max(n, 1), dtype=torch.float32, pin_memory=True)
+            # capacities in steps of 16 MB: segments of similar length share buffers (page-locking is the
+            # expensive part -- ~20 ms per 50 MB and serialised across the processes of a node)
+            cap = -(-max(n, 1) // (1 << 22)) * (1 << 22)
+            flat = torch.empty(cap, dtype=torch.float32, pin_memory=True)
         return flat[:n].view(shape)
 
     def enhance_prepared_batch(self, preps):
