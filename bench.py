@@ -418,7 +418,7 @@ def run_session_job(torch, enh, items, c, rank, world, schedule, device_resident
         counts['utt_samples'] += x.shape[-1]
 
     sched = SessionScheduler(enh, load, None, finish, batch_size=c['batch_size'], window=64,
-                             max_batch_samples=c['batch_size'] * 52 * 16000, prefetch=2, skip_existing=False,
+                             max_batch_samples=c['batch_size'] * 52 * 16000, prefetch=1, skip_existing=False,
                              strict=True, sink_fn=sink)
     rep = run_distributed(sched, exs, schedule)
     return rep, counts, bases

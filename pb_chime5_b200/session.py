@@ -161,6 +161,7 @@ class SessionScheduler:
         to_write = queue_mod.Queue(maxsize=4 * self.batch_size)
         errors = []
         stop = threading.Event()
+        slots = threading.Semaphore(max(1, self.prefetch))
         prepare = getattr(self.enhancer, 'prepare_observation', None)
         cuda_device = None
         if prepare is not None:
@@ -205,8 +206,17 @@ class SessionScheduler:
                 if self.loader_threads > 1:
                     from concurrent.futures import ThreadPoolExecutor
                     pool = ThreadPoolExecutor(self.loader_threads, initializer=bind_device)
-                for b in batch_iter:
+                while True:
+                    # a batch is claimed (from the shared work queue, when there is one) only when a
+                    # prefetch slot is free: at most `prefetch` claimed batches wait behind the one in
+                    # flight, so the tail of a task-farmed job stays short
+                    while not slots.acquire(timeout=0.1):
+                        if stop.is_set():
+                            return
                     if stop.is_set():
+                        return
+                    b = next(batch_iter, None)
+                    if b is None:
                         return
                     tl = time.perf_counter()
                     items = list(pool.map(load_one, b)) if pool is not None else [load_one(i) for i in b]
@@ -245,6 +255,7 @@ class SessionScheduler:
                 report.wait_seconds += time.perf_counter() - tw
                 if items is None:
                     break
+                slots.release()
                 report.batches += 1
                 good = []
                 for ex, data, err in items:
