@@ -38,6 +38,23 @@ def test_blocks_numpy_in_numpy_out(golden_dir):
     assert Xt.is_cuda and rel_err(Xt.cpu().numpy(), g['X_mvdr_ban']) < 1e-4
 
 
+def test_beamformer_mask_layouts(golden_dir):
+    """Masks per channel (D,T,F) / (1,D,T,F) are reduced with the median over the channels, the
+    observation may come as (1,D,T,F) (beamforming_wrapper.py:20-35)."""
+    g = np.load(golden_dir / 'gss_d8_k4.npz')
+    Obs = g['Obs'].astype(np.complex128)
+    rng = np.random.default_rng(5)
+    bf = core.Beamformer('mvdrSouden_ban', None)
+    for C in (3, 4):                                      # odd / even channel count of the mask stack
+        tm = np.clip(g['target_mask'][None] + 0.2 * rng.standard_normal((C,) + g['target_mask'].shape), 1e-3, 1)
+        dm = np.clip(g['distortion_mask'][None] + 0.2 * rng.standard_normal((C,) + g['distortion_mask'].shape), 1e-3, 1)
+        want = bf(Obs, np.median(tm, axis=0), np.median(dm, axis=0))
+        assert rel_err(bf(Obs, tm, dm), want) < 1e-5          # float32 masks: median-then-round vs round-then-median
+        assert rel_err(bf(Obs[None], tm[None], dm[None]), want) < 1e-5
+    with pytest.raises(AssertionError):
+        bf(Obs, g['target_mask'][:-1], g['distortion_mask'][:-1])
+
+
 def test_wpe_block_layouts():
     Obs, _ = synth.make_utterance(21, D=6, T=160, F=4, K=3)
     Obs[:, 3:, :] += 0.5 * Obs[:, :-3, :]
