@@ -121,6 +121,33 @@ def test_istft_perfect_reconstruction():
     assert np.abs(xr[:, :5000] - x).max() < 1e-12
 
 
+def test_stft_istft_match_scipy():
+    """nara_wpe.utils.stft / istft are un-vendored (core.py:305-321 only calls them): the oracle's
+    periodic Blackman analysis window, the framing and the biorthogonal synthesis are cross-checked
+    against scipy.signal's independent STFT / least-squares ISTFT."""
+    import warnings
+    import scipy.signal
+    size, shift = 1024, 256
+    rng = np.random.default_rng(3)
+    x = rng.standard_normal(5000)
+    w = scipy.signal.get_window('blackman', size, fftbins=True)
+    xp = np.pad(x, (size - shift, size - shift))
+    xp = np.pad(xp, (0, (-(len(xp) - size)) % shift))
+    _, _, Z = scipy.signal.stft(xp, window=w, nperseg=size, noverlap=size - shift, boundary=None, padded=False)
+    X = oracle.stft(x, size, shift, fading=True)
+    assert X.shape == Z.T.shape
+    np.testing.assert_allclose(X, Z.T * w.sum(), atol=1e-11)
+    # synthesis on spectra that are NOT the STFT of a signal (so that nothing cancels)
+    S = rng.standard_normal((23, 513)) + 1j * rng.standard_normal((23, 513))
+    S[:, 0] = S[:, 0].real
+    S[:, -1] = S[:, -1].real
+    with warnings.catch_warnings():
+        warnings.simplefilter('ignore')                   # NOLA warning: the edges are cut below
+        _, xr = scipy.signal.istft((S / w.sum()).T, window=w, nperseg=size, noverlap=size - shift, boundary=False)
+    xo = oracle.istft(S, size, shift, fading=True)
+    np.testing.assert_allclose(xo, xr[size - shift:size - shift + len(xo)], atol=1e-13)
+
+
 def test_wpe_normal_equations():
     """WPE is unpinned by the reference tree; self-check: the filter of the last
     iteration satisfies its normal equations and the output is Y - G^H Yt."""
