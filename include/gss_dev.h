@@ -29,7 +29,9 @@ int gss_debug_mstep_i8(const gss_c64* Y, const double* w, double* Phi, int B, in
  * launches one kernel of dependent-chain-free FP64 work on every SM; mode 0 = DFMA with two
  * loop-invariant operands (the textbook peak), 1 = DMMA (mma.sync.m8n8k4.f64), 2 = DFMA with three
  * distinct register operands per instruction (the operand pattern of the EM kernel's M phase:
- * 40 accumulators += weight[k] * product[i]), 3 / 4 / 5 = mode 2 at 16 (the EM kernel's occupancy) / 8 / 4 warps per SM.  *flops_out (host) = floating point operations of the launch.
+ * 40 accumulators += weight[k] * product[i]), 3 / 4 / 5 = mode 2 at 16 (the EM kernel's occupancy) / 8 / 4 warps per SM,
+ * 6 / 7 = mode 3 with 8 float32 operands widened per 40 DFMA by F2F / by integer bit manipulation (DFMA flops only).
+ * *flops_out (host) = floating point operations of the launch.
  * scratch: device, >= gss_debug_fp64_peak_scratch_bytes() bytes.  Time it with events on `stream`. */
 size_t gss_debug_fp64_peak_scratch_bytes(void);
 int gss_debug_fp64_peak(int mode, int iters, void* scratch, double* flops_out, void* stream);

@@ -48,6 +48,42 @@ __global__ void __launch_bounds__(512) fp64_dfma3_probe_kernel(double* out, int 
     out[(size_t)blockIdx.x * blockDim.x + threadIdx.x] = s;
 }
 
+// modes 6 / 7: the M-phase pattern -- 8 float32 operands widened per 40 DFMA -- with the hardware
+// conversion (F2F.F64.F32) and with integer bit manipulation (exact for normal numbers and zero)
+__device__ __forceinline__ double widen_bits(float f) {
+    const unsigned x = __float_as_uint(f), m = x & 0x7fffffffu;
+    const unsigned hi = (x & 0x80000000u) | (m ? (m >> 3) + 0x38000000u : 0u);
+    return __hiloint2double((int)hi, (int)(x << 29));
+}
+template <bool BITS>
+__global__ void __launch_bounds__(512) fp64_widen_probe_kernel(double* out, int iters) {
+    double acc[8][5], w[5];
+    float f[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        f[i] = 1.0f + threadIdx.x * 1e-4f + i * 1e-2f;
+#pragma unroll
+        for (int k = 0; k < 5; ++k) acc[i][k] = i + k;
+    }
+#pragma unroll
+    for (int k = 0; k < 5; ++k) w[k] = 1e-9 * (k + 1);
+    for (int it = 0; it < iters; ++it) {
+        double p[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) { f[i] += 1e-6f; p[i] = BITS ? widen_bits(f[i]) : (double)f[i]; }
+#pragma unroll
+        for (int k = 0; k < 5; ++k)
+#pragma unroll
+            for (int i = 0; i < 8; ++i) acc[i][k] = fma(w[k], p[i], acc[i][k]);
+    }
+    double s = 0;
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int k = 0; k < 5; ++k) s += acc[i][k];
+    out[(size_t)blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+
 __global__ void __launch_bounds__(512) fp64_dmma_probe_kernel(double* out, int iters) {
     double c[8][2];
 #pragma unroll
@@ -73,17 +109,20 @@ extern "C" size_t gss_debug_fp64_peak_scratch_bytes(void) {
 
 extern "C" int gss_debug_fp64_peak(int mode, int iters, void* scratch, double* flops_out, void* stream) {
     using namespace gss;
-    GSS_REQUIRE(scratch && iters > 0 && mode >= 0 && mode <= 5, GSS_ERR_ARG, "gss_debug_fp64_peak: bad arguments");
+    GSS_REQUIRE(scratch && iters > 0 && mode >= 0 && mode <= 7, GSS_ERR_ARG, "gss_debug_fp64_peak: bad arguments");
     // 32 warps per SM (modes 0-2); mode 2 at 16 (mode 3: the EM kernel's occupancy), 8 (mode 4) and 4 (mode 5) warps per SM
-    const int block = mode == 3 ? 256 : mode == 4 ? 128 : mode == 5 ? 64 : 512, grid = num_sms() * 2;
+    const int block = mode >= 6 ? 256 : mode == 3 ? 256 : mode == 4 ? 128 : mode == 5 ? 64 : 512, grid = num_sms() * 2;
     cudaStream_t st = (cudaStream_t)stream;
     if (mode == 0) fp64_dfma_probe_kernel<<<grid, block, 0, st>>>((double*)scratch, iters);
     else if (mode == 1) fp64_dmma_probe_kernel<<<grid, block, 0, st>>>((double*)scratch, iters);
+    else if (mode == 6) fp64_widen_probe_kernel<false><<<grid, block, 0, st>>>((double*)scratch, iters);
+    else if (mode == 7) fp64_widen_probe_kernel<true><<<grid, block, 0, st>>>((double*)scratch, iters);
     else fp64_dfma3_probe_kernel<<<grid, block, 0, st>>>((double*)scratch, iters);
     GSS_LAUNCH_CHECK("fp64_probe_kernel");
     if (flops_out)
         *flops_out = mode == 0 ? 2.0 * 8 * iters * (double)grid * block
                    : mode == 1 ? 2.0 * 8 * 256 * iters * (double)grid * (block / 32)
+                   : mode >= 6 ? 2.0 * 40 * iters * (double)grid * block
                                : (2.0 * 40 + 8) * iters * (double)grid * block;
     return GSS_OK;
 }
