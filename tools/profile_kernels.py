@@ -14,5 +14,8 @@ if which == 'em':
 elif which == 'wpe':
     for _ in range(2):
         X = ops.wpe(Y, 10, 2, 1)
+elif which == 'wpe_f64':                                      # float64 (DMMA, three-product) correlation build
+    for _ in range(2):
+        X = ops.wpe(Y, 10, 2, 1, gram_mode='f64')
 torch.cuda.synchronize()
 print('done')
