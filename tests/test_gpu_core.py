@@ -136,7 +136,7 @@ def test_gss_channel_and_class_counts(D, K):
 @pytest.mark.parametrize('D,K', [(13, 3), (14, 4), (18, 5), (22, 6),          # fused kernel on the next padded size
                                  (26, 3), (29, 4), (33, 3), (34, 2),          # D > 24: runtime-shape kernel
                                  (8, 7), (24, 8),                             # K = 7, 8: fused kernel, one CTA per SM at D = 24
-                                 (24, 6), (20, 8),                            # the largest shapes that still run two CTAs per SM / the first that do not
+                                 (24, 6), (20, 8),                            # just past the shared-memory limit of two CTAs per SM
                                  (6, 12), (4, 19), (24, 9)])                  # K > 8: runtime-shape kernel
 def test_gss_every_shape_the_reference_accepts(D, K):
     """cacgmm.py:247-248 accepts K < 20 and D < 35: every such shape runs (fused kernel for K <= 8 and
