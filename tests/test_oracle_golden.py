@@ -168,6 +168,37 @@ def test_wpe_normal_equations():
     assert np.all(Yt[:, :, 0] == 0)
 
 
+def test_wpe_matches_independent_weighted_least_squares():
+    """Second, independent statement of the published WPE iteration (Yoshioka & Nakatani 2012; what
+    nara_wpe.wpe_v8 implements): per bin, lambda_t = mean_d |x_d(t)|^2 floored at 1e-10 of its maximum,
+    G = argmin_G sum_t |y(t) - G^H ytilde(t)|^2 / lambda_t solved by QR/SVD least squares on the
+    whitened design matrix -- no Gram matrix, no normal equations -- written with explicit loops."""
+    rng = np.random.default_rng(11)
+    F, D, T, taps, delay = 2, 3, 160, 4, 2
+    Y = rng.standard_normal((F, D, T)) + 1j * rng.standard_normal((F, D, T))
+    Y[..., 3:] += 0.5 * Y[..., :-3]
+    Y[..., 7:] -= 0.3j * Y[..., :-7]
+    want = np.empty_like(Y)
+    for f in range(F):
+        x = Y[f].copy()
+        for _ in range(3):
+            lam = np.mean(np.abs(x) ** 2, axis=0)
+            lam = np.maximum(lam, 1e-10 * lam.max())
+            A = np.zeros((T, taps * D), complex)                  # row t: ytilde(t)^H / sqrt(lambda_t)
+            for t in range(T):
+                for k in range(taps):
+                    if t - delay - k >= 0:
+                        A[t, k * D:(k + 1) * D] = Y[f][:, t - delay - k].conj() / np.sqrt(lam[t])
+            B = Y[f].conj().T / np.sqrt(lam)[:, None]             # row t: y(t)^H / sqrt(lambda_t)
+            G = np.linalg.lstsq(A, B, rcond=None)[0]
+            x = Y[f] - np.stack([sum(G[k * D + e, :].conj() * Y[f][e, t - delay - k]
+                                     for k in range(taps) for e in range(D) if t - delay - k >= 0)
+                                 if t >= delay else np.zeros(D, complex) for t in range(T)], axis=1)
+        want[f] = x
+    got = oracle.wpe_bins(Y, taps=taps, delay=delay, iterations=3)
+    np.testing.assert_allclose(got, want, atol=1e-9)
+
+
 def test_bf_vector_dsl_oracle_matches_reference_fixture(golden_dir):
     """get_bf_vector DSL (beamformer_wrapper.py:108-227): the oracle restatement against vectors the
     unmodified reference produced (oracle/make_golden.py) -- same LAPACK calls, so bit for bit."""
