@@ -15,7 +15,6 @@ from __future__ import annotations
 
 import inspect
 from dataclasses import dataclass
-from functools import cached_property
 
 from . import core as _core
 from .core import GSS, WPE, Beamformer, JSON_PATH, samples_to_stft_frames  # noqa: F401  (re-exported API)
